@@ -1,0 +1,73 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_interp():
+    return load_golden("interp")
+
+
+@pytest.fixture(scope="session")
+def golden_calc():
+    return load_golden("calc")
+
+
+@pytest.fixture(scope="session")
+def golden_grids():
+    return load_golden("grids")
+
+
+@pytest.fixture(scope="session")
+def golden_setdata():
+    return load_golden("setdata")
+
+
+def assert_same(a, b, what=""):
+    """Bit-exact comparison treating NaN==NaN and checking inf signs."""
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if a.dtype == bool or b.dtype == bool:
+        assert np.array_equal(a, b), what
+        return
+    ok = (a == b) | (np.isnan(a) & np.isnan(b))
+    if not ok.all():
+        idx = np.argwhere(~ok)[0]
+        raise AssertionError(f"{what}: {np.count_nonzero(~ok)} mismatches, first at {tuple(idx)}: "
+                             f"{a[tuple(idx)]!r} vs {b[tuple(idx)]!r}")
+
+
+def assert_close(a, b, rtol=1e-10, what=""):
+    """north_star tolerance: |a-b| <= rtol*max(|b|, scale) with identical NaN / inf masks.
+    ``scale`` = the field's own magnitude (max finite |b|) times 1e-6, i.e. values more than six
+    decades below the field's peak are compared absolutely: FD2 of a field that carries a 1-ulp
+    difference cannot be relatively accurate where the derivative crosses zero."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    assert np.array_equal(np.isnan(a), np.isnan(b)), f"{what}: NaN masks differ"
+    inf = np.isinf(b)
+    assert np.array_equal(np.isinf(a), inf) and np.array_equal(a[inf], b[inf]), f"{what}: inf masks differ"
+    fin = np.isfinite(b)
+    if not fin.any():
+        return
+    scale = 1e-6 * np.max(np.abs(b[fin]))
+    err = np.abs(a[fin] - b[fin])
+    tol = rtol * np.maximum(np.abs(b[fin]), scale)
+    if not (err <= tol).all():
+        i = np.argmax(err / tol)
+        raise AssertionError(f"{what}: max err/tol = {(err / tol)[i]:.3g} (a={a[fin][i]!r}, b={b[fin][i]!r})")
