@@ -1,0 +1,97 @@
+"""Device-buffer plumbing.  PyTorch is used ONLY as the owner of device memory and streams
+(``torch.empty(..., device='cuda')``, ``tensor.data_ptr()``, ``torch.cuda.current_stream()``);
+all arithmetic happens in lib/fastcompute.so.  Nothing here computes on the CPU or with torch
+operators -- if CUDA is unavailable the functions raise ``BackendError``.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+
+import numpy as np
+
+from . import _lib
+from .exceptions import BackendError
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise BackendError("meteotools_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return t
+
+
+def stream():
+    return ct.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ct.c_void_p(t.data_ptr()) if t is not None else ct.c_void_p(0)
+
+
+def is_tensor(x):
+    t = _torch
+    return t is not None and isinstance(x, t.Tensor)
+
+
+def empty(shape, dtype=None):
+    t = require_cuda()
+    return t.empty(tuple(int(s) for s in shape), dtype=dtype or t.float64, device="cuda")
+
+
+def to_device(a, dtype=np.float64):
+    """Host array (any float dtype / layout) or CUDA tensor -> contiguous CUDA tensor of `dtype`.
+    float32 host data is uploaded as float32 (half the PCIe bytes) and widened on the device
+    (exact); other dtypes are converted on the host first."""
+    t = require_cuda()
+    if is_tensor(a):
+        if not a.is_cuda:
+            a = a.cuda()
+        if a.dtype != t.float64 and dtype == np.float64:
+            return cast_f64(a.contiguous())
+        return a.contiguous()
+    a = np.asarray(a)
+    if dtype == np.float64 and a.dtype == np.float32:
+        return cast_f64(t.from_numpy(np.ascontiguousarray(a)).cuda())
+    return t.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+def cast_f64(x):
+    """f32 CUDA tensor -> f64 CUDA tensor through mt_cast_f32_f64 (exact widening)."""
+    t = torch()
+    if x.dtype == t.float64:
+        return x
+    if x.dtype != t.float32:
+        raise BackendError(f"unsupported device dtype {x.dtype}: pass float64 or float32 tensors")
+    out = t.empty(x.shape, dtype=t.float64, device=x.device)
+    _lib.check(_lib.load().mt_cast_f32_f64(ptr(x), ptr(out), x.numel(), stream()), "mt_cast_f32_f64")
+    return out
+
+
+def to_host(x):
+    return x.detach().cpu().numpy()
+
+
+def permute3(src, shape, strides):
+    """Dense tensor dst of `shape` with dst[i,j,k] = src.flat[i*s0 + j*s1 + k*s2]."""
+    dst = empty(shape)
+    n0, n1, n2 = (int(s) for s in shape)
+    s0, s1, s2 = (int(s) for s in strides)
+    _lib.check(_lib.load().mt_permute3(ptr(src), ptr(dst), n0, n1, n2, s0, s1, s2, stream()),
+               "mt_permute3")
+    return dst
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (const double *const *) for the multi-variable entry points."""
+    arr = (ct.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr

@@ -1,0 +1,451 @@
+// Fused dynamics diagnostics: the cylindrical set of
+// grids/cylindrical_grid.py:264-508 ("F2") and the Cartesian set of
+// grids/cartesian_grid.py:232-364 ("F3").
+//
+// The reference evaluates every diagnostic as a chain of full-array NumPy passes (each FD2 alone
+// makes ~6 temporaries).  Here a settings file's whole set is two passes over HBM:
+//   stage A (point-wise): vr, vt, wind speed, kinetic energy, Tv, rho, density factor, Th,
+//                         Th_rho, Coriolis and centrifugal terms;
+//   stage B (stencil):    every FD2-based quantity (vorticity, divergence, PV, deformation,
+//                         filamentation, pressure-gradient / agradient force) from the stage-A
+//                         fields, one thread per point, neighbours through L1/L2.
+// Stages are separately launchable so that a level-sharded multi-GPU run can exchange the one
+// halo level of the z-differentiated stage-A fields between them.
+// Every expression keeps the reference's order of evaluation (bit-exact for pure arithmetic).
+#include "fd.cuh"
+#include "thermo.cuh"
+
+namespace {
+
+using mt::nan_f64;
+using mt::inf_f64;
+
+template <int LAYOUT>
+struct Lay {
+    int nz, nt, nr;
+    int64_t sz, st, sr;
+    __host__ __device__ Lay(int nz_, int nt_, int nr_) : nz(nz_), nt(nt_), nr(nr_)
+    {
+        if (LAYOUT == MT_LAYOUT_ZTR) {
+            sr = 1, st = nr, sz = (int64_t)nt * nr;
+        } else {
+            sz = 1, sr = nz, st = (int64_t)nr * nz;
+        }
+    }
+    __device__ __forceinline__ void decode(int64_t m, int &iz, int &it, int &ir) const
+    {
+        if (LAYOUT == MT_LAYOUT_ZTR) {
+            ir = (int)(m % nr);
+            const int64_t q = m / nr;
+            it = (int)(q % nt);
+            iz = (int)(q / nt);
+        } else {
+            iz = (int)(m % nz);
+            const int64_t q = m / nz;
+            ir = (int)(q % nr);
+            it = (int)(q / nr);
+        }
+    }
+};
+
+struct GridP {
+    double dz, dt, dr;
+    const double *r, *sin_t, *cos_t;
+    int own_lo, own_hi;  // owned local level range [own_lo, own_hi)
+    bool bottom, top;
+};
+
+struct StageAOut {
+    double *vr, *vt, *wind_speed, *kinetic_energy, *Tv, *rho, *density_factor, *Th, *Th_rho,
+        *coriolis_force, *centrifugal_force, *aam;
+};
+
+// ------------------------------------------------------------------------------- stage A
+template <int LAYOUT, bool CYL>
+__global__ void __launch_bounds__(256)
+k_stage_a(Lay<LAYOUT> L, GridP g, mt_dyn_in_t in, mt::th::Hydro hyd, StageAOut o)
+{
+    const int64_t total = (int64_t)L.nz * L.nt * L.nr;
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total;
+         m += (int64_t)gridDim.x * blockDim.x) {
+        int iz, it, ir;
+        L.decode(m, iz, it, ir);
+        const double u = __ldg(in.u + m), v = __ldg(in.v + m);
+        double vr = 0, vt = 0;
+        if (CYL) {
+            const double s = __ldg(g.sin_t + it), c = __ldg(g.cos_t + it);
+            vr = v * s + u * c;  // cylindrical_grid.py:267
+            vt = v * c - u * s;  // :268
+            if (o.vr) o.vr[m] = vr;
+            if (o.vt) o.vt[m] = vt;
+        }
+        if (o.wind_speed) __stcs(o.wind_speed + m, sqrt(u * u + v * v));  // (u**2+v**2)**0.5
+        if (o.kinetic_energy && in.w) {
+            const double w = __ldg(in.w + m);
+            const double ke = CYL ? (vr * vr + vt * vt + w * w) / 2 : (u * u + v * v + w * w) / 2;
+            __stcs(o.kinetic_energy + m, ke);
+        }
+        const bool need_thermo = o.Tv || o.rho || o.density_factor || o.Th || o.Th_rho;
+        if (need_thermo) {
+            const double qv = __ldg(in.qv + m);
+            double T = 0, P = 0;
+            if (in.T) T = __ldg(in.T + m);
+            if (in.p) P = __ldg(in.p + m);
+            if (o.Tv || o.rho) {
+                const double Tv = mt::th::Tv_from_qv(T, qv);
+                if (o.Tv) __stcs(o.Tv + m, Tv);
+                if (o.rho) o.rho[m] = mt::th::rho(P, Tv);
+            }
+            if (o.density_factor || o.Th || o.Th_rho) {
+                double df = 0;
+                if (o.density_factor || o.Th_rho) {
+                    if (hyd.n < 0) df = (1 + qv / 0.622) / 1.0;  // no hydrometeors: b = 1 (:443-445)
+                    else df = mt::th::density_factor(qv, hyd, m);
+                    if (o.density_factor) __stcs(o.density_factor + m, df);
+                }
+                const double Th = in.Th ? __ldg(in.Th + m) : mt::th::theta(T, P);
+                if (o.Th) __stcs(o.Th + m, Th);
+                if (o.Th_rho) o.Th_rho[m] = Th * df;  // :453
+            }
+        }
+        if (CYL && (o.coriolis_force || o.centrifugal_force || o.aam)) {
+            const double rr = __ldg(g.r + ir);
+            if (o.coriolis_force) __stcs(o.coriolis_force + m, __ldg(in.f + (int64_t)it * L.nr + ir) * vt);
+            if (o.centrifugal_force) __stcs(o.centrifugal_force + m, vt * vt / rr);
+            if (o.aam)  // :297  vt*r + 0.5*f*r**2
+                __stcs(o.aam + m, vt * rr + 0.5 * __ldg(in.f + (int64_t)it * L.nr + ir) * (rr * rr));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- stage B
+struct StageBIn {
+    const double *a, *b, *w, *thr, *p, *rho, *f;  // cyl: a=vr, b=vt ; car: a=u, b=v
+};
+struct StageBOut {
+    double *radial_PG_force, *agradient_force;
+    double *zeta_r, *zeta_t, *zeta_z, *abs_zeta_z, *div_hori, *div, *PV;
+    double *shear_deform, *stretch_deform, *filamentation_time;
+    uint8_t *strain_region;
+};
+
+template <int LAYOUT, bool CYL>
+__global__ void __launch_bounds__(256)
+k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o)
+{
+    const int64_t total = (int64_t)L.nz * L.nt * L.nr;
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total;
+         m += (int64_t)gridDim.x * blockDim.x) {
+        int iz, it, ir;
+        L.decode(m, iz, it, ir);
+        if (iz < g.own_lo || iz >= g.own_hi) continue;
+        const int nz = L.nz, nt = L.nt, nr = L.nr;
+        const int64_t sz = L.sz, st = L.st, sr = L.sr;
+        // axis accessors: element j along one axis through the point m
+#define AX_Z(F) [&](int k) { return __ldg((F) + m + (int64_t)(k - iz) * sz); }
+#define AX_T(F) [&](int k) { return __ldg((F) + m + (int64_t)(k - it) * st); }
+#define AX_R(F) [&](int k) { return __ldg((F) + m + (int64_t)(k - ir) * sr); }
+        const bool want_zr = o.zeta_r || o.PV;
+        const bool want_zt = o.zeta_t || o.PV;
+        const bool want_zz = o.zeta_z || o.abs_zeta_z || o.PV || o.filamentation_time || o.strain_region;
+        const bool want_def = o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
+        const bool want_div = o.div_hori || o.div;
+        double zeta_r = 0, zeta_t = 0, zeta_z = 0, abs_zz = 0;
+        const double rr = CYL ? __ldg(g.r + ir) : 1.0;
+        double da_dt = 0, db_dt = 0;  // d(vr|u)/dtheta|dy , d(vt|v)/dtheta|dy
+        if (want_zz || want_def || want_div) {
+            da_dt = mt::fd2(AX_T(in.a), it, nt, g.dt);
+            db_dt = mt::fd2(AX_T(in.b), it, nt, g.dt);
+        }
+        double db_dz = 0;
+        if (want_zr || (!CYL && want_zt)) db_dz = mt::fd2_shard(AX_Z(in.b), iz, nz, g.dz, g.bottom, g.top);
+        if (want_zr) {
+            const double dw_dt = mt::fd2(AX_T(in.w), it, nt, g.dt);
+            // cyl :387-388  FD2(w,dtheta,1)/r - FD2(vt,dz,0) ; car :250  FD2(w,dy,1) - FD2(v,dz,0)
+            zeta_r = CYL ? dw_dt / rr - db_dz : dw_dt - db_dz;
+            if (o.zeta_r) __stcs(o.zeta_r + m, zeta_r);
+        }
+        if (want_zt) {
+            const double dw_dr = mt::fd2(AX_R(in.w), ir, nr, g.dr);
+            if (CYL) {
+                const double da_dz = mt::fd2_shard(AX_Z(in.a), iz, nz, g.dz, g.bottom, g.top);
+                zeta_t = da_dz - dw_dr;  // :389-390
+            } else {
+                zeta_t = db_dz - dw_dr;  // cartesian_grid.py:251 (sic: v, not u)
+            }
+            if (o.zeta_t) __stcs(o.zeta_t + m, zeta_t);
+        }
+        double da_dr = 0, db_dr = 0;
+        if (!CYL && (want_zz || want_def || want_div)) {
+            da_dr = mt::fd2(AX_R(in.a), ir, nr, g.dr);
+            db_dr = mt::fd2(AX_R(in.b), ir, nr, g.dr);
+        }
+        if (want_zz) {
+            if (CYL) {
+                auto vt_r = [&](int k) { return __ldg(in.b + m + (int64_t)(k - ir) * sr) * __ldg(g.r + k); };
+                zeta_z = mt::fd2(vt_r, ir, nr, g.dr) / rr - da_dt / rr;  // :391-392
+            } else {
+                zeta_z = db_dr - da_dt;  // :252 FD2(v,dx,2) - FD2(u,dy,1)
+            }
+            if (o.zeta_z) __stcs(o.zeta_z + m, zeta_z);
+            if (o.abs_zeta_z || o.PV) {
+                abs_zz = zeta_z + __ldg(in.f + (int64_t)it * nr + ir);  // :400
+                if (o.abs_zeta_z) __stcs(o.abs_zeta_z + m, abs_zz);
+            }
+        }
+        if (want_div) {
+            double dh;
+            if (CYL) {
+                auto r_vr = [&](int k) { return __ldg(g.r + k) * __ldg(in.a + m + (int64_t)(k - ir) * sr); };
+                dh = mt::fd2(r_vr, ir, nr, g.dr) / rr + db_dt / rr;  // :408-409
+            } else {
+                dh = da_dr + db_dt;  // :266-267
+            }
+            if (o.div_hori) __stcs(o.div_hori + m, dh);
+            if (o.div) __stcs(o.div + m, dh + mt::fd2_shard(AX_Z(in.w), iz, nz, g.dz, g.bottom, g.top));
+        }
+        if (o.PV) {
+            const double dthr_dr = mt::fd2(AX_R(in.thr), ir, nr, g.dr);
+            const double dthr_dt = mt::fd2(AX_T(in.thr), it, nt, g.dt);
+            const double dthr_dz = mt::fd2_shard(AX_Z(in.thr), iz, nz, g.dz, g.bottom, g.top);
+            const double r_part = zeta_r * dthr_dr;                                  // :463 / :319
+            const double t_part = CYL ? zeta_t * dthr_dt / rr : zeta_t * dthr_dt;    // :464-465 / :320
+            const double z_part = abs_zz * dthr_dz;                                  // :466 / :321
+            __stcs(o.PV + m, (r_part + t_part + z_part) / __ldg(in.rho + m));
+        }
+        if (want_def) {
+            double sh, stc;
+            if (CYL) {
+                const double vr = __ldg(in.a + m), vt = __ldg(in.b + m);
+                const double dvr_dr = mt::fd2(AX_R(in.a), ir, nr, g.dr);
+                const double dvt_dr = mt::fd2(AX_R(in.b), ir, nr, g.dr);
+                sh = dvr_dr - vr / rr - db_dt / rr;   // :490-491
+                stc = dvt_dr - vt / rr + da_dt / rr;  // :492-493
+            } else {
+                sh = da_dr - db_dt;   // :344-345 FD2(u,dx) - FD2(v,dy)
+                stc = db_dr + da_dt;  // :346-347 FD2(v,dx) + FD2(u,dy)
+            }
+            if (o.shear_deform) __stcs(o.shear_deform + m, sh);
+            if (o.stretch_deform) __stcs(o.stretch_deform + m, stc);
+            if (o.filamentation_time || o.strain_region) {
+                const double s2 = sh * sh + stc * stc, z2 = zeta_z * zeta_z;
+                const bool strain = s2 > z2;  // :504-505
+                if (o.strain_region) o.strain_region[m] = strain ? 1 : 0;
+                if (o.filamentation_time)
+                    __stcs(o.filamentation_time + m, strain ? 2 * pow(s2 - z2, -0.5) : inf_f64());  // :501-508
+            }
+        }
+        if (CYL && (o.radial_PG_force || o.agradient_force)) {
+            const double pg = -mt::fd2(AX_R(in.p), ir, nr, g.dr) / __ldg(in.rho + m);  // :343
+            if (o.radial_PG_force) __stcs(o.radial_PG_force + m, pg);
+            if (o.agradient_force) {
+                const double vt = __ldg(in.b + m);
+                const double cor = __ldg(in.f + (int64_t)it * nr + ir) * vt;  // :341
+                const double cen = vt * vt / rr;                             // :342
+                __stcs(o.agradient_force + m, cor + cen + pg);               // :344-346
+            }
+        }
+#undef AX_Z
+#undef AX_T
+#undef AX_R
+    }
+}
+
+// nanmean over theta + anomaly (cylindrical_grid.py:225-229).  One thread per (z, r); the sum
+// runs over theta in index order.  NOTE: NumPy's pairwise summation is NOT reproduced bit for
+// bit (reduction order differs): tolerance 1e-10 relative, stated in the tests.
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+k_azimuthal(Lay<LAYOUT> L, const double *__restrict__ var, double *__restrict__ sym,
+            double *__restrict__ asy)
+{
+    const int64_t total = (int64_t)L.nz * L.nr;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        int iz, ir;
+        if (LAYOUT == MT_LAYOUT_ZTR) {
+            ir = (int)(q % L.nr);
+            iz = (int)(q / L.nr);
+        } else {
+            iz = (int)(q % L.nz);
+            ir = (int)(q / L.nz);
+        }
+        const int64_t base = iz * L.sz + ir * L.sr;
+        double s = 0.0;
+        int cnt = 0;
+        for (int t = 0; t < L.nt; ++t) {
+            const double v = __ldg(var + base + t * L.st);
+            if (!isnan(v)) {
+                s += v;
+                ++cnt;
+            }
+        }
+        const double mean = cnt ? s / (double)cnt : nan_f64();
+        sym[(int64_t)iz * L.nr + ir] = mean;  // sym is (nz, nr) C-order
+        if (asy)
+            for (int t = 0; t < L.nt; ++t) asy[base + t * L.st] = __ldg(var + base + t * L.st) - mean;
+    }
+}
+
+bool check_grid(const mt_grid_t *g, bool cyl)
+{
+    if (!g) {
+        mt::set_error("grid is null");
+        return false;
+    }
+    if (g->nz < 1 || g->nt < 3 || g->nr < 3 || g->nz > 2147483647LL || g->nt > 2147483647LL ||
+        g->nr > 2147483647LL) {
+        mt::set_error("grid extents must satisfy nt,nr >= 3 (FD2 needs 3 points)");
+        return false;
+    }
+    if (g->layout != MT_LAYOUT_ZTR && g->layout != MT_LAYOUT_TRZ) {
+        mt::set_error("unknown layout %d", g->layout);
+        return false;
+    }
+    if (cyl && (!g->r || !g->sin_t || !g->cos_t)) {
+        mt::set_error("cylindrical grid needs r, sin_t, cos_t tables");
+        return false;
+    }
+    if (g->halo_lo < 0 || g->halo_hi < 0 || g->halo_lo + g->halo_hi >= g->nz) {
+        mt::set_error("bad halo description");
+        return false;
+    }
+    return true;
+}
+
+GridP grid_params(const mt_grid_t *g)
+{
+    GridP p;
+    p.dz = g->dz, p.dt = g->dt, p.dr = g->dr;
+    p.r = g->r, p.sin_t = g->sin_t, p.cos_t = g->cos_t;
+    p.own_lo = (int)g->halo_lo;
+    p.own_hi = (int)(g->nz - g->halo_hi);
+    p.bottom = g->is_bottom != 0;
+    p.top = g->is_top != 0;
+    return p;
+}
+
+mt::th::Hydro hydro_of(const mt_dyn_in_t *in)
+{
+    mt::th::Hydro h;
+    h.n = 0;
+    for (int k = 0; k < 6; ++k) h.q[k] = nullptr;
+    for (int k = 0; k < 6 && in->q[k]; ++k) h.q[h.n++] = in->q[k];
+    if (h.n == 0) h.n = -1;
+    return h;
+}
+
+template <bool CYL>
+int run_sets(const mt_grid_t *g, const mt_dyn_in_t *in, const StageAOut &a, const StageBIn &bi,
+             const StageBOut &bo, int stages, bool need_a, bool need_b, cudaStream_t s)
+{
+    const int64_t total = g->nz * g->nt * g->nr;
+    const unsigned grid = mt::grid_for(total, 256, 8);
+    GridP p = grid_params(g);
+    mt::th::Hydro hyd = hydro_of(in);
+    if ((stages & 1) && need_a) {
+        mt::ProfScope prof(CYL ? "k_stage_a_cyl" : "k_stage_a_car", (mt_stream_t)s);
+        if (g->layout == MT_LAYOUT_ZTR)
+            k_stage_a<MT_LAYOUT_ZTR, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_ZTR>((int)g->nz, (int)g->nt, (int)g->nr), p, *in, hyd, a);
+        else
+            k_stage_a<MT_LAYOUT_TRZ, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_TRZ>((int)g->nz, (int)g->nt, (int)g->nr), p, *in, hyd, a);
+        MT_LAUNCH_CHECK();
+    }
+    if ((stages & 2) && need_b) {
+        mt::ProfScope prof(CYL ? "k_stage_b_cyl" : "k_stage_b_car", (mt_stream_t)s);
+        if (g->layout == MT_LAYOUT_ZTR)
+            k_stage_b<MT_LAYOUT_ZTR, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_ZTR>((int)g->nz, (int)g->nt, (int)g->nr), p, bi, bo);
+        else
+            k_stage_b<MT_LAYOUT_TRZ, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_TRZ>((int)g->nz, (int)g->nt, (int)g->nr), p, bi, bo);
+        MT_LAUNCH_CHECK();
+    }
+    return MT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mt_cyl_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_cyl_d_out_t *out, int stages,
+             mt_stream_t stream)
+{
+    if (!check_grid(g, true)) return MT_EINVAL;
+    MT_REQUIRE(in && out && in->u && in->v, "mt_cyl_d: u and v are required");
+    const mt_cyl_d_out_t &o = *out;
+    const bool z_needed = o.zeta_r || o.zeta_t || o.div || o.PV;
+    MT_REQUIRE(!z_needed || (g->nz - g->halo_lo - g->halo_hi >= 1 &&
+                             g->nz >= 3),
+               "mt_cyl_d: z-derivatives need at least 3 local levels");
+    const bool b_uses_w = o.zeta_r || o.zeta_t || o.div || o.PV;
+    MT_REQUIRE(!b_uses_w || in->w, "mt_cyl_d: w is required for the requested outputs");
+    const bool need_b = o.radial_PG_force || o.agradient_force || o.zeta_r || o.zeta_t || o.zeta_z ||
+                        o.abs_zeta_z || o.div_hori || o.div || o.PV || o.shear_deform ||
+                        o.stretch_deform || o.filamentation_time || o.strain_region;
+    const bool need_ab = o.zeta_r || o.zeta_t || o.zeta_z || o.abs_zeta_z || o.div_hori || o.div || o.PV ||
+                         o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
+    MT_REQUIRE(!((stages & MT_STAGE_B) && need_ab) || (o.vr && o.vt),
+               "mt_cyl_d: stencil outputs need the vr and vt buffers");
+    MT_REQUIRE(!((stages & MT_STAGE_B) && o.agradient_force) || o.vt, "mt_cyl_d: agradient_force needs vt");
+    MT_REQUIRE(!(o.PV) || (o.Th_rho && o.rho && in->f), "mt_cyl_d: PV needs Th_rho, rho buffers and f");
+    MT_REQUIRE(!(o.radial_PG_force || o.agradient_force) || (o.rho && in->p),
+               "mt_cyl_d: the pressure-gradient force needs p and the rho buffer");
+    MT_REQUIRE(!(o.abs_zeta_z || o.agradient_force || o.coriolis_force || o.aam) || in->f, "mt_cyl_d: f is required");
+    const bool thermo = o.Tv || o.rho || o.density_factor || o.Th || o.Th_rho;
+    MT_REQUIRE(!thermo || in->qv, "mt_cyl_d: qv is required for Tv/rho/density_factor/Th_rho");
+    MT_REQUIRE(!(o.Tv || o.rho) || (in->T && in->p), "mt_cyl_d: Tv/rho need T and p");
+    MT_REQUIRE(!(o.Th || o.Th_rho) || in->Th || (in->T && in->p), "mt_cyl_d: Th needs Th or (T, p)");
+    StageAOut a{o.vr, o.vt, o.wind_speed, o.kinetic_energy, o.Tv, o.rho, o.density_factor, o.Th,
+                o.Th_rho, o.coriolis_force, o.centrifugal_force, o.aam};
+    StageBIn bi{o.vr, o.vt, in->w, o.Th_rho, in->p, o.rho, in->f};
+    StageBOut bo{o.radial_PG_force, o.agradient_force, o.zeta_r, o.zeta_t, o.zeta_z, o.abs_zeta_z,
+                 o.div_hori, o.div, o.PV, o.shear_deform, o.stretch_deform, o.filamentation_time,
+                 o.strain_region};
+    return run_sets<true>(g, in, a, bi, bo, stages, true, need_b, (cudaStream_t)stream);
+}
+
+int mt_car_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_car_d_out_t *out, int stages,
+             mt_stream_t stream)
+{
+    if (!check_grid(g, false)) return MT_EINVAL;
+    MT_REQUIRE(in && out && in->u && in->v, "mt_car_d: u and v are required");
+    const mt_car_d_out_t &o = *out;
+    const bool b_uses_w = o.zeta_r || o.zeta_t || o.div || o.PV;
+    MT_REQUIRE(!b_uses_w || (in->w && g->nz >= 3), "mt_car_d: w and >= 3 local levels are required");
+    MT_REQUIRE(!(o.PV) || (o.Th_rho && o.rho && in->f), "mt_car_d: PV needs Th_rho, rho buffers and f");
+    MT_REQUIRE(!(o.abs_zeta_z) || in->f, "mt_car_d: f is required");
+    const bool thermo = o.Tv || o.rho || o.density_factor || o.Th || o.Th_rho;
+    MT_REQUIRE(!thermo || in->qv, "mt_car_d: qv is required for Tv/rho/density_factor/Th_rho");
+    MT_REQUIRE(!(o.Tv || o.rho) || (in->T && in->p), "mt_car_d: Tv/rho need T and p");
+    MT_REQUIRE(!(o.Th || o.Th_rho) || in->Th || (in->T && in->p), "mt_car_d: Th needs Th or (T, p)");
+    const bool need_a = o.wind_speed || o.kinetic_energy || thermo;
+    const bool need_b = o.zeta_r || o.zeta_t || o.zeta_z || o.abs_zeta_z || o.div_hori || o.div || o.PV ||
+                        o.shear_deform || o.stretch_deform || o.filamentation_time;
+    StageAOut a{nullptr, nullptr, o.wind_speed, o.kinetic_energy, o.Tv, o.rho, o.density_factor, o.Th,
+                o.Th_rho, nullptr, nullptr, nullptr};
+    StageBIn bi{in->u, in->v, in->w, o.Th_rho, in->p, o.rho, in->f};
+    StageBOut bo{nullptr, nullptr, o.zeta_r, o.zeta_t, o.zeta_z, o.abs_zeta_z, o.div_hori, o.div, o.PV,
+                 o.shear_deform, o.stretch_deform, o.filamentation_time, nullptr};
+    return run_sets<false>(g, in, a, bi, bo, stages, need_a, need_b, (cudaStream_t)stream);
+}
+
+int mt_azimuthal_mean(const double *var, const mt_grid_t *g, double *sym, double *asy,
+                      mt_stream_t stream)
+{
+    MT_REQUIRE(var && sym && g && g->nz >= 1 && g->nt >= 1 && g->nr >= 1, "mt_azimuthal_mean: bad arguments");
+    const unsigned grid = mt::grid_for(g->nz * g->nr, 128, 8);
+    mt::ProfScope prof("k_azimuthal", stream);
+    if (g->layout == MT_LAYOUT_ZTR)
+        k_azimuthal<MT_LAYOUT_ZTR><<<grid, 128, 0, (cudaStream_t)stream>>>(
+            Lay<MT_LAYOUT_ZTR>((int)g->nz, (int)g->nt, (int)g->nr), var, sym, asy);
+    else if (g->layout == MT_LAYOUT_TRZ)
+        k_azimuthal<MT_LAYOUT_TRZ><<<grid, 128, 0, (cudaStream_t)stream>>>(
+            Lay<MT_LAYOUT_TRZ>((int)g->nz, (int)g->nt, (int)g->nr), var, sym, asy);
+    else {
+        mt::set_error("mt_azimuthal_mean: unknown layout");
+        return MT_EINVAL;
+    }
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+// Point-wise thermodynamics: single-op kernels behind mt_pointwise, the
+// condensation-temperature fixed point (mt_calc_tc) and the fused cyl_td set (mt_cyl_td, "F4").
+//
+// calc_Tc (calc/thermaldynamic.py:392-402) stops when the GLOBAL np.max(|Tc-Tc2|) < 0.1, a
+// NaN-sensitive test.  It is reproduced without any host round trip: iteration i reduces its
+// max |diff| (as the bit pattern of a non-negative double, for which unsigned integer order ==
+// floating order and every NaN sorts above +inf) into scratch[i]; iteration i+1 starts by
+// reading scratch[i] and returns immediately when it is < 0.1 (or was never written: 0).
+#include "thermo.cuh"
+
+namespace {
+
+using namespace mt::th;
+
+template <int OP>
+__device__ __forceinline__ double apply(double a, double b, double c)
+{
+    switch (OP) {
+        case MT_OP_THETA: return theta(a, b);
+        case MT_OP_T: return T_from_theta(a, b);
+        case MT_OP_SAT_VAPOR: return sat_vapor(a);
+        case MT_OP_VAPOR: return b * sat_vapor(a);                        // :134
+        case MT_OP_SAT_QV: return sat_qv_from_es(sat_vapor(a), b);
+        case MT_OP_QV_TO_VAPOR: return qv_to_vapor(a, b);
+        case MT_OP_THETA_ES: return exp_factor(theta(a, b), sat_qv_from_es(sat_vapor(a), b), a);  // :187-189
+        case MT_OP_TD: return Td_from_vapor(a);
+        case MT_OP_QV: return sat_qv_from_es(b, a);                       // 0.622*vapor/(P-vapor), :256
+        case MT_OP_THETA_V: return theta_v(a, b, c);
+        case MT_OP_TV_QV: return Tv_from_qv(a, b);
+        case MT_OP_TV_VAPOR: return Tv_from_vapor(a, b, c);
+        case MT_OP_RHO: return rho(a, b);
+        case MT_OP_THETA_E: return exp_factor(a, b, c);
+        case MT_OP_MOIST_DTDZ: return moist_dTdz(a, b);
+        case MT_OP_RH: return a / sat_vapor(b);                           // :529-530
+        case MT_OP_P_TO_Z: return log(b / a) * (Rd * c / g);              // :33-34: log(P0/P)*H
+        case MT_OP_Z_TO_P: return b * exp(-a / (Rd * c / g));             // :51-52
+        case MT_OP_ADD: return a + b;
+    }
+    return mt::nan_f64();
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_pointwise(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ c,
+            double sb, double sc, double *__restrict__ out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double va = __ldg(a + i);
+        const double vb = b ? __ldg(b + i) : sb;
+        const double vc = c ? __ldg(c + i) : sc;
+        out[i] = apply<OP>(va, vb, vc);
+    }
+}
+
+// ---- block max of |diff| bit patterns ---------------------------------------------------------
+__device__ __forceinline__ void block_max_to(unsigned long long v, unsigned long long *dst)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    __shared__ unsigned long long smax[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smax[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < (int)(blockDim.x >> 5)) ? smax[lane] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+            v = other > v ? other : v;
+        }
+        if (lane == 0 && v != 0ull) atomicMax(dst, v);
+    }
+}
+
+__device__ __forceinline__ unsigned long long absbits(double d)
+{
+    return (unsigned long long)__double_as_longlong(fabs(d));
+}
+
+// One fixed-point sweep: Tc <- step(T,P,qv,Tc_prev) where Tc_prev = T for the first sweep.
+__global__ void __launch_bounds__(256)
+k_tc_iter(const double *__restrict__ T, const double *__restrict__ P, const double *__restrict__ qv,
+          double *__restrict__ Tc, int64_t n, int iter, unsigned long long *__restrict__ maxbits)
+{
+    if (iter > 0 && __longlong_as_double((long long)maxbits[iter - 1]) < 0.1) return;  // converged
+    unsigned long long m = 0ull;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = __ldg(T + i);
+        const double prev = iter == 0 ? t : Tc[i];
+        const double cur = Tc_step(t, __ldg(P + i), __ldg(qv + i), prev);
+        Tc[i] = cur;
+        const unsigned long long b = absbits(cur - prev);
+        m = b > m ? b : m;
+    }
+    block_max_to(m, maxbits + iter);
+}
+
+__global__ void k_tc_count(unsigned long long *maxbits)
+{
+    int count = 0;
+    for (int i = 0; i < 10; ++i) {
+        count = i + 1;
+        if (__longlong_as_double((long long)maxbits[i]) < 0.1) break;
+    }
+    reinterpret_cast<double *>(maxbits)[15] = (double)count;
+}
+
+// ---- fused cyl_td main pass: one read of T,p,qv(,qc,qr), every requested output, and the first
+//      Tc sweep.
+__global__ void __launch_bounds__(256)
+k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restrict__ maxbits)
+{
+    unsigned long long m = 0ull;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double T = __ldg(in.T + i), P = __ldg(in.p + i), qv = __ldg(in.qv + i);
+        const double Th = theta(T, P);
+        const double es = sat_vapor(T);
+        const double qvs = sat_qv_from_es(es, P);
+        const double vap = qv_to_vapor(P, qv);  // thermaldynamic_calculation.py:36-37
+        if (out.Th) __stcs(out.Th + i, Th);
+        if (out.vapor_s) __stcs(out.vapor_s + i, es);
+        if (out.qvs) __stcs(out.qvs + i, qvs);
+        if (out.vapor) __stcs(out.vapor + i, vap);
+        if (out.RH) __stcs(out.RH + i, vap / es);
+        if (out.Td) __stcs(out.Td + i, Td_from_vapor(vap));
+        if (out.Th_es) __stcs(out.Th_es + i, exp_factor(Th, qvs, T));
+        if (out.Th_v) {
+            double ql = 0.0;  // :66-78: qc+qr, qc, qr or the default 0
+            if (in.qc && in.qr) ql = __ldg(in.qc + i) + __ldg(in.qr + i);
+            else if (in.qc) ql = __ldg(in.qc + i);
+            else if (in.qr) ql = __ldg(in.qr + i);
+            __stcs(out.Th_v + i, theta_v(Th, qv, ql));
+        }
+        const double Tv = Tv_from_qv(T, qv);
+        if (out.Tv) __stcs(out.Tv + i, Tv);
+        if (out.rho) __stcs(out.rho + i, rho(P, Tv));
+        if (out.moist_dTdz) __stcs(out.moist_dTdz + i, moist_dTdz(T, qvs));
+        if (out.Tc) {
+            const double cur = Tc_step(T, P, qv, T);
+            out.Tc[i] = cur;
+            const unsigned long long b = absbits(cur - T);
+            m = b > m ? b : m;
+        }
+    }
+    if (out.Tc) block_max_to(m, maxbits);
+}
+
+__global__ void __launch_bounds__(256)
+k_td_theta_e(const double *__restrict__ T, const double *__restrict__ P, const double *__restrict__ qv,
+             const double *__restrict__ Th, const double *__restrict__ Tc, double *__restrict__ Th_e,
+             int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double th = Th ? __ldg(Th + i) : theta(__ldg(T + i), __ldg(P + i));
+        __stcs(Th_e + i, exp_factor(th, __ldg(qv + i), __ldg(Tc + i)));
+    }
+}
+
+int tc_tail(const double *T, const double *P, const double *qv, double *Tc, int64_t n,
+            unsigned long long *bits, int first_iter, cudaStream_t s)
+{
+    const unsigned grid = mt::grid_for(n, 256, 8);
+    for (int it = first_iter; it < 10; ++it) {
+        mt::ProfScope prof("k_tc_iter", (mt_stream_t)s);
+        k_tc_iter<<<grid, 256, 0, s>>>(T, P, qv, Tc, n, it, bits);
+        MT_LAUNCH_CHECK();
+    }
+    k_tc_count<<<1, 1, 0, s>>>(bits);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mt_pointwise(int op, const double *a, const double *b, const double *c, double sb, double sc,
+                 double *out, int64_t n, mt_stream_t stream)
+{
+    MT_REQUIRE(a && out && n >= 0, "mt_pointwise: null pointer");
+    if (n == 0) return MT_OK;
+    const unsigned grid = mt::grid_for(n, 256, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    mt::ProfScope prof("k_pointwise", stream);
+    switch (op) {
+#define PW(K) \
+    case K: k_pointwise<K><<<grid, 256, 0, s>>>(a, b, c, sb, sc, out, n); break;
+        PW(MT_OP_THETA) PW(MT_OP_T) PW(MT_OP_SAT_VAPOR) PW(MT_OP_VAPOR) PW(MT_OP_SAT_QV)
+        PW(MT_OP_QV_TO_VAPOR) PW(MT_OP_THETA_ES) PW(MT_OP_TD) PW(MT_OP_QV) PW(MT_OP_THETA_V)
+        PW(MT_OP_TV_QV) PW(MT_OP_TV_VAPOR) PW(MT_OP_RHO) PW(MT_OP_THETA_E) PW(MT_OP_MOIST_DTDZ)
+        PW(MT_OP_RH) PW(MT_OP_P_TO_Z) PW(MT_OP_Z_TO_P) PW(MT_OP_ADD)
+#undef PW
+        default: mt::set_error("mt_pointwise: unknown op %d", op); return MT_EINVAL;
+    }
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+int mt_calc_tc(const double *T, const double *P, const double *qv, double *Tc, int64_t n,
+               double *scratch, mt_stream_t stream)
+{
+    MT_REQUIRE(T && P && qv && Tc && scratch && n > 0, "mt_calc_tc: null pointer or empty array");
+    cudaStream_t s = (cudaStream_t)stream;
+    MT_CUDA(cudaMemsetAsync(scratch, 0, 16 * sizeof(double), s));
+    return tc_tail(T, P, qv, Tc, n, reinterpret_cast<unsigned long long *>(scratch), 0, s);
+}
+
+int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *scratch,
+              mt_stream_t stream)
+{
+    MT_REQUIRE(in && out && in->T && in->p && in->qv && n > 0, "mt_cyl_td: T, p, qv are required");
+    MT_REQUIRE(!out->Th_e || out->Tc, "mt_cyl_td: Th_e needs a Tc output buffer");
+    MT_REQUIRE(!out->Tc || scratch, "mt_cyl_td: Tc needs the 16-double scratch");
+    cudaStream_t s = (cudaStream_t)stream;
+    auto bits = reinterpret_cast<unsigned long long *>(scratch);
+    if (out->Tc) MT_CUDA(cudaMemsetAsync(scratch, 0, 16 * sizeof(double), s));
+    {
+        mt::ProfScope prof("k_td_main", stream);
+        k_td_main<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits);
+        MT_LAUNCH_CHECK();
+    }
+    if (out->Tc) {
+        int rc = tc_tail(in->T, in->p, in->qv, out->Tc, n, bits, 1, s);
+        if (rc != MT_OK) return rc;
+    }
+    if (out->Th_e) {
+        mt::ProfScope prof("k_td_theta_e", stream);
+        k_td_theta_e<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(in->T, in->p, in->qv, out->Th, out->Tc,
+                                                             out->Th_e, n);
+        MT_LAUNCH_CHECK();
+    }
+    return MT_OK;
+}
+
+}  // extern "C"

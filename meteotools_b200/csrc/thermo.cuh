@@ -1,0 +1,67 @@
+// Point-wise moist thermodynamics of calc/thermaldynamic.py, evaluated in the reference's
+// (NumPy left-to-right) order so that every +,-,*,/ rounds identically; exp/log/pow are CUDA's
+// double-precision functions (<= 1-2 ulp from NumPy's: the 1e-10 tolerance of the north star).
+#pragma once
+#include "common.cuh"
+
+namespace mt {
+namespace th {
+
+// calc/thermaldynamic.py:4-13
+constexpr double Rd = 287.0, Cp = 1004.0, g = 9.8;
+constexpr double kappa = Rd / Cp;
+constexpr double Lv = 2.5e6, A = 2.53e11, B = 5420.0;
+constexpr double CpRd = Cp / Rd;
+constexpr double A622 = A * 0.622;
+constexpr double Lv2 = Lv * Lv;
+constexpr double one_m_eps = 1 - 0.622;
+
+__device__ __forceinline__ double theta(double T, double P) { return T * pow(100000 / P, kappa); }          // :84
+__device__ __forceinline__ double T_from_theta(double th, double P) { return th * pow(P / 100000, kappa); }  // :101
+__device__ __forceinline__ double sat_vapor(double T)                                                          // :116
+{
+    return 611.2 * exp(17.67 * (T - 273.15) / (T - 273.15 + 243.5));
+}
+__device__ __forceinline__ double sat_qv_from_es(double es, double P) { return 0.622 * es / (P - es); }      // :151
+__device__ __forceinline__ double qv_to_vapor(double P, double qv) { return P * qv / (0.622 + qv); }          // :168
+__device__ __forceinline__ double Td_from_vapor(double es)                                                     // :224-225
+{
+    const double lnes = log(es / 611.2);
+    return 243.5 * lnes / (17.67 - lnes) + 273.15;
+}
+__device__ __forceinline__ double theta_v(double th, double qv, double ql) { return th * (1 + qv * 0.61 - ql); }  // :309
+__device__ __forceinline__ double Tv_from_qv(double T, double qv) { return T * (1 + (qv / 0.622)) / (1 + qv); }  // :335
+__device__ __forceinline__ double Tv_from_vapor(double T, double vap, double P)                                // :333
+{
+    return T / (1 - (vap / P) * one_m_eps);
+}
+__device__ __forceinline__ double rho(double P, double Tv) { return P / (Rd * Tv); }                           // :364
+__device__ __forceinline__ double Tc_step(double T, double P, double qv, double Tc2)                           // :396
+{
+    return B / (log(A622 / P / qv * pow(T / Tc2, CpRd)));
+}
+__device__ __forceinline__ double exp_factor(double th, double qv, double T)  // :189 / :456
+{
+    return th * exp(Lv * qv / Cp / T);
+}
+__device__ __forceinline__ double moist_dTdz(double T, double qvs)                                              // :486
+{
+    return -g * ((1 + Lv * qvs / Rd / T) / (Cp + Lv2 * qvs * 0.622 / Rd / (T * T)));
+}
+
+// density factor of cylindrical_grid.py:423-447 / cartesian_grid.py:279-303:
+// a = 1 + qv/0.622 ; b = 1 + qv + qc + qr + ... (left to right) ; a/b
+struct Hydro {
+    const double *q[6];
+    int n;
+};
+__device__ __forceinline__ double density_factor(double qv, const Hydro &h, int64_t i)
+{
+    const double a = 1 + qv / 0.622;
+    double b = 1 + qv;
+    for (int k = 0; k < h.n; ++k) b = b + __ldg(h.q[k] + i);
+    return a / b;
+}
+
+}  // namespace th
+}  // namespace mt

@@ -1,0 +1,89 @@
+// Staging helpers for the host-facing wrappers: exact f32 -> f64 upcast and a dense 3-D
+// permutation copy (layout changes between the user's C-order arrays and the library's
+// level-fastest "TRZ" order) through a padded shared-memory tile so that both the read and the
+// write are coalesced.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_cast_f32_f64(const float *__restrict__ in, double *__restrict__ out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (double)__ldg(in + i);
+}
+
+// dst is dense (n0, n1, n2); dst[i,j,k] = src[i*s0 + j*s1 + k*s2].
+// Tiles of 32x32 over (the axis that is contiguous in src) x (k); generic fallback otherwise.
+__global__ void __launch_bounds__(256)
+k_permute3_generic(const double *__restrict__ src, double *__restrict__ dst, int64_t n0, int64_t n1,
+                   int64_t n2, int64_t s0, int64_t s1, int64_t s2)
+{
+    const int64_t total = n0 * n1 * n2;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = t % n2, q = t / n2;
+        const int64_t j = q % n1, i = q / n1;
+        dst[t] = __ldg(src + i * s0 + j * s1 + k * s2);
+    }
+}
+
+// Case s0 == 1 (src contiguous along dst axis 0), dst contiguous along axis 2: transpose (i,k)
+// planes for each j through shared memory.
+__global__ void __launch_bounds__(256)
+k_permute3_t02(const double *__restrict__ src, double *__restrict__ dst, int64_t n0, int64_t n1,
+               int64_t n2, int64_t s1, int64_t s2)
+{
+    __shared__ double tile[32][33];
+    const int64_t tiles_i = (n0 + 31) / 32, tiles_k = (n2 + 31) / 32;
+    const int64_t ntiles = tiles_i * tiles_k * n1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+        const int64_t ti = tile_id % tiles_i, q = tile_id / tiles_i;
+        const int64_t tk = q % tiles_k, j = q / tiles_k;
+        const int64_t i0 = ti * 32, k0 = tk * 32;
+        for (int r = ty; r < 32; r += 8) {  // read: i contiguous
+            const int64_t i = i0 + tx, k = k0 + r;
+            if (i < n0 && k < n2) tile[r][tx] = __ldg(src + i + j * s1 + k * s2);
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {  // write: k contiguous
+            const int64_t i = i0 + r, k = k0 + tx;
+            if (i < n0 && k < n2) dst[(i * n1 + j) * n2 + k] = tile[tx][r];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream)
+{
+    MT_REQUIRE(in && out && n >= 0, "mt_cast_f32_f64: bad arguments");
+    if (n == 0) return MT_OK;
+    mt::ProfScope prof("k_cast_f32_f64", stream);
+    k_cast_f32_f64<<<mt::grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+int mt_permute3(const double *src, double *dst, int64_t n0, int64_t n1, int64_t n2, int64_t s0,
+                int64_t s1, int64_t s2, mt_stream_t stream)
+{
+    MT_REQUIRE(src && dst && src != dst && n0 > 0 && n1 > 0 && n2 > 0, "mt_permute3: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    mt::ProfScope prof("k_permute3", stream);
+    if (s0 == 1 && s2 != 1 && n0 >= 8 && n2 >= 8) {
+        const int64_t ntiles = ((n0 + 31) / 32) * ((n2 + 31) / 32) * n1;
+        k_permute3_t02<<<mt::grid_for(ntiles, 1, 16), 256, 0, s>>>(src, dst, n0, n1, n2, s1, s2);
+    } else {
+        k_permute3_generic<<<mt::grid_for(n0 * n1 * n2, 256, 8), 256, 0, s>>>(src, dst, n0, n1, n2, s0, s1, s2);
+    }
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""Cartesian (z, y, x) grid -- same methods and attribute names as the reference's
+``meteotools/grids/cartesian_grid.py`` (:13-391); arrays live on the device in C order
+("ZTR" with t = y, r = x), kernels are the Cartesian instantiation of ``mt_car_d``.
+
+The odd vorticity components of the reference (``zeta_t = dv/dz - dw/dx``, :251) are reproduced
+as written.  Smoothers (:142-229) and range averages (:370-391) are SURVEY 8(f) "next" rows.
+"""
+import numpy as np
+
+from .. import _device as D
+from .. import _lib
+from ..tools import timer
+from .cylindrical_grid import cylindrical_grid, _HYDRO_SETS
+from .grid_general import gridsystem
+from .thermaldynamic_calculation import calc_thermaldynamic
+
+
+class cartesian_grid(gridsystem, calc_thermaldynamic):
+    _layout = _lib.MT_LAYOUT_ZTR
+
+    def init_grid(self):  # :17-25
+        self.meta_convert_to_float('dx', 'dy', 'dz', 'z_start', 'SOR_parameter', 'iteration_tolerance')
+        self.meta_convert_to_int('Nx', 'Ny', 'Nz', 'max_iteration_times')
+        self.create_coord()
+        self.varlist3D = []
+        self.varlist2D = []
+
+    def make_center_loc(self):  # :28-30
+        self.center_xloc = (self.x[0] + self.x[-1]) / 2
+        self.center_yloc = (self.y[0] + self.y[-1]) / 2
+
+    def create_coord(self):  # :32-46
+        self.x = np.arange(0., self.Nx * self.dx, self.dx)
+        self.y = np.arange(0., self.Ny * self.dy, self.dy)
+        self.z = np.arange(0, self.Nz * self.dz, self.dz) + self.z_start
+        self.make_center_loc()
+        xx, yy = np.meshgrid(self.x, self.y)
+        object.__setattr__(self, 'xx', xx)   # host coordinate tables, not device fields
+        object.__setattr__(self, 'yy', yy)
+        object.__setattr__(self, 'dis_from_center',
+                           (xx - self.center_xloc) ** 2 + (yy - self.center_yloc) ** 2)
+        self.set_coord_meta('z', 'z', self.z, unit='m', description='Z coordinate')
+        self.set_coord_meta('y', 'y', self.y, unit='m', description='Y coordinate')
+        self.set_coord_meta('x', 'x', self.x, unit='m', description='X coordinate')
+
+    def _grid_shape3(self):
+        return (self.Nz, self.Ny, self.Nx)
+
+    # the cylindrical grid's set_data machinery works on (Ntheta, Nr) == (Ny, Nx) targets
+    Ntheta = property(lambda self: self.Ny)
+    Nr = property(lambda self: self.Nx)
+
+    def set_horizontal_location(self, offset_x, offset_y):  # :48-59
+        if not self._has('center_xloc') or not self._has('center_yloc'):
+            self.make_center_loc()
+        self.hinterp_target_xloc = self.x + offset_x - self.center_xloc
+        self.hinterp_target_yloc = self.y + offset_y - self.center_yloc
+        xx, yy = np.meshgrid(self.hinterp_target_xloc, self.hinterp_target_yloc)
+        self.__dict__.pop('_plan', None)
+        self.hinterp_target_xxloc, self.hinterp_target_yyloc = xx, yy
+
+    xTR = property(lambda self: self.hinterp_target_xxloc)
+    yTR = property(lambda self: self.hinterp_target_yyloc)
+
+    def _targets_dev(self):
+        return self.device('hinterp_target_xxloc'), self.device('hinterp_target_yyloc')
+
+    _target_box = cylindrical_grid._target_box
+    _interp2d_var = cylindrical_grid._interp2d_var
+    _setdata3d = cylindrical_grid._setdata3d
+    _plan_for = cylindrical_grid._plan_for
+
+    @timer
+    def set_data(self, src_dx, src_dy, src_vertical, vertical_interp_order=1, inclusive=False, **vardict):
+        """Interpolate source fields onto this grid (:76-125); terrain: z <= hgt -> NaN (:127-136)."""
+        if vertical_interp_order != 1:
+            raise NotImplementedError("spline vertical interpolation is a later row (SURVEY 8f-3)")
+        cur3d = []
+        for varname, var in vardict.items():
+            if len(var.shape) == 3:
+                self.varlist3D.append(varname)
+                cur3d.append(varname)
+            elif len(var.shape) == 2:
+                self._put(varname, self._interp2d_var(src_dx, src_dy, var), ndim=2)
+                self.varlist2D.append(varname)
+        if cur3d:
+            self._setdata3d(src_dx, src_dy, src_vertical, [vardict[n] for n in cur3d], cur3d, None, inclusive)
+        if 'hgt' in self.varlist2D:
+            self.set_terrain()
+            self.terrain_mask_vars()
+
+    def set_terrain(self):  # :127-131 (the mask itself is applied by the kernel)
+        pass
+
+    @property
+    def terrain_mask(self):
+        return self.z.reshape(-1, 1, 1) <= np.asarray(self.hgt)[None]
+
+    def terrain_mask_vars(self):  # :134-136
+        lib = _lib.load()
+        n = self.Ny * self.Nx
+        zd, hd = D.to_device(self.z), self.device('hgt')
+        for varname in self.varlist3D:
+            t = self.device(varname)
+            self._fields[varname].host = None
+            _lib.check(lib.mt_terrain_mask_car(D.ptr(t), self.Nz, n, n, 1, D.ptr(zd), D.ptr(hd), D.stream()),
+                       'mt_terrain_mask_car')
+
+    # ------------------------------------------------------------------ fused dynamics (F3)
+    def _grid_struct(self, nz=None, halo=(0, 0), ends=(True, True)):
+        g = _lib.mt_grid_t()
+        g.nz, g.nt, g.nr = (self.Nz if nz is None else nz), self.Ny, self.Nx
+        g.layout = self._layout
+        g.dz, g.dt, g.dr = self.dz, self.dy, self.dx
+        g.halo_lo, g.halo_hi = halo
+        g.is_bottom, g.is_top = int(ends[0]), int(ends[1])
+        return g
+
+    def _hydro_names(self):  # :285-303
+        for names in _HYDRO_SETS:
+            if self._has(*names):
+                return names
+        return ()
+
+    def _run_car_d(self, outputs, stages=_lib.MT_STAGE_ALL, existing=()):
+        lib = _lib.load()
+        din = _lib.mt_dyn_in_t()
+        for k in ("u", "v", "w", "p", "T", "Th", "qv", "f"):
+            setattr(din, k, self.device(k).data_ptr() if self._has(k) else None)
+        hyd = self._hydro_names()
+        if not hyd and ('density_factor' in outputs or 'Th_rho' in outputs):
+            print('Warning: no liquid / solid hydrometeor mixing ratio set; Th_rho will equal Th_v')
+        for i in range(6):
+            din.q[i] = self.device(hyd[i]).data_ptr() if i < len(hyd) else None
+        dout = _lib.mt_car_d_out_t()
+        bufs = {}
+        for k in outputs:
+            bufs[k] = self._new()
+            setattr(dout, k, bufs[k].data_ptr())
+        for k in existing:
+            setattr(dout, k, self.device(k).data_ptr())
+        _lib.check(lib.mt_car_d(self._grid_struct(), din, dout, stages, D.stream()), 'mt_car_d')
+        for k, b in bufs.items():
+            self._put(k, b)
+
+    def calc_diagnostics(self, outputs=None):
+        """The whole car_d set (test_car_dynamics.py:144-202) in two HBM passes."""
+        names = list(outputs) if outputs is not None else \
+            [k for k in _lib.CAR_D_OUT if k != 'Th' or not self._has('Th')]
+        if not self._has('u', 'v'):
+            raise AttributeError('u and v must be set first')
+        self._run_car_d(names)
+        return self
+
+    def _uvw(self, *need):
+        if not self._has(*need):
+            raise AttributeError(', '.join(need) + ' must be set first')
+
+    def calc_wind_speed(self):  # :232-236
+        self._uvw('u', 'v')
+        self._run_car_d(['wind_speed'], _lib.MT_STAGE_A)
+
+    def calc_kinetic_energy(self):  # :238-243
+        self._uvw('u', 'v', 'w')
+        self._run_car_d(['kinetic_energy'], _lib.MT_STAGE_A)
+
+    def calc_vorticity_3D(self):  # :248-254
+        self._uvw('u', 'v', 'w')
+        self._run_car_d(['zeta_r', 'zeta_t', 'zeta_z'], _lib.MT_STAGE_B)
+
+    def calc_abs_vorticity_3D(self):  # :256-262
+        if not self._has('zeta_z'):
+            self.calc_vorticity_3D()
+        if self._has('f'):
+            self._run_car_d(['abs_zeta_z'], _lib.MT_STAGE_B)
+        else:
+            raise AttributeError('f must be set first')
+
+    def calc_divergence_hori(self):  # :264-269
+        self._uvw('u', 'v')
+        self._run_car_d(['div_hori'], _lib.MT_STAGE_B)
+
+    def calc_divergence(self):  # :271-277
+        self._uvw('u', 'v', 'w')
+        self._run_car_d(['div'], _lib.MT_STAGE_B)
+
+    def calc_density_factor(self):  # :279-303
+        if not self._has('qv'):
+            raise AttributeError('qv must be set first')
+        self._run_car_d(['density_factor'], _lib.MT_STAGE_A)
+
+    def calc_density_potential_temperature(self):  # :305-309
+        self.calc_density_factor()
+        if not self._has('Th'):
+            self.calc_theta()
+        self._run_car_d(['Th_rho'], _lib.MT_STAGE_A)
+
+    def calc_PV(self):  # :311-322
+        if not self._has('Th_rho'):
+            self.calc_density_potential_temperature()
+        if not self._has('abs_zeta_z'):
+            self.calc_abs_vorticity_3D()
+        if not self._has('rho'):
+            self.calc_rho()
+        self._run_car_d(['PV'], _lib.MT_STAGE_B, existing=('Th_rho', 'rho'))
+
+    def calc_vorticity_z(self):  # :328-332
+        self._uvw('u', 'v')
+        self._run_car_d(['zeta_z'], _lib.MT_STAGE_B)
+
+    def calc_abs_vorticity_z(self):  # :334-340
+        if not self._has('zeta_z'):
+            self.calc_vorticity_z()
+        if self._has('f'):
+            self._run_car_d(['abs_zeta_z'], _lib.MT_STAGE_B)
+        else:
+            raise AttributeError('f must be set first')
+
+    def calc_deformation(self):  # :342-349
+        self._uvw('u', 'v')
+        self._run_car_d(['shear_deform', 'stretch_deform'], _lib.MT_STAGE_B)
+
+    def calc_filamentation(self):  # :351-364
+        if not self._has('shear_deform') or not self._has('stretch_deform'):
+            self.calc_deformation()
+        if not self._has('zeta_z'):
+            self.calc_vorticity_z()
+        self._run_car_d(['filamentation_time'], _lib.MT_STAGE_B)
+
+    def smooth1d(self, *a, **k):
+        raise NotImplementedError("smoothers are a later row (SURVEY 8f-2)")
+
+    smooth2d = smooth3d = smooth1d
+
+    def calc_horizontal_average(self, *a, **k):
+        raise NotImplementedError("range averages are a later row (SURVEY 8f-1)")
+
+    calc_vertical_average = calc_horizontal_average

@@ -1,0 +1,456 @@
+"""Cylindrical (z, theta, r) grid -- same methods and attribute names as the reference's
+``meteotools/grids/cylindrical_grid.py`` (:14-597), with every array operation executed by the
+CUDA library:
+
+* ``set_data``  (:95-137)  -> ``mt_setdata``: vertical interpolation (wrf.interplevel semantics,
+  parity unpinned) of the bounding box of the targets, bilinear gather, terrain mask -- fused,
+  batched over variables, only the touched source box is uploaded;
+* ``calc_*``    (:264-508) -> ``mt_cyl_d`` with the output set the method needs (the reference's
+  attribute-presence dispatch and AttributeError contract are kept);
+* ``calc_diagnostics()``   -> the whole cyl_d set in two HBM passes (stage A + stage B).
+
+Fields live on the device in (theta, r, z) memory order ("TRZ": z contiguous), which is what the
+gather produces and what the reference's own interpolation returns (a layer-fastest strided
+array); through the attribute protocol they appear as (Nz, Ntheta, Nr) arrays.
+Spline vertical interpolation (ver_interp_order=2) is a SURVEY 8(f) "next" row.
+"""
+import numpy as np
+
+from .. import _device as D
+from .. import _lib
+from ..calc import Make_cyclinder_coord
+from ..exceptions import DimensionError
+from ..tools import timer
+from .grid_general import gridsystem
+from .thermaldynamic_calculation import calc_thermaldynamic
+
+_HYDRO_SETS = (("qc", "qr", "qi", "qs", "qg", "qh"), ("qc", "qr", "qi", "qs", "qg"),
+               ("qc", "qr", "qi", "qs"), ("qc", "qr", "qi"), ("qc", "qr"), ("qc",), ("qr",), ())
+
+
+class cylindrical_grid(gridsystem, calc_thermaldynamic):
+    _layout = _lib.MT_LAYOUT_TRZ
+
+    def init_grid(self):  # :19-25
+        self.meta_convert_to_float('dr', 'dtheta', 'dz', 'dt', 'z_start', 'r_start', 'theta_start')
+        self.meta_convert_to_int('Nr', 'Ntheta', 'Nz')
+        self.create_coord()
+
+    def create_coord(self):  # :27-40
+        self.r = np.arange(self.r_start, self.Nr * self.dr, self.dr)
+        self.theta = np.arange(self.theta_start, self.Ntheta * self.dtheta, self.dtheta)
+        self.z = np.arange(0, self.Nz * self.dz, self.dz) + self.z_start
+        self.set_coord_meta('z', 'vertical', self.z, unit='m', description='Vertical coordinate')
+        self.set_coord_meta('theta', 'tangential', self.theta, unit='rad',
+                            description='Tangential coordinate')
+        self.set_coord_meta('r', 'radial', self.r, unit='m', description='Radial coordinate')
+        self.__dict__.pop('_grid_cache', None)
+
+    def _grid_shape3(self):
+        return (self.Nz, self.Ntheta, self.Nr)
+
+    def set_horizontal_location(self, offset_x, offset_y):  # :42-49
+        xTR, yTR = Make_cyclinder_coord([offset_y, offset_x], self.r, self.theta)
+        self.__dict__.pop('_plan', None)
+        self.xTR, self.yTR = xTR, yTR
+
+    # ------------------------------------------------------------------ grid descriptor for C
+    def _grid_struct(self, nz=None, halo=(0, 0), ends=(True, True)):
+        cache = self.__dict__.get('_grid_cache')
+        if cache is None:
+            # sin/cos tables from NumPy on the host (bit-identical to the reference's
+            # np.sin(theta) / np.cos(theta), :266-268)
+            cache = dict(r=D.to_device(self.r), sin=D.to_device(np.sin(self.theta)),
+                         cos=D.to_device(np.cos(self.theta)))
+            self.__dict__['_grid_cache'] = cache
+        g = _lib.mt_grid_t()
+        g.nz, g.nt, g.nr = (self.Nz if nz is None else nz), self.Ntheta, self.Nr
+        g.layout = self._layout
+        g.dz, g.dt, g.dr = self.dz, self.dtheta, self.dr
+        g.r, g.sin_t, g.cos_t = cache['r'].data_ptr(), cache['sin'].data_ptr(), cache['cos'].data_ptr()
+        g.halo_lo, g.halo_hi = halo
+        g.is_bottom, g.is_top = int(ends[0]), int(ends[1])
+        return g
+
+    # ------------------------------------------------------------------------- set_data (F1)
+    def _target_box(self, nx, ny, dx, dy):
+        """Bounding box [y0,y1) x [x0,x1) (source indices) of all four-corner stencils."""
+        with np.errstate(all='ignore'):
+            xi, yi = self.xTR / dx, self.yTR / dy
+        if np.nanmax(self.xTR) > dx * (nx - 1) or np.nanmin(self.xTR) < 0:
+            raise ValueError(f"X target outside the grid range 0 ~ {dx * (nx - 1)}")
+        if np.nanmax(self.yTR) > dy * (ny - 1) or np.nanmin(self.yTR) < 0:
+            raise ValueError(f"Y target outside the grid range 0 ~ {dy * (ny - 1)}")
+        x0, x1 = int(np.nanmin(xi)), min(int(np.nanmax(xi)) + 2, nx)
+        y0, y1 = int(np.nanmin(yi)), min(int(np.nanmax(yi)) + 2, ny)
+        return y0, y1, x0, x1
+
+    def _targets_dev(self):
+        return self.device('xTR'), self.device('yTR')
+
+    def _interp2d_var(self, dx, dy, var):
+        """2-D variable -> (theta, r) device tensor (interp2D_fast, :104-105)."""
+        var = np.asarray(var) if not D.is_tensor(var) else var
+        ny, nx = var.shape
+        self._target_box(nx, ny, dx, dy)
+        src = D.to_device(var)
+        xd, yd = self._targets_dev()
+        out = self._new(2)
+        _lib.check(_lib.load().mt_interp2d_layers(D.ptr(src), 1, ny, nx, 0, nx, 1, float(dx), float(dy),
+                                                  D.ptr(xd), D.ptr(yd), xd.numel(), D.ptr(out), 0, 1,
+                                                  D.stream()), 'mt_interp2d_layers')
+        return out
+
+    @timer
+    def set_data(self, wrf_dx, wrf_dy, wrf_vertical, ver_interp_order=1, inclusive=False, **vardict):
+        """Interpolate source fields (z, y, x) / (y, x) onto this grid (:95-137).
+
+        ``inclusive``: bracket test of the vertical interpolation, see include/meteotools_b200.h
+        (MT_IL_INCLUSIVE); default = the strict test of wrf-python's DINTERP3DZ."""
+        if ver_interp_order != 1:
+            raise NotImplementedError("spline vertical interpolation is a later row (SURVEY 8f-3)")
+        self.varlist3D, self.varlist2D = [], []
+        for varname, var in vardict.items():
+            if len(var.shape) == 3:
+                self.varlist3D.append(varname)
+            elif len(var.shape) == 2:
+                self._put(varname, self._interp2d_var(wrf_dx, wrf_dy, var), ndim=2)
+                self.varlist2D.append(varname)
+        hgt_idx = None
+        if 'hgt' in self.varlist2D:
+            self.set_terrain()
+            hgt_idx = self._hgt_idx_dev
+        if self.varlist3D:
+            self._setdata3d(wrf_dx, wrf_dy, wrf_vertical, [vardict[n] for n in self.varlist3D],
+                            self.varlist3D, hgt_idx, inclusive)
+
+    def _setdata3d(self, dx, dy, vert, sources, names, hgt_idx, inclusive):
+        lib = _lib.load()
+        t = D.torch()
+        nz, ny, nx = vert.shape
+        y0, y1, x0, x1 = self._target_box(nx, ny, dx, dy)
+
+        def is_f32(a):
+            return a.dtype == (t.float32 if D.is_tensor(a) else np.float32)
+
+        def crop(a):  # upload only the box that the targets touch
+            if D.is_tensor(a):
+                return a[:, y0:y1, x0:x1].contiguous()
+            return np.ascontiguousarray(a[:, y0:y1, x0:x1])
+        # direction of DINTERP3DZ from column (0,0) of the FULL coordinate array
+        direction = 1 if float(vert[0, 0, 0]) > float(vert[nz - 1, 0, 0]) else 0
+        levels = D.to_device(self.z)
+        order = 1 if np.all(np.diff(self.z) > 0) else (-1 if np.all(np.diff(self.z) < 0) else 0)
+        xd, yd = self._targets_dev()
+        n = xd.numel()
+        plan = self._plan_for(dx, dy, nx, ny)
+        trz = self._layout == _lib.MT_LAYOUT_TRZ
+        vert_cache = {}
+        # float32 sources: wrf-python returns float32 (result rounded), reproduced by ROUND_F32;
+        # they are uploaded as float32 (half the PCIe bytes) when the coordinate is float32 too.
+        for want32 in (False, True):
+            group = [(nm, s) for nm, s in zip(names, sources) if is_f32(s) == want32]
+            if not group:
+                continue
+            dtype = _lib.MT_F32 if (want32 and is_f32(vert)) else _lib.MT_F64
+            np_dt = np.float32 if dtype == _lib.MT_F32 else np.float64
+            if dtype not in vert_cache:
+                vert_cache[dtype] = D.to_device(crop(vert), dtype=np_dt)
+            vert_d = vert_cache[dtype]
+            flags = (_lib.MT_IL_INCLUSIVE if inclusive else 0) | (_lib.MT_IL_ROUND_F32 if want32 else 0)
+            for b0 in range(0, len(group), _lib.MT_MAX_VARS):
+                batch = group[b0:b0 + _lib.MT_MAX_VARS]
+                srcs = [D.to_device(crop(s), dtype=np_dt) for _, s in batch]
+                outs = [self._new() for _ in batch]
+                wsb = lib.mt_setdata_workspace_bytes(len(batch), self.Nz, y0, y1, x0, x1)
+                ws = D.empty(((wsb + 7) // 8,))
+                _lib.check(lib.mt_setdata(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, y1 - y0,
+                                          x1 - x0, y0, x0, ny, nx, float(dx), float(dy), y0, y1, x0, x1,
+                                          D.ptr(levels), self.Nz, order, direction, D.ptr(xd), D.ptr(yd),
+                                          D.ptr(plan[0]), D.ptr(plan[1]), n, D.ptr(hgt_idx),
+                                          D.ptr_array(outs), 1 if trz else n, self.Nz if trz else 1, flags,
+                                          D.ptr(ws), wsb, D.stream()), 'mt_setdata')
+                for (name, _), o in zip(batch, outs):
+                    self._put(name, o)
+
+    def _plan_for(self, dx, dy, nx, ny):
+        """Per-target stencil (indices + weights), built once per (grid location, source grid)."""
+        key = (float(dx), float(dy), int(nx), int(ny))
+        plan = self.__dict__.get('_plan')
+        if plan is None or plan[2] != key:
+            xd, yd = self._targets_dev()
+            n = xd.numel()
+            ix = D.empty((n, 4), D.torch().int32)
+            w = D.empty((n, 2))
+            _lib.check(_lib.load().mt_interp2d_plan(D.ptr(xd), D.ptr(yd), n, float(dx), float(dy), nx, ny,
+                                                    D.ptr(ix), D.ptr(w), D.stream()), 'mt_interp2d_plan')
+            plan = (ix, w, key)
+            self.__dict__['_plan'] = plan
+        return plan
+
+    def set_terrain(self):  # :139-176
+        hgt = self.device('hgt')
+        idx = D.empty((self.Ntheta, self.Nr), D.torch().int32)
+        _lib.check(_lib.load().mt_terrain_index_cyl(D.ptr(hgt), self.Ntheta, self.Nr, self.z_start, self.dz,
+                                                    D.ptr(idx), D.stream()), 'mt_terrain_index_cyl')
+        self.__dict__['_hgt_idx_dev'] = idx
+
+    @property
+    def hgt_idx(self):
+        return D.to_host(self._hgt_idx_dev)
+
+    @property
+    def hgt_mask(self):  # :171-176
+        return np.where(self.hgt_idx.reshape(1, self.Ntheta, self.Nr)
+                        > np.arange(0, self.Nz, 1).reshape(-1, 1, 1), 1, 0)
+
+    def terrain_mask_vars(self):  # :178-181
+        lib = _lib.load()
+        n = self.Ntheta * self.Nr
+        for varname in self.varlist3D:
+            t = self.device(varname)
+            self._fields[varname].host = None
+            sz, sn = (1, self.Nz) if self._layout == _lib.MT_LAYOUT_TRZ else (n, 1)
+            _lib.check(lib.mt_terrain_mask_cyl(D.ptr(t), self.Nz, n, sz, sn, D.ptr(self._hgt_idx_dev),
+                                               D.stream()), 'mt_terrain_mask_cyl')
+
+    # ------------------------------------------------------------------ fused dynamics (F2)
+    def _hydro_names(self):  # :429-447: which hydrometeors enter the density factor
+        for names in _HYDRO_SETS:
+            if self._has(*names):
+                return names
+        return ()
+
+    def _run_cyl_d(self, outputs, stages=_lib.MT_STAGE_ALL, existing=()):
+        """One ``mt_cyl_d`` call producing `outputs`; `existing` names are stage-A fields that are
+        already on the grid and only read (stage B)."""
+        lib = _lib.load()
+        g = self._grid_struct()
+        din = _lib.mt_dyn_in_t()
+        for k in ("u", "v", "w", "p", "T", "Th", "qv", "f"):
+            setattr(din, k, self.device(k).data_ptr() if self._has(k) else None)
+        hyd = self._hydro_names()
+        if not hyd and ('density_factor' in outputs or 'Th_rho' in outputs):
+            print('Warning: no liquid / solid hydrometeor mixing ratio set; Th_rho will equal Th_v')
+        for i in range(6):
+            din.q[i] = self.device(hyd[i]).data_ptr() if i < len(hyd) else None
+        dout = _lib.mt_cyl_d_out_t()
+        bufs = {}
+        for k in outputs:
+            bufs[k] = self._new(dtype=D.torch().uint8 if k == 'strain_region' else None)
+            setattr(dout, k, bufs[k].data_ptr())
+        for k in existing:
+            setattr(dout, k, self.device(k).data_ptr())
+        _lib.check(lib.mt_cyl_d(g, din, dout, stages, D.stream()), 'mt_cyl_d')
+        for k, b in bufs.items():
+            self._put(k, b)
+
+    def calc_diagnostics(self, outputs=None):
+        """The whole cyl_d diagnostic set (test_cyl_dynamics.py:148-227) in two HBM passes."""
+        names = list(outputs) if outputs is not None else \
+            [k for k in _lib.CYL_D_OUT if k not in ('Th',) or not self._has('Th')]
+        if not self._has('u', 'v'):
+            raise AttributeError('u and v must be set first')
+        self._run_cyl_d(names)
+        return self
+
+    # ---- per-method API of the reference -------------------------------------------------------
+    def calc_vr_vt(self):  # :264-270
+        if self._has('u', 'v'):
+            self._run_cyl_d(['vr', 'vt'], _lib.MT_STAGE_A)
+        else:
+            raise AttributeError('u and v must be set first')
+
+    def _vr_vt_2d(self, uname, vname, vrname, vtname):
+        """2-D (theta, r) rotation through the same kernel with Nz = 1."""
+        lib = _lib.load()
+        g = self._grid_struct(nz=1)
+        g.layout = _lib.MT_LAYOUT_ZTR
+        din = _lib.mt_dyn_in_t()
+        din.u, din.v = self.device(uname).data_ptr(), self.device(vname).data_ptr()
+        dout = _lib.mt_cyl_d_out_t()
+        vr, vt = self._new(2), self._new(2)
+        dout.vr, dout.vt = vr.data_ptr(), vt.data_ptr()
+        _lib.check(lib.mt_cyl_d(g, din, dout, _lib.MT_STAGE_A, D.stream()), 'mt_cyl_d')
+        self._put(vrname, vr, 2)
+        self._put(vtname, vt, 2)
+
+    def calc_vr_vt10(self):  # :272-278
+        if self._has('u10', 'v10'):
+            self._vr_vt_2d('u10', 'v10', 'vr10', 'vt10')
+        else:
+            raise AttributeError('u10 and v10 must be set first')
+
+    def calc_fric_vr_vt(self):  # :280-288
+        if self._has('fric_u', 'fric_v'):
+            lib = _lib.load()
+            din = _lib.mt_dyn_in_t()
+            din.u, din.v = self.device('fric_u').data_ptr(), self.device('fric_v').data_ptr()
+            dout = _lib.mt_cyl_d_out_t()
+            vr, vt = self._new(), self._new()
+            dout.vr, dout.vt = vr.data_ptr(), vt.data_ptr()
+            _lib.check(lib.mt_cyl_d(self._grid_struct(), din, dout, _lib.MT_STAGE_A, D.stream()), 'mt_cyl_d')
+            self._put('fric_vr', vr)
+            self._put('fric_vt', vt)
+        else:
+            raise AttributeError('fric_u and fric_v must be set first')
+
+    def calc_aam(self):  # :290-297
+        if not self._has('f'):
+            raise AttributeError('f must be set first')
+        if not self._has('vt') or not self._has('vr'):
+            self.calc_vr_vt()
+        # vt is recomputed from u, v by stage A (same expression, same bits)
+        self._run_cyl_d(['aam', 'vr', 'vt'], _lib.MT_STAGE_A)
+
+    def calc_agradient_force(self):  # :335-348
+        if not self._has('vt'):
+            self.calc_vr_vt()
+        if not self._has('rho'):
+            self.calc_rho()
+        if self._has('p', 'f'):
+            self._run_cyl_d(['coriolis_force', 'centrifugal_force'], _lib.MT_STAGE_A)
+            self._run_cyl_d(['radial_PG_force', 'agradient_force'], _lib.MT_STAGE_B,
+                            existing=('vr', 'vt', 'rho') if self._has('vr') else ('vt', 'rho'))
+        else:
+            raise AttributeError('p and f must be set first')
+
+    def calc_wind_speed(self):  # :354-358
+        if self._has('u', 'v'):
+            self._run_cyl_d(['wind_speed'], _lib.MT_STAGE_A)
+        else:
+            raise AttributeError('u and v must be set first')
+
+    def calc_wind_speed10(self):  # :360-364
+        if self._has('u10', 'v10'):
+            lib = _lib.load()
+            g = self._grid_struct(nz=1)
+            g.layout = _lib.MT_LAYOUT_ZTR
+            din = _lib.mt_dyn_in_t()
+            din.u, din.v = self.device('u10').data_ptr(), self.device('v10').data_ptr()
+            dout = _lib.mt_cyl_d_out_t()
+            ws = self._new(2)
+            dout.wind_speed = ws.data_ptr()
+            _lib.check(lib.mt_cyl_d(g, din, dout, _lib.MT_STAGE_A, D.stream()), 'mt_cyl_d')
+            self._put('wind_speed10', ws, 2)
+        else:
+            raise AttributeError('u10 and v10 must be set first')
+
+    def calc_kinetic_energy(self):  # :366-373
+        if not self._has('vr') or not self._has('vt'):
+            self.calc_vr_vt()
+        if self._has('w'):
+            self._run_cyl_d(['kinetic_energy'], _lib.MT_STAGE_A)
+        else:
+            raise AttributeError('w must be set first')
+
+    def _need_vr_vt(self):
+        if not self._has('vr') or not self._has('vt'):
+            self.calc_vr_vt()
+
+    def calc_vorticity_3D(self):  # :383-394
+        self._need_vr_vt()
+        if self._has('w'):
+            self._run_cyl_d(['zeta_r', 'zeta_t', 'zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        else:
+            raise AttributeError('w must be set first')
+
+    def calc_abs_vorticity_3D(self):  # :396-402
+        if not self._has('zeta_z'):
+            self.calc_vorticity_3D()
+        if self._has('f'):
+            self._run_cyl_d(['abs_zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        else:
+            raise AttributeError('f must be set first')
+
+    def calc_divergence_hori(self):  # :404-409
+        self._need_vr_vt()
+        self._run_cyl_d(['div_hori'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+
+    def calc_divergence(self):  # :412-421
+        self._need_vr_vt()
+        if self._has('w'):
+            self._run_cyl_d(['div'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        else:
+            raise AttributeError('w must be set first')
+
+    def calc_density_factor(self):  # :423-447
+        if not self._has('qv'):
+            raise AttributeError('qv must be set first')
+        self._run_cyl_d(['density_factor'], _lib.MT_STAGE_A)
+
+    def calc_density_potential_temperature(self):  # :449-453
+        self.calc_density_factor()
+        if not self._has('Th'):
+            self.calc_theta()
+        self._run_cyl_d(['Th_rho'], _lib.MT_STAGE_A)
+
+    def calc_PV(self):  # :455-467
+        if not self._has('Th_rho'):
+            self.calc_density_potential_temperature()
+        if not self._has('abs_zeta_z'):
+            self.calc_abs_vorticity_3D()
+        if not self._has('rho'):
+            self.calc_rho()
+        self._run_cyl_d(['PV'], _lib.MT_STAGE_B, existing=('vr', 'vt', 'Th_rho', 'rho'))
+
+    def calc_vorticity_z(self):  # :473-477
+        self._need_vr_vt()
+        self._run_cyl_d(['zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+
+    def calc_abs_vorticity_z(self):  # :479-485
+        if not self._has('zeta_z'):
+            self.calc_vorticity_z()
+        if self._has('f'):
+            self._run_cyl_d(['abs_zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        else:
+            raise AttributeError('f must be set first')
+
+    def calc_deformation(self):  # :487-493
+        self._need_vr_vt()
+        self._run_cyl_d(['shear_deform', 'stretch_deform'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+
+    def calc_filamentation(self):  # :495-508
+        if not self._has('shear_deform') or not self._has('stretch_deform'):
+            self.calc_deformation()
+        if not self._has('zeta_z'):
+            self.calc_vorticity_z()
+        self._run_cyl_d(['filamentation_time', 'strain_region'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+
+    # ------------------------------------------------------- azimuthal statistics (a13)
+    def calc_axisymmetric_asymmetric(self, varname):  # :214-235
+        if varname not in dir(self):
+            raise AttributeError(f'no variable named {varname}')
+        f = self._fields.get(varname)
+        if f is None or f.ndim != 3:
+            # 2-D / 1-D variables: tiny host reductions, as the reference
+            var = np.asarray(getattr(self, varname))
+            setattr(self, f'sym_{varname}', np.nanmean(var, axis=0) if var.ndim == 2 else np.nanmean(var))
+            setattr(self, f'asy_{varname}', var - getattr(self, f'sym_{varname}'))
+            return
+        var = self.device(varname)
+        sym = D.empty((self.Nz, self.Nr))
+        asy = self._new()
+        _lib.check(_lib.load().mt_azimuthal_mean(D.ptr(var), self._grid_struct(), D.ptr(sym), D.ptr(asy),
+                                                 D.stream()), 'mt_azimuthal_mean')
+        object.__setattr__(self, f'sym_{varname}', D.to_host(sym))
+        self._put(f'asy_{varname}', asy)
+
+    def find_rmw_and_speed(self):  # :300-314
+        if not self._has('sym_vt'):
+            if not self._has('vt'):
+                self.calc_vr_vt()
+            self.calc_axisymmetric_asymmetric('vt')
+        if not self._has('sym_wind_speed'):
+            if not self._has('wind_speed'):
+                self.calc_wind_speed()
+            self.calc_axisymmetric_asymmetric('wind_speed')
+        max_wind_r_idx = np.nanargmax(self.sym_wind_speed, axis=1)   # (Nz, Nr) host array: tiny
+        self.RMW = self.r[max_wind_r_idx]
+        self.wspd_max_RMW = self.sym_wind_speed[np.arange(self.Nz), max_wind_r_idx]
+        self.vt_max_RMW = self.sym_vt[np.arange(self.Nz), max_wind_r_idx]
+
+    def calc_horizontal_average(self, *a, **k):
+        raise NotImplementedError("range averages are a later row (SURVEY 8f-1)")
+
+    calc_vertical_average = calc_IKE = calc_IKE10 = calc_axisymmetry = calc_horizontal_average

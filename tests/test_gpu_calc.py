@@ -1,0 +1,87 @@
+"""GPU parity of meteotools_b200.calc against golden outputs of the
+reference and the oracle.  Finite differences: bit-exact.  Thermodynamics: 1e-10 relative
+(CUDA's exp/log/pow differ from NumPy's by <= 1-2 ulp), identical NaN masks."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, assert_same
+from oracle import calc_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    import meteotools_b200.calc as C
+    return C
+
+
+def test_fd_golden_bit_exact(C, golden_calc):
+    g = golden_calc
+    for name in ("FD2", "FD4", "FD2_front", "FD2_back", "FD2_2", "FD2_2_front", "FD2_2_back"):
+        for ax in range(3):
+            assert_same(getattr(C, name)(g["c_a"], 0.7, ax), g[f"o_{name}_{ax}"], f"{name} axis {ax}")
+    assert_same(C.FD2(g["c_a"], 0.7, -1), g["o_FD2_2"], "negative axis")
+
+
+def test_fd_kat_and_shapes(C):  # test_calc.py:81-91
+    a = np.add.reduce(np.meshgrid(*[np.arange(n, dtype=float) for n in (4, 5, 6)], indexing="ij"))
+    assert np.all(C.FD2(a, 2, 0) == 0.5)
+    b = C.FD2_front(a, 2, 0)
+    assert np.all(np.isnan(b[-2:])) and abs(np.nansum(b) - 30) < 1e-13
+    rng = np.random.default_rng(3)
+    for shape, ax in (((17,), 0), ((9, 33), 1), ((4, 3, 5, 6), 2), ((3, 1000, 7), 1)):
+        v = rng.standard_normal(shape)
+        v.flat[3] = np.nan
+        assert_same(C.FD2(v, 1.3, ax), co.FD2(v, 1.3, ax), f"FD2 {shape} axis {ax}")
+    with pytest.raises(IndexError):
+        C.FD2(np.zeros((2, 5)), 1.0, 0)
+    with pytest.raises(TypeError):
+        C.FD2(np.zeros((5, 5)), 1.0, 0, cyclic=True)   # unreachable in the reference too
+
+
+def test_thermo_golden(C, golden_calc):
+    g = golden_calc
+    T, P, qv, ql, RH = g["t_T"], g["t_P"], g["t_qv"], g["t_ql"], g["t_RH"]
+    th = C.calc_theta(T, P)
+    vap = C.qv_to_vapor(P, qv)
+    assert_same(vap, g["o_qv_to_vapor"], "qv_to_vapor (pure arithmetic)")
+    assert_same(C.calc_Tv(T, qv=qv), g["o_Tv"], "Tv (pure arithmetic)")
+    assert_same(C.calc_rho(P, Tv=g["o_Tv"]), g["o_rho"], "rho (pure arithmetic)")
+    assert_same(C.calc_qv(P, vapor=g["o_qv_to_vapor"]), g["o_qv"], "qv (pure arithmetic)")
+    pairs = {
+        "theta": th, "T": C.calc_T(g["o_theta"], P), "sat_vapor": C.calc_saturated_vapor(T),
+        "vapor_RH": C.calc_vapor(T, RH), "sat_qv": C.calc_saturated_qv(T, P),
+        "theta_es": C.calc_theta_es(T, P), "Td": C.calc_Td(es=g["o_qv_to_vapor"]),
+        "theta_v": C.calc_theta_v(theta=g["o_theta"], qv=qv, ql=ql),
+        "Tv_vapor": C.calc_Tv(T, P=P, vapor=g["o_qv_to_vapor"]),
+        "Tc": C.calc_Tc(T, P, qv=qv), "theta_e": C.calc_theta_e(theta=g["o_theta"], qv=qv, Tc=g["o_Tc"]),
+        "dTdz": C.calc_dTdz(T=T, P=P), "RH": C.calc_RH(T=T, vapor=g["o_qv_to_vapor"]),
+    }
+    for k, v in pairs.items():
+        assert_close(v, g[f"o_{k}"], 1e-10, k)
+    assert_same(C.calc_theta_v(theta=g["o_theta"], qv=qv, ql=ql), g["o_theta_v"], "theta_v (pure arithmetic)")
+    # dispatch through optional arguments, scalars and errors
+    from meteotools_b200.exceptions import InputError
+    assert_close(C.calc_Td(P=P, qv=qv), g["o_Td"], 1e-10, "Td from (P,qv)")
+    assert_close(C.calc_theta_e(T=T, P=P, qv=qv), g["o_theta_e"], 1e-10, "theta_e from (T,P,qv)")
+    assert abs(C.calc_theta(300.0, 90000.0) - co.theta(300.0, 90000.0)) < 1e-10
+    assert C.calc_dTdz() == -9.8 / 1004.
+    with pytest.raises(InputError):
+        C.calc_Td()
+    with pytest.raises(InputError):
+        C.calc_Tv(T)
+
+
+def test_tc_iteration_semantics(C, golden_calc):
+    g = golden_calc
+    T, P, qv = g["t_T"], g["t_P"], g["t_qv"]
+    ref, n_ref = co.Tc(T, P, qv, return_iters=True)
+    got, n = C.calc_Tc(T, P, qv=qv, return_iterations=True)
+    assert n == n_ref and 1 < n < 10
+    assert_close(got, ref, 1e-10, "Tc")
+    Tn = T.copy()
+    Tn[0, 0, 0] = np.nan       # NaN anywhere: np.max is NaN, all 10 sweeps run
+    got, n = C.calc_Tc(Tn, P, qv=qv, return_iterations=True)
+    assert n == 10
+    assert_close(got, g["o_Tc_nan"], 1e-10, "Tc with NaN")

@@ -1,0 +1,232 @@
+"""GPU parity of meteotools_b200.grids against golden outputs
+of the UNMODIFIED reference grid classes (tests/golden/{grids,setdata}.npz) and the oracle.
+
+Pure-arithmetic outputs (everything made of +,-,*,/,sqrt in the reference's order) must be
+BIT-EXACT; outputs that pass through exp/log/pow are held to 1e-10 relative with identical NaN /
+inf masks (tolerance rule: conftest.assert_close)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_close, assert_same
+from golden.make_golden import CAR, CAR_OUT, CYL, SD, TD_OUT
+from oracle import calc_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+# cyl_d outputs with no transcendental in their dependency chain (Th_rho/PV depend on theta=pow)
+CYL_EXACT = ["vr", "vt", "wind_speed", "Tv", "rho", "coriolis_force", "centrifugal_force",
+             "radial_PG_force", "agradient_force", "kinetic_energy", "zeta_r", "zeta_t", "zeta_z",
+             "abs_zeta_z", "div_hori", "div", "density_factor", "shear_deform", "stretch_deform",
+             "strain_region"]
+CYL_CLOSE = ["Th", "Th_rho", "PV", "filamentation_time"]
+CAR_EXACT = ["wind_speed", "kinetic_energy", "zeta_r", "zeta_t", "zeta_z", "abs_zeta_z", "div_hori",
+             "div", "density_factor", "Tv", "rho", "shear_deform", "stretch_deform"]
+
+
+def _cyl(golden, with_Th=False):
+    from meteotools_b200.grids import cylindrical_grid
+    cyl = cylindrical_grid(dict(CYL))
+    for k, v in golden.items():
+        if k.startswith("g_cyl_"):
+            setattr(cyl, k[len("g_cyl_"):], v.copy())
+    return cyl
+
+
+def test_cyl_d_fused(golden_grids):
+    g = golden_grids
+    cyl = _cyl(g).calc_diagnostics()
+    for k in CYL_EXACT:
+        assert_same(getattr(cyl, k), g[f"o_cyl_{k}"], f"cyl {k}")
+    for k in CYL_CLOSE:
+        assert_close(getattr(cyl, k), g[f"o_cyl_{k}"], 1e-10, f"cyl {k}")
+    # r[0] = 0 column: NaN / inf exactly where the reference has them
+    assert np.isnan(cyl.zeta_z[:, :, 0]).any() or np.isinf(cyl.zeta_z[:, :, 0]).any()
+
+
+def test_cyl_d_methods_match_reference_sequence(golden_grids):
+    """The per-method API of the reference, in the order of test_cyl_dynamics.py:148-227."""
+    g = golden_grids
+    cyl = _cyl(g)
+    for m in ("calc_vr_vt", "calc_wind_speed", "find_rmw_and_speed", "calc_agradient_force",
+              "calc_kinetic_energy", "calc_vorticity_3D", "calc_abs_vorticity_3D", "calc_vorticity_z",
+              "calc_abs_vorticity_z", "calc_divergence_hori", "calc_divergence",
+              "calc_density_potential_temperature", "calc_PV", "calc_deformation", "calc_filamentation"):
+        getattr(cyl, m)()
+    for k in CYL_EXACT:
+        assert_same(getattr(cyl, k), g[f"o_cyl_{k}"], f"cyl {k}")
+    for k in CYL_CLOSE:
+        assert_close(getattr(cyl, k), g[f"o_cyl_{k}"], 1e-10, f"cyl {k}")
+    assert_close(cyl.sym_vt, g["o_cyl_sym_vt"], 1e-10, "sym_vt")
+    assert_close(cyl.asy_vt, g["o_cyl_asy_vt"], 1e-10, "asy_vt")
+    assert_same(cyl.RMW, g["o_cyl_RMW"], "RMW")
+    assert_close(cyl.vt_max_RMW, g["o_cyl_vt_max_RMW"], 1e-10, "vt_max_RMW")
+    cyl.calc_aam()
+    r = cyl.r.reshape(1, 1, -1)
+    assert_same(cyl.aam, g["o_cyl_vt"] * r + 0.5 * g["g_cyl_f"] * r ** 2, "aam")
+
+
+def test_cyl_attribute_contract(golden_grids):
+    """AttributeError dispatch of the reference (test_cyl_dynamics.py:245-377) and the field store."""
+    cyl = _cyl(golden_grids)
+    del cyl.w
+    for m in ("calc_kinetic_energy", "calc_vorticity_3D", "calc_divergence"):
+        with pytest.raises(AttributeError):
+            getattr(cyl, m)()
+    cyl.calc_vorticity_z()          # does not need w
+    del cyl.f
+    with pytest.raises(AttributeError):
+        cyl.calc_abs_vorticity_z()
+    del cyl.u
+    del cyl.vr
+    with pytest.raises(AttributeError):
+        cyl.calc_vr_vt()
+    assert 'u' not in dir(cyl) and 'zeta_z' in dir(cyl)
+    with pytest.raises(ValueError):
+        cyl.zeta_z[0, 0, 0] = 1.0      # read-only view: modify by assignment
+    cyl.zeta_z = np.asarray(cyl.zeta_z) * 2
+    assert cyl.zeta_z.flags.writeable is False
+
+
+def test_cyl_td_fused_and_methods(golden_grids):
+    g = golden_grids
+    from meteotools_b200.grids import cylindrical_grid
+    exact = {"vapor", "Tv", "rho"}      # no exp/log/pow
+    for mode in ("fused", "methods"):
+        td = cylindrical_grid(dict(CYL))
+        for k in ("T", "p", "qv", "qc", "qr"):
+            setattr(td, k, g[f"g_cyl_{k}"].copy())
+        if mode == "fused":
+            td.calc_all_thermaldynamic()
+        else:
+            for m in ("calc_theta", "calc_saturated_vapor", "calc_saturated_qv", "calc_vapor", "calc_RH",
+                      "calc_Td", "calc_theta_es", "calc_theta_v", "calc_Tv", "calc_rho", "calc_Tc",
+                      "calc_theta_e"):
+                getattr(td, m)()
+            td.calc_moist_dTdz()    # qvs present -> the dry rate (reference quirk)
+            assert td.moist_dTdz == -9.8 / 1004.
+            del td.qvs
+            td.calc_moist_dTdz()
+        for k in TD_OUT:
+            if k in exact:
+                assert_same(getattr(td, k), g[f"o_td_{k}"], f"{mode} td {k}")
+            else:
+                assert_close(getattr(td, k), g[f"o_td_{k}"], 1e-10, f"{mode} td {k}")
+    # dependency contract of test_cyl_thermaldynamics.py:96-260
+    td = cylindrical_grid(dict(CYL))
+    td.T, td.p = g["g_cyl_T"].copy(), g["g_cyl_p"].copy()
+    td.calc_theta()
+    del td.T
+    with pytest.raises(AttributeError):
+        td.calc_theta()
+    td.calc_T()
+    assert_close(td.T, g["g_cyl_T"], 1e-10, "T from theta")
+    del td.p
+    with pytest.raises(AttributeError):
+        td.calc_saturated_qv()
+
+
+def test_car_d(golden_grids):
+    g = golden_grids
+    from meteotools_b200.grids import cartesian_grid
+    for mode in ("fused", "methods"):
+        car = cartesian_grid(dict(CAR))
+        for k, v in g.items():
+            if k.startswith("g_car_"):
+                setattr(car, k[len("g_car_"):], v.copy())
+        if mode == "fused":
+            car.calc_diagnostics()
+        else:
+            for m in ("calc_wind_speed", "calc_kinetic_energy", "calc_vorticity_3D", "calc_abs_vorticity_3D",
+                      "calc_divergence_hori", "calc_divergence", "calc_density_potential_temperature",
+                      "calc_PV", "calc_deformation", "calc_filamentation"):
+                getattr(car, m)()
+        for k in CAR_OUT:
+            if k in CAR_EXACT:
+                assert_same(getattr(car, k), g[f"o_car_{k}"], f"{mode} car {k}")
+            else:
+                assert_close(getattr(car, k), g[f"o_car_{k}"], 1e-10, f"{mode} car {k}")
+
+
+def test_set_data_cyl_golden(golden_setdata):
+    """Fused set_data (box upload, vertical + bilinear + terrain mask) == the reference pipeline."""
+    g = golden_setdata
+    from meteotools_b200.grids import cylindrical_grid
+    dx = float(g["s_dx"])
+    cyl = cylindrical_grid(dict(SD))
+    cyl.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    assert_same(cyl.xTR, g["o_sd_xTR"], "xTR")
+    cyl.set_data(dx, dx, g["s_z3d"], u=g["s_u"], T=g["s_T"], f=g["s_f"], hgt=g["s_hgt"])
+    assert_same(cyl.f, g["o_sd_cyl_f"], "f")
+    assert_same(cyl.hgt, g["o_sd_cyl_hgt"], "hgt")
+    assert_same(cyl.hgt_idx, g["o_sd_cyl_hgt_idx"], "hgt_idx")
+    assert_same(cyl.u, g["o_sd_cyl_u"], "u")
+    assert_same(cyl.T, g["o_sd_cyl_T"], "T")
+    assert np.isnan(cyl.u).any() and not np.isnan(cyl.u).all()
+    cyl2 = cylindrical_grid(dict(SD))
+    cyl2.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    cyl2.set_data(dx, dx, g["s_z3d"], u=g["s_u"])
+    assert_same(cyl2.u, g["o_sd_cyl_u_nomask"], "u without terrain")
+    # float32 sources: wrf-python rounds the level-interpolated field to float32
+    cyl3 = cylindrical_grid(dict(SD))
+    cyl3.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    u32, z32 = g["s_u"].astype(np.float32), g["s_z3d"].astype(np.float32)
+    cyl3.set_data(dx, dx, z32, u=u32)
+    ref = oracle.interp2D_fast_layers(dx, dx, g["o_sd_xTR"], g["o_sd_yTR"], oracle.interplevel(u32, z32, cyl3.z))
+    assert_same(cyl3.u, ref, "float32 pipeline")
+    with pytest.raises(ValueError):
+        cyl3.set_horizontal_location(0.0, 0.0)
+        cyl3.set_data(dx, dx, g["s_z3d"], u=g["s_u"])
+
+
+def test_set_data_car_golden(golden_setdata):
+    g = golden_setdata
+    from meteotools_b200.grids import cartesian_grid
+    dx = float(g["s_dx"])
+    car = cartesian_grid(dict(Nx=10, Ny=9, Nz=10, dx=3000, dy=3000, dz=600, z_start=100,
+                              vertical_coord_type="z", SOR_parameter=1.9, max_iteration_times=10,
+                              iteration_tolerance=0.05))
+    car.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    car.set_data(dx, dx, g["s_z3d"], u=g["s_u"], hgt=g["s_hgt"])
+    assert_same(car.hgt, g["o_sd_car_hgt"], "car hgt")
+    assert_same(car.u, g["o_sd_car_u"], "car u")
+
+
+def test_interplevel_device(golden_setdata):
+    """mt_interplevel alone: increasing (height) and decreasing (pressure) coordinates, descending
+    level list, inclusive switch, non-monotone columns (literal scan) -- against the oracle."""
+    import torch
+    from meteotools_b200 import _device as D, _lib
+    lib = _lib.load()
+    g = golden_setdata
+
+    def run(field, vert, levels, order, flags=0, box=None):
+        nz, ny, nx = vert.shape
+        y0, y1, x0, x1 = box or (0, ny, 0, nx)
+        f, v, lv = D.to_device(field), D.to_device(vert), D.to_device(np.asarray(levels, float))
+        out = torch.empty((len(levels), y1 - y0, x1 - x0), dtype=torch.float64, device="cuda")
+        _lib.check(lib.mt_interplevel(D.ptr_array([f]), 1, D.ptr(v), _lib.MT_F64, nz, ny, nx, y0, y1, x0, x1,
+                                      D.ptr(lv), len(levels), order, -1, D.ptr_array([out]),
+                                      (y1 - y0) * (x1 - x0), x1 - x0, 1, flags, D.stream()))
+        return out.cpu().numpy()
+
+    z3d, T, p3d, plev = g["s_z3d"], g["s_T"], g["s_p3d"], g["s_plev"]
+    zlev = np.arange(10) * 600.0 + 100.0
+    assert_same(run(T, z3d, zlev, 1), g["o_interplevel_z"], "height, ascending levels")
+    assert_same(run(T, p3d, plev, -1), g["o_interplevel_p"], "pressure, descending levels")
+    assert_same(run(T, p3d, plev[::-1].copy(), 1), g["o_interplevel_p"][::-1], "pressure, ascending levels")
+    assert_same(run(T, z3d, zlev[[3, 0, 7, 2]], 0), g["o_interplevel_z"][[3, 0, 7, 2]], "unsorted levels")
+    assert_same(run(T, z3d, zlev, 1, box=(3, 20, 5, 31)), g["o_interplevel_z"][:, 3:20, 5:31], "box")
+    # inclusive switch at exact model levels
+    v = np.arange(5.0).reshape(5, 1, 1) * np.ones((5, 3, 4))
+    assert np.isnan(run(v * 10, v, [2.0], 1)).all()
+    assert (run(v * 10, v, [2.0], 1, _lib.MT_IL_INCLUSIVE) == 20.0).all()
+    # non-monotone columns take the literal first-match-from-the-top scan
+    rng = np.random.default_rng(12)
+    vert = np.cumsum(rng.random((9, 6, 7)), axis=0)
+    vert[4, ::2, ::3] -= 1.2
+    fld = rng.standard_normal((9, 6, 7))
+    lev = np.linspace(0.5, 4.0, 8)
+    assert_same(run(fld, vert, lev, 1), oracle.interplevel(fld, vert, lev), "non-monotone")
+    assert_same(run(fld, vert, lev, 1, _lib.MT_IL_INCLUSIVE), oracle.interplevel(fld, vert, lev, inclusive=True),
+                "non-monotone inclusive")
