@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of meteotools_b200 (contract: see the task statement / DESIGN.md).
+
+Workload "S2+cyl_td" (BASELINE.json configs[1] + the north star's target): ONE step = one WRF
+time step of a 1000x1000x60 float64 field:
+    cart->cyl ingest (cylindrical_grid.set_data: vertical interpolation to 60 height levels +
+    bilinear gather + terrain mask) of the 12 3-D fields and 2 2-D fields of the reference's
+    test_cyl_thermaldynamics.py:44-56 call, onto the (60 z, 360 theta, 300 r) grid, followed by
+    the full cyl_td diagnostic set (13 outputs, incl. the calc_Tc fixed point).
+metric  = output grid points/s: target-grid points (60*360*300 = 6.48 M per step) per second
+          through the whole step.
+value   = device-resident: sources already in HBM (full 1000x1000x60 arrays), CUDA-event timed.
+e2e     = the public grid API with HOST (pinned) buffers: H2D of the touched boxes, kernels, D2H
+          of the 13 thermodynamic outputs, wall clock around synchronised steps.
+N > 1   = one process per GPU, every rank processes its own time steps (weak scaling, no
+          data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+import argparse
+import ctypes as ct
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NZ, NY, NX, DX = 60, 1000, 1000, 2000.0
+CYL = dict(Nr=300, Ntheta=360, Nz=60, dr=1000, dtheta=2 * np.pi / 360, dz=300, z_start=100, r_start=0,
+           theta_start=0, vertical_coord_type="z", dt=300)
+NAMES3D = ["u", "v", "w", "p", "T", "Th", "qv", "qc", "qr", "qi", "qs", "qg"]
+NAMES2D = ["f", "hgt"]
+NPTS = CYL["Nz"] * CYL["Ntheta"] * CYL["Nr"]
+METRIC = "output grid points/sec (cart->cyl set_data + cyl_td diagnostics, 1000x1000x60 f64 WRF field)"
+UNIT = "grid points/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ synthetic WRF step
+def make_step(seed, pinned):
+    """SURVEY 8(d) S2-style source: terrain-following heights over Gaussian hills (so that low
+    target levels fall below ground: NaN path), smooth + noise fields.  Returns host arrays
+    (pinned when `pinned`), all float64 C-order."""
+    rng = np.random.default_rng(seed)
+    if pinned:
+        import torch
+
+        def alloc(shape):
+            return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    else:
+        def alloc(shape):
+            return np.empty(shape)
+    yy, xx = np.meshgrid(np.arange(NY) * DX, np.arange(NX) * DX, indexing="ij")
+    cx, cy = (NX - 1) * DX / 2, (NY - 1) * DX / 2
+    hgt = alloc((NY, NX))
+    hgt[:] = (1500.0 * np.exp(-((xx - cx - 150e3) ** 2 + (yy - cy + 80e3) ** 2) / 120e3 ** 2)
+              + 900.0 * np.exp(-((xx - cx + 200e3) ** 2 + (yy - cy - 100e3) ** 2) / 90e3 ** 2))
+    f2d = alloc((NY, NX))
+    f2d[:] = 5e-5 + 2e-11 * (yy - cy)
+    k = (np.arange(NZ) / (NZ - 1)) ** 1.5
+    z3d = alloc((NZ, NY, NX))
+    np.multiply((20000.0 - hgt)[None], k[:, None, None], out=z3d)
+    z3d += hgt[None]
+    noise = [rng.standard_normal((NZ, NY, NX), dtype=np.float32) for _ in range(3)]
+    v = {n: alloc((NZ, NY, NX)) for n in NAMES3D}
+    swirl = 30.0 * np.sin(2 * np.pi * xx / (NX * DX)) * np.cos(2 * np.pi * yy / (NY * DX))
+    np.multiply(noise[0], 3.0, out=v["u"]); v["u"] += swirl[None]
+    np.multiply(noise[1], 3.0, out=v["v"]); v["v"] -= swirl.T[None]
+    np.multiply(noise[2], 0.5, out=v["w"])
+    np.divide(z3d, -8000.0, out=v["p"]); np.exp(v["p"], out=v["p"]); v["p"] *= 1e5; v["p"] += noise[1]
+    np.multiply(z3d, -6.5e-3, out=v["T"]); v["T"] += 300.0; v["T"] += noise[2]
+    np.divide(1e5, v["p"], out=v["Th"]); np.power(v["Th"], 287.0 / 1004.0, out=v["Th"]); v["Th"] *= v["T"]
+    np.abs(noise[0], out=noise[0]); np.abs(noise[1], out=noise[1]); np.abs(noise[2], out=noise[2])
+    np.multiply(noise[0], 1e-3, out=v["qv"]); v["qv"] += 1e-3
+    for i, n in enumerate(("qc", "qr", "qi", "qs", "qg")):
+        np.multiply(noise[i % 3][::-1] if i >= 3 else noise[i], 1e-4, out=v[n])
+    return dict(z3d=z3d, hgt=hgt, f=f2d, vars3d=v)
+
+
+def make_grid():
+    from meteotools_b200.grids import cylindrical_grid
+    cyl = cylindrical_grid(dict(CYL))
+    cyl.set_horizontal_location(((NX + 1) / 2 - 1) * DX, ((NY + 1) / 2 - 1) * DX)   # wrfout_grid.py:69-70
+    return cyl
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU reference step
+def reference_step(step, cyl_z, xTR, yTR, sample_vars):
+    """The reference's own order of work on the host (oracle port of fastcompute.f90 + DINTERP3DZ
+    restatement + numpy thermodynamics), for `sample_vars` of the 12 3-D variables; returns the
+    per-part seconds.  cylindrical_grid.set_data:95-137 + thermaldynamic_calculation.py chain."""
+    import oracle
+    from oracle import calc_oracle as co
+    t = {}
+    t0 = time.perf_counter()
+    hgt_c = oracle.interp2D_fast(DX, DX, xTR, yTR, step["hgt"])
+    oracle.interp2D_fast(DX, DX, xTR, yTR, step["f"])
+    idx = co.cyl_terrain_index(hgt_c, float(CYL["z_start"]), float(CYL["dz"]))
+    t["2d+terrain"] = time.perf_counter() - t0
+    out = {}
+    t_il = t_h = t_m = 0.0
+    for name in sample_vars:
+        t0 = time.perf_counter()
+        lev = oracle.interplevel(step["vars3d"][name], step["z3d"], cyl_z)     # full domain, as the reference
+        t1 = time.perf_counter()
+        c = oracle.interp2D_fast_layers(DX, DX, xTR, yTR, lev)
+        t2 = time.perf_counter()
+        out[name] = co.cyl_terrain_mask(c, idx)
+        t3 = time.perf_counter()
+        t_il, t_h, t_m = t_il + t1 - t0, t_h + t2 - t1, t_m + t3 - t2
+    t["interplevel/var"], t["interp2D_layers/var"], t["mask/var"] = (x / len(sample_vars) for x in (t_il, t_h, t_m))
+    return t, out
+
+
+def reference_td(fields):
+    from oracle import calc_oracle as co
+    t0 = time.perf_counter()
+    with np.errstate(all="ignore"):
+        co.cyl_td_set(fields["T"], fields["p"], fields["qv"], fields["qc"], fields["qr"])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(step, cyl, threads):
+    """Bounded sample: the 5 variables cyl_td needs (T, p, qv, qc, qr) go through the full CPU
+    set_data path (their cost x 12/5 estimates all 12 variables), then the full cyl_td set."""
+    import oracle
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    sample = ["T", "p", "qv", "qc", "qr"]
+    t, fields = reference_step(step, cyl.z, np.asarray(cyl.xTR), np.asarray(cyl.yTR), sample)
+    t_td = reference_td(fields)
+    per_var = t["interplevel/var"] + t["interp2D_layers/var"] + t["mask/var"]
+    est = t["2d+terrain"] + len(NAMES3D) * per_var + t_td
+    return {"value": NPTS / est, "unit": UNIT, "cores": threads, "kind": oracle.kind(),
+            "sample": (f"set_data of 5 of 12 3-D variables (full-domain interplevel {t['interplevel/var']:.2f} s/var, "
+                       f"interp2D_fast_layers {t['interp2D_layers/var']:.2f} s/var, mask {t['mask/var']:.2f} s/var; "
+                       f"x12/5 extrapolated) + 2-D fields {t['2d+terrain']:.2f} s + full cyl_td set {t_td:.2f} s "
+                       f"=> {est:.1f} s/step"),
+            "seconds_per_step_est": est}
+
+
+def synthetic_cyl_fields(seed=1):
+    """cyl_td inputs directly on the (60,360,300) grid (SURVEY 8d S3 distributions) with the
+    terrain NaNs a real step carries (so that calc_Tc runs its 10 sweeps, as in the GPU arm)."""
+    rng = np.random.default_rng(seed)
+    shp = (CYL["Nz"], CYL["Ntheta"], CYL["Nr"])
+    zz = (np.arange(CYL["Nz"]) * float(CYL["dz"]) + float(CYL["z_start"])).reshape(-1, 1, 1)
+    f = {"p": 1e5 * np.exp(-zz / 8000.0) + rng.standard_normal(shp),
+         "T": 300 - 6.5e-3 * zz + rng.standard_normal(shp),
+         "qv": 1e-3 + 1e-3 * np.abs(rng.standard_normal(shp)),
+         "qc": 1e-4 * np.abs(rng.standard_normal(shp)), "qr": 1e-4 * np.abs(rng.standard_normal(shp))}
+    for v in f.values():
+        v[:3, 100:140, 150:] = np.nan
+    return f
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU path (oracle port; gfortran is absent) on all host
+    cores.  Each step is a BOUNDED SAMPLE of the workload: 2-D fields + terrain index, the full
+    set_data path (full-domain interplevel, asfortranarray copy, bilinear, mask) for ONE of the
+    12 3-D variables (x12 extrapolated), and the full cyl_td set on grid-shaped fields."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    step = make_step(0, pinned=False)
+    # host-only grid coordinates (same numbers as cylindrical_grid.create_coord / Make_cyclinder_coord)
+    r = np.arange(0, CYL["Nr"] * float(CYL["dr"]), float(CYL["dr"]))
+    th = np.arange(0, CYL["Ntheta"] * float(CYL["dtheta"]), float(CYL["dtheta"]))
+    z = np.arange(0, CYL["Nz"] * float(CYL["dz"]), float(CYL["dz"])) + float(CYL["z_start"])
+    rr, tt = np.meshgrid(r, th)
+    cx = ((NX + 1) / 2 - 1) * DX
+    xTR, yTR = rr * np.cos(tt) + cx, rr * np.sin(tt) + cx
+    td_fields = synthetic_cyl_fields()
+    times, t_start = [], time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        t, _ = reference_step(step, z, xTR, yTR, [NAMES3D[i % len(NAMES3D)]])
+        t_td = reference_td(td_fields)
+        per_var = t["interplevel/var"] + t["interp2D_layers/var"] + t["mask/var"]
+        est = t["2d+terrain"] + len(NAMES3D) * per_var + t_td
+        if i >= args.warmup:
+            times.append(est)
+        if time.perf_counter() - t_start > 200 and times:   # keep the whole run within minutes
+            break
+    est = float(np.mean(times))
+    val = NPTS / est
+    sample_txt = ("each step = 2-D fields + terrain + full CPU set_data path for 1 of the 12 3-D variables "
+                  "(x12 extrapolated) + full cyl_td set; %d of %d timed steps executed" % (len(times), args.steps))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": oracle.kind(), "sample": sample_txt},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def config_dict():
+    return {"workload": "S2+cyl_td: cylindrical_grid.set_data (12 3-D + 2 2-D fields, 1000x1000x60 f64 -> 60z x 360theta x 300r, "
+                        "terrain-masked) + full cyl_td set (13 outputs)",
+            "source": [NZ, NY, NX], "target": [CYL["Nz"], CYL["Ntheta"], CYL["Nr"]],
+            "points_per_step": NPTS, "l2_policy": "inputs larger than L2 (touched source boxes 13 x 43 MB + 25 x 52 MB outputs per step >> 126 MB)",
+            "parallelism": "time steps sharded over ranks, no collective"}
+
+
+# ------------------------------------------------------------------------------ main (b200 arm)
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from meteotools_b200 import _device as D, _lib
+    from meteotools_b200.pipeline import CylStepPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = make_step(rank, pinned=True)
+    cyl = make_grid()
+    # ---------------- value: device-resident sources -------------------------------------------
+    dev3d = {k: torch.from_numpy(v).cuda() for k, v in step["vars3d"].items()}
+    dev2d = {"f": torch.from_numpy(step["f"]).cuda(), "hgt": torch.from_numpy(step["hgt"]).cuda()}
+    devz = torch.from_numpy(step["z3d"]).cuda()
+    pipe = CylStepPipeline(cyl, (NZ, NY, NX), DX, DX, NAMES3D, names2d=("f",), hgt=True, resident=True)
+    pipe.bind_device(devz, dev3d, dev2d, direction=0)
+    for _ in range(args.warmup):
+        pipe.run()
+    barrier()
+    clocks = Clocks(local)
+    clocks.start()
+    launches0 = lib.mt_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pipe.run()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.mt_launch_count() - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop()
+    barrier()
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * NPTS / (ms * 1e-3)
+
+    # ---------------- roofline: per-launch CUDA events over the same steps ----------------------
+    lib.mt_profile_enable(1)
+    for _ in range(args.steps):
+        pipe.run()
+    buf = ct.create_string_buffer(1 << 16)
+    _lib.check(lib.mt_profile_fetch(buf, len(buf)))
+    lib.mt_profile_enable(0)
+    tc_iters = int(D.to_host(pipe.scratch)[15])
+    kern = {}
+    for line in buf.value.decode().strip().splitlines():
+        name, cnt, tot = line.split()
+        kern[name] = (int(cnt), float(tot))
+    roof = roofline(kern, pipe, cyl, tc_iters, args.steps)
+
+    # ---------------- e2e: public grid API, host (pinned) buffers ---------------------------------
+    del pipe, dev3d, devz
+    torch.cuda.empty_cache()
+    td_names = list(_lib.TD_OUT)
+
+    def e2e_step():
+        cyl.set_data.__wrapped__(cyl, DX, DX, step["z3d"], f=step["f"], hgt=step["hgt"], **step["vars3d"])
+        cyl.calc_all_thermaldynamic()
+        return cyl.to_host(*td_names)
+    for _ in range(2):
+        res = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    y0, y1, x0, x1 = cyl._target_box(NX, NY, DX, DX)
+    h2d = (len(NAMES3D) + 1) * NZ * (y1 - y0) * (x1 - x0) * 8 + 2 * NY * NX * 8
+    d2h = len(td_names) * NPTS * 8
+    assert all(res[k].shape == (CYL["Nz"], CYL["Ntheta"], CYL["Nr"]) for k in td_names)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(),
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": world * NPTS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                    "path": "cylindrical_grid.set_data + calc_all_thermaldynamic + to_host (pinned host buffers)"},
+            "roofline": roof, "tc_iterations": tc_iters,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            out["cpu_baseline"] = cpu_baseline(step, cyl, os.cpu_count() or 1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(kern, pipe, cyl, tc_iters, steps):
+    """Dominant kernel of the step: algorithmic bytes per launch / CUDA-event duration per launch."""
+    peak, which = peaks()
+    y0, y1, x0, x1 = pipe.box
+    box = (y1 - y0) * (x1 - x0)
+    V, nlev, nz, n = len(NAMES3D), CYL["Nz"], NZ, pipe.n
+    # unique source columns touched by the four-corner stencils (SURVEY 8d "U")
+    ix = D_to_host(pipe.plan[0])
+    nx_full = NX
+    cells = np.unique(np.concatenate([ix[:, 2] * nx_full + ix[:, 0], ix[:, 2] * nx_full + ix[:, 1],
+                                      ix[:, 3] * nx_full + ix[:, 0], ix[:, 3] * nx_full + ix[:, 1]]))
+    U = int(cells.size)
+    alg = {
+        # reads (V fields + coordinate) x nz x box columns, writes V x nlev x box columns
+        "k_interplevel": 8.0 * box * (nz * (V + 1) + nlev * V),
+        # 8*(L*N + L*U) per variable + the plan (32 B/point) once per variable slice
+        "k_gather2d_lf": V * 8.0 * (nlev * n + nlev * U) + V * 32.0 * n,
+        "k_td_main": 8.0 * NPTS * (5 + 12),
+        "k_tc_iter": 8.0 * NPTS * 5,
+        "k_td_theta_e": 8.0 * NPTS * 4,
+    }
+    rows = []
+    for name, (cnt, tot) in kern.items():
+        per = tot / cnt
+        launches_per_step = cnt / steps
+        eff_cnt = cnt
+        if name == "k_tc_iter":   # sweeps after convergence return at once: count only executed ones
+            eff_cnt = steps * max(tc_iters - 1, 1)
+            per = tot / eff_cnt
+        a = alg.get(name)
+        rows.append({"kernel": name, "launches_per_step": launches_per_step, "ms_per_step": tot / steps,
+                     "avg_ms_per_launch": per,
+                     "achieved_gbs": (a / (per * 1e-3) / 1e9) if a else None, "alg_bytes_per_launch": a})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    top = rows[0]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top["kernel"])
+    return {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak,
+            "peak_source": which, "unit": "GB/s",
+            "frac": (top["achieved_gbs"] / peak) if top["achieved_gbs"] else None, "traffic": traffic,
+            "unique_source_columns": U, "box_columns": box, "kernels": rows,
+            "step_alg_bytes": sum(alg[k] * (max(tc_iters - 1, 1) if k == "k_tc_iter" else 1) for k in alg),
+            "note": "per-launch CUDA events (mt_profile_*) over the same steps, re-run after the timed region"}
+
+
+def D_to_host(t):
+    return t.detach().cpu().numpy().astype(np.int64)
+
+
+if __name__ == "__main__":
+    main()

@@ -297,6 +297,12 @@ int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream)
 int mt_permute3(const double *src, double *dst, int64_t n0, int64_t n1, int64_t n2, int64_t s0,
                 int64_t s1, int64_t s2, mt_stream_t stream);
 
+/* strided H2D upload of the column box [y0,y1)x[x0,x1) of a C-order (nz,ny,nx) HOST array (4- or
+ * 8-byte elements) into a dense (nz,y1-y0,x1-x0) device array: the host side of the "upload only
+ * what the targets touch" rule of mt_setdata.  Asynchronous when `host` is pinned. */
+int mt_upload_box(const void *host, int elem_bytes, int64_t nz, int64_t ny, int64_t nx, int64_t y0,
+                  int64_t y1, int64_t x0, int64_t x1, void *dev, mt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

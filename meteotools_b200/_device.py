@@ -78,7 +78,30 @@ def cast_f64(x):
 
 
 def to_host(x):
-    return x.detach().cpu().numpy()
+    """Device tensor -> NumPy array backed by PINNED host memory (torch's caching host allocator
+    recycles the blocks, so repeated downloads run at PCIe speed without re-pinning)."""
+    t = torch()
+    h = t.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    h.copy_(x, non_blocking=True)
+    t.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
+def upload_box(a, y0, y1, x0, x1, out=None):
+    """Column box of a C-order (nz,ny,nx) host array -> dense device tensor (same dtype) with one
+    strided DMA (mt_upload_box); no host-side crop copy."""
+    t = require_cuda()
+    a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64) or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+    nz, ny, nx = a.shape
+    if out is None:
+        out = t.empty((nz, y1 - y0, x1 - x0), dtype=t.float32 if a.dtype == np.float32 else t.float64,
+                      device="cuda")
+    _lib.check(_lib.load().mt_upload_box(ct.c_void_p(a.ctypes.data), a.dtype.itemsize, nz, ny, nx, y0, y1,
+                                         x0, x1, ptr(out), stream()), "mt_upload_box")
+    out._mt_keepalive = a   # the async DMA reads `a` until the stream reaches this point
+    return out
 
 
 def permute3(src, shape, strides):

@@ -87,3 +87,24 @@ int mt_permute3(const double *src, double *dst, int64_t n0, int64_t n1, int64_t 
 }
 
 }  // extern "C"
+
+// Strided host->device upload of the column box [y0,y1)x[x0,x1) of a C-order (nz,ny,nx) HOST
+// array into a dense (nz, y1-y0, x1-x0) device array: one cudaMemcpy3DAsync (DMA straight from
+// the caller's buffer -- at PCIe speed when it is pinned), no host-side crop copy.
+extern "C" int mt_upload_box(const void *host, int elem_bytes, int64_t nz, int64_t ny, int64_t nx,
+                             int64_t y0, int64_t y1, int64_t x0, int64_t x1, void *dev,
+                             mt_stream_t stream)
+{
+    MT_REQUIRE(host && dev && (elem_bytes == 4 || elem_bytes == 8), "mt_upload_box: bad arguments");
+    MT_REQUIRE(nz > 0 && 0 <= y0 && y0 < y1 && y1 <= ny && 0 <= x0 && x0 < x1 && x1 <= nx,
+               "mt_upload_box: box outside the array");
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(host), (size_t)nx * elem_bytes, (size_t)nx * elem_bytes, (size_t)ny);
+    p.srcPos = make_cudaPos((size_t)x0 * elem_bytes, (size_t)y0, 0);
+    p.dstPtr = make_cudaPitchedPtr(dev, (size_t)(x1 - x0) * elem_bytes, (size_t)(x1 - x0) * elem_bytes, (size_t)(y1 - y0));
+    p.dstPos = make_cudaPos(0, 0, 0);
+    p.extent = make_cudaExtent((size_t)(x1 - x0) * elem_bytes, (size_t)(y1 - y0), (size_t)nz);
+    p.kind = cudaMemcpyHostToDevice;
+    MT_CUDA(cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
+    return MT_OK;
+}

@@ -125,18 +125,19 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                             self.varlist3D, hgt_idx, inclusive)
 
     def _setdata3d(self, dx, dy, vert, sources, names, hgt_idx, inclusive):
+        """3-D variables: one ``mt_setdata`` per batch of <= 16 variables.  Host arrays are
+        uploaded box-only with one strided DMA each (``mt_upload_box``); CUDA tensors are used in
+        place (full array, no copy)."""
         lib = _lib.load()
         t = D.torch()
         nz, ny, nx = vert.shape
         y0, y1, x0, x1 = self._target_box(nx, ny, dx, dy)
+        on_dev = D.is_tensor(vert)
+        if any(D.is_tensor(s) != on_dev for s in sources):
+            raise TypeError("sources and the vertical coordinate must all be host arrays or all CUDA tensors")
 
         def is_f32(a):
             return a.dtype == (t.float32 if D.is_tensor(a) else np.float32)
-
-        def crop(a):  # upload only the box that the targets touch
-            if D.is_tensor(a):
-                return a[:, y0:y1, x0:x1].contiguous()
-            return np.ascontiguousarray(a[:, y0:y1, x0:x1])
         # direction of DINTERP3DZ from column (0,0) of the FULL coordinate array
         direction = 1 if float(vert[0, 0, 0]) > float(vert[nz - 1, 0, 0]) else 0
         levels = D.to_device(self.z)
@@ -145,6 +146,21 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         n = xd.numel()
         plan = self._plan_for(dx, dy, nx, ny)
         trz = self._layout == _lib.MT_LAYOUT_TRZ
+        if on_dev:   # resident sources: region = the full array
+            sny, snx, oy, ox = ny, nx, 0, 0
+        else:        # host sources: region = the box
+            sny, snx, oy, ox = y1 - y0, x1 - x0, y0, x0
+
+        def stage(a, want32):
+            if on_dev:
+                a = a.contiguous()
+                return a if (is_f32(a) and want32) else D.cast_f64(a)
+            a = np.asarray(a)
+            if a.dtype == np.float32 and not want32:
+                return D.cast_f64(D.upload_box(a, y0, y1, x0, x1))
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            return D.upload_box(a, y0, y1, x0, x1)
         vert_cache = {}
         # float32 sources: wrf-python returns float32 (result rounded), reproduced by ROUND_F32;
         # they are uploaded as float32 (half the PCIe bytes) when the coordinate is float32 too.
@@ -152,20 +168,20 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             group = [(nm, s) for nm, s in zip(names, sources) if is_f32(s) == want32]
             if not group:
                 continue
-            dtype = _lib.MT_F32 if (want32 and is_f32(vert)) else _lib.MT_F64
-            np_dt = np.float32 if dtype == _lib.MT_F32 else np.float64
+            use32 = want32 and is_f32(vert)
+            dtype = _lib.MT_F32 if use32 else _lib.MT_F64
             if dtype not in vert_cache:
-                vert_cache[dtype] = D.to_device(crop(vert), dtype=np_dt)
+                vert_cache[dtype] = stage(vert, use32)
             vert_d = vert_cache[dtype]
             flags = (_lib.MT_IL_INCLUSIVE if inclusive else 0) | (_lib.MT_IL_ROUND_F32 if want32 else 0)
             for b0 in range(0, len(group), _lib.MT_MAX_VARS):
                 batch = group[b0:b0 + _lib.MT_MAX_VARS]
-                srcs = [D.to_device(crop(s), dtype=np_dt) for _, s in batch]
+                srcs = [stage(s, use32) for _, s in batch]
                 outs = [self._new() for _ in batch]
                 wsb = lib.mt_setdata_workspace_bytes(len(batch), self.Nz, y0, y1, x0, x1)
                 ws = D.empty(((wsb + 7) // 8,))
-                _lib.check(lib.mt_setdata(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, y1 - y0,
-                                          x1 - x0, y0, x0, ny, nx, float(dx), float(dy), y0, y1, x0, x1,
+                _lib.check(lib.mt_setdata(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, sny, snx,
+                                          oy, ox, ny, nx, float(dx), float(dy), y0, y1, x0, x1,
                                           D.ptr(levels), self.Nz, order, direction, D.ptr(xd), D.ptr(yd),
                                           D.ptr(plan[0]), D.ptr(plan[1]), n, D.ptr(hgt_idx),
                                           D.ptr_array(outs), 1 if trz else n, self.Nz if trz else 1, flags,

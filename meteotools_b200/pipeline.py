@@ -1,0 +1,198 @@
+"""Persistent per-time-step pipeline and the multi-GPU driver.
+
+``CylStepPipeline`` is the production form of "set_data + diagnostics for one WRF time step":
+everything that does not depend on the step (target plan, bounding box, level table, workspace,
+output buffers) is prepared once; per step only ``upload`` (box-only strided DMA from the host
+arrays), ``run`` (3-4 C calls: terrain index, mt_setdata, mt_cyl_td and/or mt_cyl_d) and
+``download`` remain.  Results are identical to ``cylindrical_grid.set_data`` + ``calc_*``.
+
+Multi-GPU: WRF time steps are independent, so ``shard_steps`` deals them round-robin to the
+ranks of a ``torch.distributed`` job (one process per GPU, no data-path collective); vertical
+levels couple only through FD2(., dz, axis=0), for which ``halo_exchange_levels`` sends one
+boundary level to each neighbour (NCCL send/recv; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _device as D
+from . import _lib
+
+
+def shard_steps(n_steps: int, rank: int, world: int):
+    """Time steps of this rank: round-robin, so that ranks stay balanced for any n_steps."""
+    return list(range(rank, n_steps, world))
+
+
+def level_shard(nz: int, rank: int, world: int):
+    """Contiguous level block [lo, hi) of `rank` (sizes differ by at most one level) and the
+    halo levels it needs for a centred z-difference: (lo, hi, halo_lo, halo_hi)."""
+    base, rem = divmod(nz, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi, (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+
+
+def halo_exchange_levels(fields, halo_lo, halo_hi, rank, world, dist=None):
+    """One-level halo exchange along axis 0 of level-sharded (nz_local, ny, nx) C-order tensors
+    (owned levels are [halo_lo, nz_local-halo_hi)).  Batched isend/irecv pairs with rank +- 1;
+    works on CUDA tensors with NCCL and on CPU tensors with gloo."""
+    import torch.distributed as dist_mod
+    dist = dist or dist_mod
+    ops = []
+    for f in fields:
+        n = f.shape[0]
+        if halo_lo:   # talk to rank-1: send my first owned level, receive its last owned level
+            ops.append(dist.P2POp(dist.isend, f[halo_lo], rank - 1))
+            ops.append(dist.P2POp(dist.irecv, f[0], rank - 1))
+        if halo_hi:   # talk to rank+1
+            ops.append(dist.P2POp(dist.isend, f[n - 1 - halo_hi], rank + 1))
+            ops.append(dist.P2POp(dist.irecv, f[n - 1], rank + 1))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class CylStepPipeline:
+    """cart -> cyl ingest (+ terrain mask) and fused diagnostics of one time step on one GPU."""
+
+    def __init__(self, grid, src_shape, dx, dy, names3d, names2d=("f",), hgt=True, dtype=np.float64,
+                 td_outputs=tuple(_lib.TD_OUT), dyn_outputs=None, inclusive=False, resident=False):
+        t = D.require_cuda()
+        self.g, self.lib = grid, _lib.load()
+        self.nz, self.ny, self.nx = src_shape
+        self.dx, self.dy = float(dx), float(dy)
+        self.names3d, self.names2d, self.has_hgt = list(names3d), list(names2d), bool(hgt)
+        assert len(self.names3d) <= _lib.MT_MAX_VARS
+        self.np_dtype = np.dtype(dtype)
+        self.mt_dtype = _lib.MT_F32 if self.np_dtype == np.float32 else _lib.MT_F64
+        self.t_dtype = t.float32 if self.np_dtype == np.float32 else t.float64
+        self.flags = (_lib.MT_IL_INCLUSIVE if inclusive else 0) | \
+                     (_lib.MT_IL_ROUND_F32 if self.np_dtype == np.float32 else 0)
+        self.box = grid._target_box(self.nx, self.ny, self.dx, self.dy)
+        y0, y1, x0, x1 = self.box
+        self.resident = resident
+        self.region = (self.ny, self.nx, 0, 0) if resident else (y1 - y0, x1 - x0, y0, x0)
+        g = grid
+        self.levels = D.to_device(g.z)
+        self.order = 1 if np.all(np.diff(g.z) > 0) else (-1 if np.all(np.diff(g.z) < 0) else 0)
+        self.xd, self.yd = g._targets_dev()
+        self.n = self.xd.numel()
+        self.plan = g._plan_for(self.dx, self.dy, self.nx, self.ny)
+        self.wsb = self.lib.mt_setdata_workspace_bytes(len(self.names3d), g.Nz, y0, y1, x0, x1)
+        self.ws = D.empty(((self.wsb + 7) // 8,))
+        self.out3d = {k: g._new() for k in self.names3d}
+        self.out2d = {k: g._new(2) for k in self.names2d + (["hgt"] if hgt else [])}
+        self.hgt_idx = D.empty((g.Ntheta, g.Nr), t.int32) if hgt else None
+        self.td_names = list(td_outputs or [])
+        if "Th_e" in self.td_names and "Tc" not in self.td_names:
+            self.td_names.append("Tc")
+        self.td_out = {k: g._new() for k in self.td_names}
+        self.dyn_names = list(dyn_outputs or [])
+        self.dyn_out = {k: g._new(dtype=t.uint8 if k == "strain_region" else None) for k in self.dyn_names}
+        self.scratch = D.empty((16,))
+        self.direction = -1
+        if not resident:   # persistent device staging for the uploaded boxes
+            shp = (self.nz, y1 - y0, x1 - x0)
+            self.stage3d = {k: t.empty(shp, dtype=self.t_dtype, device="cuda") for k in self.names3d}
+            self.stage_vert = t.empty(shp, dtype=self.t_dtype, device="cuda")
+            self.stage2d = {k: t.empty((self.ny, self.nx), dtype=t.float64, device="cuda")
+                            for k in self.out2d}
+        self._build_structs()
+
+    # ---- per-step input binding -----------------------------------------------------------
+    def h2d_bytes(self):
+        y0, y1, x0, x1 = self.box
+        return (len(self.names3d) + 1) * self.nz * (y1 - y0) * (x1 - x0) * self.np_dtype.itemsize + \
+            len(self.out2d) * self.ny * self.nx * 8
+
+    def upload(self, vert, vars3d, vars2d):
+        """Host arrays -> device staging: box-only strided DMA for the 3-D fields."""
+        y0, y1, x0, x1 = self.box
+        self.direction = 1 if float(vert[0, 0, 0]) > float(vert[self.nz - 1, 0, 0]) else 0
+        D.upload_box(vert, y0, y1, x0, x1, out=self.stage_vert)
+        for k in self.names3d:
+            D.upload_box(vars3d[k], y0, y1, x0, x1, out=self.stage3d[k])
+        t = D.torch()
+        for k in self.out2d:
+            self.stage2d[k].copy_(t.from_numpy(np.ascontiguousarray(vars2d[k], dtype=np.float64)),
+                                  non_blocking=True)
+        self._bind(self.stage_vert, self.stage3d, self.stage2d)
+
+    def bind_device(self, vert, vars3d, vars2d, direction):
+        """Use resident full-size device arrays (no copy)."""
+        self.direction = int(direction)
+        self._bind(vert, vars3d, vars2d)
+
+    def _bind(self, vert, vars3d, vars2d):
+        self._vert = vert
+        self._src3d = [vars3d[k] for k in self.names3d]
+        self._src2d = vars2d
+        self._src_ptrs = D.ptr_array(self._src3d)
+
+    def _build_structs(self):
+        g = self.g
+        self._out_ptrs = D.ptr_array([self.out3d[k] for k in self.names3d])
+        if self.td_names:
+            self._tin, self._tout = _lib.mt_td_in_t(), _lib.mt_td_out_t()
+            for k in _lib.TD_IN:
+                setattr(self._tin, k, self.out3d[k].data_ptr() if k in self.out3d else None)
+            for k in self.td_names:
+                setattr(self._tout, k, self.td_out[k].data_ptr())
+        if self.dyn_names:
+            self._grid = g._grid_struct()
+            self._din, self._dout = _lib.mt_dyn_in_t(), _lib.mt_cyl_d_out_t()
+            for k in ("u", "v", "w", "p", "T", "Th", "qv"):
+                setattr(self._din, k, self.out3d[k].data_ptr() if k in self.out3d else None)
+            self._din.f = self.out2d["f"].data_ptr() if "f" in self.out2d else None
+            hyd = [k for k in _lib.HYDRO if k in self.out3d]
+            for i in range(6):
+                self._din.q[i] = self.out3d[hyd[i]].data_ptr() if i < len(hyd) else None
+            for k in self.dyn_names:
+                setattr(self._dout, k, self.dyn_out[k].data_ptr())
+
+    # ---- the step ---------------------------------------------------------------------------
+    def run(self):
+        lib, g, s = self.lib, self.g, D.stream()
+        y0, y1, x0, x1 = self.box
+        sny, snx, oy, ox = self.region
+        for k, o in self.out2d.items():   # 2-D fields: bilinear only
+            _lib.check(lib.mt_interp2d_layers(D.ptr(self._src2d[k]), 1, self.ny, self.nx, 0, self.nx, 1,
+                                              self.dx, self.dy, D.ptr(self.xd), D.ptr(self.yd), self.n,
+                                              D.ptr(o), 0, 1, s), "mt_interp2d_layers")
+        if self.has_hgt:
+            _lib.check(lib.mt_terrain_index_cyl(D.ptr(self.out2d["hgt"]), g.Ntheta, g.Nr, g.z_start, g.dz,
+                                                D.ptr(self.hgt_idx), s), "mt_terrain_index_cyl")
+        _lib.check(lib.mt_setdata(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype, self.nz,
+                                  sny, snx, oy, ox, self.ny, self.nx, self.dx, self.dy, y0, y1, x0, x1,
+                                  D.ptr(self.levels), g.Nz, self.order, self.direction, D.ptr(self.xd),
+                                  D.ptr(self.yd), D.ptr(self.plan[0]), D.ptr(self.plan[1]), self.n,
+                                  D.ptr(self.hgt_idx), self._out_ptrs, 1, g.Nz, self.flags, D.ptr(self.ws),
+                                  self.wsb, s), "mt_setdata")
+        if self.td_names:
+            _lib.check(lib.mt_cyl_td(self._tin, self._tout, self.n * g.Nz, D.ptr(self.scratch), s), "mt_cyl_td")
+        if self.dyn_names:
+            _lib.check(lib.mt_cyl_d(self._grid, self._din, self._dout, _lib.MT_STAGE_ALL, s), "mt_cyl_d")
+
+    def download(self, names=None):
+        """Results as NumPy (Nz, Ntheta, Nr) views of pinned host copies."""
+        pool = {**self.out3d, **self.td_out, **self.dyn_out}
+        names = list(names) if names is not None else list(self.td_out) + list(self.dyn_out)
+        t = D.torch()
+        hosts = {}
+        for k in names:
+            h = t.empty(pool[k].shape, dtype=pool[k].dtype, pin_memory=True)
+            h.copy_(pool[k], non_blocking=True)
+            hosts[k] = h
+        t.cuda.current_stream().synchronize()
+        return {k: h.numpy().transpose(2, 0, 1) for k, h in hosts.items()}
+
+    def d2h_bytes(self, names=None):
+        names = list(names) if names is not None else list(self.td_out) + list(self.dyn_out)
+        return len(names) * self.n * self.g.Nz * 8
+
+    def store_into_grid(self):
+        """Attach the step's device buffers to the grid object as fields (no copy)."""
+        for pool, nd in ((self.out3d, 3), (self.td_out, 3), (self.dyn_out, 3), (self.out2d, 2)):
+            for k, v in pool.items():
+                self.g._put(k, v, nd)

@@ -52,17 +52,25 @@ def assert_same(a, b, what=""):
                              f"{a[tuple(idx)]!r} vs {b[tuple(idx)]!r}")
 
 
-def assert_close(a, b, rtol=1e-10, what=""):
-    """north_star tolerance: |a-b| <= rtol*max(|b|, scale) with identical NaN / inf masks.
+def assert_close(a, b, rtol=1e-10, what="", nonfinite="exact"):
+    """north_star tolerance: |a-b| <= rtol*max(|b|, scale) at finite points, same finite mask.
     ``scale`` = the field's own magnitude (max finite |b|) times 1e-6, i.e. values more than six
     decades below the field's peak are compared absolutely: FD2 of a field that carries a 1-ulp
-    difference cannot be relatively accurate where the derivative crosses zero."""
+    difference cannot be relatively accurate where the derivative crosses zero.
+
+    nonfinite="exact": NaN and +-inf must sit at identical points with identical signs.
+    nonfinite="class": only finite-vs-non-finite must agree.  Used for exp/log/pow-derived fields
+    in the r = 0 column of the cylindrical grid, where the reference divides rounding noise such
+    as 3v-4v+v (identical v) by r[0] = 0: the sign of that noise, hence inf vs -inf vs NaN, flips
+    with a 1-ulp change of the input (DESIGN.md "singular column")."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
-    assert np.array_equal(np.isnan(a), np.isnan(b)), f"{what}: NaN masks differ"
-    inf = np.isinf(b)
-    assert np.array_equal(np.isinf(a), inf) and np.array_equal(a[inf], b[inf]), f"{what}: inf masks differ"
     fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin), f"{what}: finite masks differ"
+    if nonfinite == "exact":
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{what}: NaN masks differ"
+        inf = np.isinf(b)
+        assert np.array_equal(a[inf], b[inf]), f"{what}: inf signs differ"
     if not fin.any():
         return
     scale = 1e-6 * np.max(np.abs(b[fin]))
