@@ -326,7 +326,7 @@ def main():
     buf = ct.create_string_buffer(1 << 16)
     _lib.check(lib.mt_profile_fetch(buf, len(buf)))
     lib.mt_profile_enable(0)
-    tc_iters = int(D.to_host(pipe.scratch)[15])
+    tc_iters = int(D.to_host(pipe.scratch[:16])[15])
     kern = {}
     for line in buf.value.decode().strip().splitlines():
         name, cnt, tot = line.split()
@@ -394,10 +394,13 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
     alg = {
         # reads (V fields + coordinate) x nz x box columns, writes V x nlev x box columns
         "k_interplevel": 8.0 * box * (nz * (V + 1) + nlev * V),
+        "k_interplevel_tile": 8.0 * box * (nz * (V + 1) + nlev * V),
         # 8*(L*N + L*U) per variable + the plan (32 B/point) once per variable slice
         "k_gather2d_lf": V * 8.0 * (nlev * n + nlev * U) + V * 32.0 * n,
-        "k_td_main": 8.0 * NPTS * (5 + 12),
-        "k_tc_iter": 8.0 * NPTS * 5,
+        # reads T,p,qv,qc,qr; writes 12 outputs (incl. the first Tc sweep) + the sweep-invariant g
+        "k_td_main": 8.0 * NPTS * (5 + 13),
+        # reads g, Tc; writes Tc
+        "k_tc_iter": 8.0 * NPTS * 3,
         "k_td_theta_e": 8.0 * NPTS * 4,
     }
     rows = []

@@ -217,7 +217,7 @@ int mt_pointwise(int op, const double *a, const double *b, const double *c, doub
 
 /* condensation temperature (calc/thermaldynamic.py:367-402): up to 10 fixed-point iterations
  * with the reference's GLOBAL stop test np.max(|Tc-Tc2|) < 0.1 (NaN-sensitive).  `scratch`:
- * 16 doubles of device memory.  Fully asynchronous (the stop test is evaluated on the device);
+ * 16 + n doubles of device memory (16 control words + the sweep-invariant term per point).  Fully asynchronous (the stop test is evaluated on the device);
  * scratch[15] receives the number of iterations executed (as a double). */
 int mt_calc_tc(const double *T, const double *P, const double *qv, double *Tc, int64_t n,
                double *scratch, mt_stream_t stream);
@@ -250,7 +250,7 @@ typedef struct {
     double *Th, *vapor_s, *qvs, *vapor, *RH, *Td, *Th_es, *Th_v, *Tv, *rho, *Tc, *Th_e,
         *moist_dTdz;
 } mt_td_out_t;
-/* scratch: 16 doubles (see mt_calc_tc).  Tc, Th and qv handling: Th_e needs Tc; when out->Tc is
+/* scratch: 16 + n doubles (see mt_calc_tc).  Tc, Th and qv handling: Th_e needs Tc; when out->Tc is
  * NULL but Th_e is requested the call fails with MT_EINVAL. */
 int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *scratch,
               mt_stream_t stream);

@@ -192,14 +192,14 @@ def calc_Tc(T, P, RH=None, vapor=None, qv=None, return_iterations=False):
     (Td_, Pd, qd), shape, scalar_out, want_tensor = _prepare([T, P, qv])
     ops = [x if D.is_tensor(x) else D.to_device(np.full(shape, x)) for x in (Td_, Pd, qd)]
     out = D.empty(shape)
-    scratch = D.empty((16,))
+    scratch = D.empty((16 + out.numel(),))
     _lib.check(_lib.load().mt_calc_tc(D.ptr(ops[0]), D.ptr(ops[1]), D.ptr(ops[2]), D.ptr(out), out.numel(),
                                       D.ptr(scratch), D.stream()), "mt_calc_tc")
     res = out if want_tensor else D.to_host(out)
     if scalar_out and not want_tensor:
         res = float(res[0])
     if return_iterations:
-        return res, int(D.to_host(scratch)[15])
+        return res, int(D.to_host(scratch[:16])[15])
     return res
 
 

@@ -232,7 +232,7 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o)
                 const bool strain = s2 > z2;  // :504-505
                 if (o.strain_region) o.strain_region[m] = strain ? 1 : 0;
                 if (o.filamentation_time)
-                    __stcs(o.filamentation_time + m, strain ? 2 * pow(s2 - z2, -0.5) : inf_f64());  // :501-508
+                    __stcs(o.filamentation_time + m, strain ? 2 * (1.0 / sqrt(s2 - z2)) : inf_f64());  // :501-508, x**-0.5 as 1/sqrt(x): <= 1 ulp
             }
         }
         if (CYL && (o.radial_PG_force || o.agradient_force)) {

@@ -129,6 +129,165 @@ k_interplevel(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz, int6
     }
 }
 
+// ------------------------------------------------------------------ tiled variant (hot path, F1)
+// Used when the output is the dense level-fastest box array [by][bx][nlev] that mt_setdata feeds
+// to the gather.  A CTA owns TC consecutive box columns and streams nvar+1 source tiles
+// ([nz][TC]: the coordinate, then every variable) through a DOUBLE-BUFFERED shared-memory ring
+// filled with cp.async (LDGSTS: no register staging, the next tile lands while the current one
+// is consumed):
+//   tile 0 (coordinate): one thread per column checks monotonicity; all threads then bracket
+//      every (column, level) pair by binary search in shared memory (monotone columns: the
+//      unique / topmost bracket, identical to the scan from the top; other columns: the literal
+//      scan) and keep kp (1 byte) and w2 (8 bytes) per pair in shared memory;
+//   tile v+1 (variable v): all threads produce the TC*nlev outputs in level-fastest order, i.e.
+//      one contiguous, fully coalesced segment of TC*nlev doubles.
+// Every HBM byte is touched once (ncu: dram bytes == algorithmic bytes); rows are padded to TC+1
+// elements so that the per-lane varying level index does not collide on shared-memory banks.
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(T) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, bool INCLUSIVE>
+__global__ void __launch_bounds__(256)
+k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz, int64_t ny, int64_t nx,
+                   int64_t y0, int64_t x0, int by, int bx, const double *__restrict__ levels, int nlev,
+                   int levels_order, int direction, int round_f32, int TC, int off_w2, int off_lev,
+                   int off_kp, int off_mono, int off_col)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int pitch = TC + 1;
+    T *tiles = reinterpret_cast<T *>(smem_raw);                                  // [2][nz][pitch]
+    double *w2s = reinterpret_cast<double *>(smem_raw + off_w2);                 // [TC][nlev]
+    double *lev_s = reinterpret_cast<double *>(smem_raw + off_lev);              // [nlev]
+    unsigned char *kps = smem_raw + off_kp;                                      // [TC][nlev]
+    unsigned char *mono_s = smem_raw + off_mono;                                 // [TC]
+    long long *coloff = reinterpret_cast<long long *>(smem_raw + off_col);       // [TC]
+    const int tile_elems = nz * pitch;
+    const int tc_shift = __ffs(TC) - 1;  // TC is a power of two
+
+    const int64_t plane = ny * nx;
+    const int64_t ncol = (int64_t)by * bx;
+    const int decreasing = direction >= 0 ? direction
+                                          : (ld<T>(vert, 0) > ld<T>(vert, (int64_t)(nz - 1) * plane) ? 1 : 0);
+    const int im = decreasing ? 0 : 1, ip = decreasing ? 1 : 0;
+    const double sgn = decreasing ? -1.0 : 1.0;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int l = tid; l < nlev; l += nthr) lev_s[l] = levels[l];
+
+    const int64_t ntiles = (ncol + TC - 1) / TC;
+    for (int64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+        const int64_t c0 = tile_id * TC;
+        const int tc = (int)min((int64_t)TC, ncol - c0);
+        __syncthreads();  // previous tile's consumers are done with the ring and `coloff`
+        if (tid < tc) {   // global column offset of tile column j
+            const int64_t c = c0 + tid;
+            const int64_t cy = c / bx;
+            coloff[tid] = (y0 + cy) * nx + (x0 + (c - cy * bx));
+        }
+        __syncthreads();
+        // t = 0: coordinate, t = v+1: variable v.  Consecutive threads copy consecutive columns
+        // of one level row: coalesced.
+        auto prefetch = [&](int t) {
+            const T *src = reinterpret_cast<const T *>(t == 0 ? vert : ptrs.field[t - 1]);
+            T *dst = tiles + (t & 1) * tile_elems;
+            for (int e = tid; e < nz * TC; e += nthr) {
+                const int k = e >> tc_shift, j = e & (TC - 1);
+                if (j < tc) cp_async_elem(dst + k * pitch + j, src + (int64_t)k * plane + coloff[j]);
+            }
+            cp_async_commit();
+        };
+        prefetch(0);
+        prefetch(1);
+        cp_async_wait<1>();
+        __syncthreads();
+        const T *vt = tiles;  // coordinate tile
+        if (tid < tc) {       // monotone (in the chosen direction) per column
+            bool mono = true;
+            double prev = sgn * (double)vt[tid];
+            for (int k = 1; k < nz; ++k) {
+                const double cur = sgn * (double)vt[k * pitch + tid];
+                mono = mono && (cur >= prev);
+                prev = cur;
+            }
+            mono_s[tid] = mono ? 1 : 0;
+        }
+        __syncthreads();
+        for (int e = tid; e < tc * nlev; e += nthr) {  // bracket every (column, level) pair
+            const int j = e / nlev, lev = e - j * nlev;
+            const double want = lev_s[lev];
+            int kp = -1;
+            if (mono_s[j]) {
+                const double ww = sgn * want;  // upper bound: first K with vv[K] > ww
+                int lo = 0, hi = nz;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sgn * (double)vt[mid * pitch + j] > ww) hi = mid;
+                    else lo = mid + 1;
+                }
+                const int K = lo;
+                if (K >= 1 && K <= nz - 1) {
+                    if (INCLUSIVE) kp = K;
+                    else if (sgn * (double)vt[(K - 1) * pitch + j] < ww) kp = K;
+                } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * pitch + j] == ww) {
+                    kp = nz - 1;
+                }
+            } else {
+                for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
+                    const double vlo = (double)vt[(q - im) * pitch + j], vhi = (double)vt[(q - ip) * pitch + j];
+                    const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
+                    if (hit) {
+                        kp = q;
+                        break;
+                    }
+                }
+            }
+            double w2 = 0.0;
+            if (kp >= 0) {
+                const double vlo = (double)vt[(kp - im) * pitch + j], vhi = (double)vt[(kp - ip) * pitch + j];
+                w2 = (want - vlo) / (vhi - vlo);
+            }
+            kps[e] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
+            w2s[e] = w2;
+        }
+        for (int v = 0; v < nvar; ++v) {
+            const int t = v + 1;
+            __syncthreads();  // brackets visible; tile t-1 (the other ring slot) fully consumed
+            if (t + 1 <= nvar) {
+                prefetch(t + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();  // tile t has landed for every thread
+            const T *ft = tiles + (t & 1) * tile_elems;
+            double *__restrict__ o = ptrs.out[v] + c0 * nlev;
+            for (int e = tid; e < tc * nlev; e += nthr) {
+                const int j = e / nlev;
+                const int kp = kps[e];
+                double r;
+                if (kp == 255) {
+                    r = nan_f64();
+                } else {
+                    const double w2 = w2s[e];
+                    const double w1 = 1.0 - w2;
+                    r = w1 * (double)ft[(kp - im) * pitch + j] + w2 * (double)ft[(kp - ip) * pitch + j];
+                    if (round_f32) r = (double)(float)r;
+                }
+                o[e] = r;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- terrain (a7)
 // np.floor_divide on doubles (numpy npy_divmod): fmod-based, then floor with a 0.5 guard.
 __device__ __forceinline__ double np_floor_divide(double a, double b)
@@ -266,9 +425,52 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
         p.out[v] = out[v];
     }
     const int by = (int)(y1 - y0), bx = (int)(x1 - x0);
-    const unsigned grid = mt::grid_for((int64_t)by * bx, 128, 16);
     const int rf = (flags & MT_IL_ROUND_F32) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
+    // hot path: dense level-fastest box output -> shared-memory tiled kernel
+    if (o_lev == 1 && o_x == nlev && o_y == (int64_t)bx * nlev && nz <= 254) {
+        const size_t eb = dtype == MT_F64 ? 8 : 4;
+        struct Lay { size_t w2, lev, kp, mono, col, total; };
+        auto layout = [&](int tc) {
+            Lay L;
+            size_t b = 2 * (size_t)nz * (tc + 1) * eb;
+            L.w2 = (b + 15) & ~size_t(15);
+            L.lev = L.w2 + (size_t)tc * nlev * 8;
+            L.kp = L.lev + (size_t)nlev * 8;
+            L.mono = L.kp + (size_t)tc * nlev;
+            L.col = (L.mono + tc + 7) & ~size_t(7);
+            L.total = L.col + (size_t)tc * 8;
+            return L;
+        };
+        int TC = 64;
+        while (TC > 8 && layout(TC).total > 56 * 1024) TC >>= 1;   // >= 4 CTAs per SM
+        const Lay L = layout(TC);
+        if (L.total <= 200 * 1024) {
+            const int64_t ntiles = ((int64_t)by * bx + TC - 1) / TC;
+            const int ctas = (int)(220 * 1024 / L.total);
+            const unsigned grid_t = mt::grid_for(ntiles, 1, ctas < 1 ? 1 : (ctas > 8 ? 8 : ctas));
+            mt::ProfScope prof("k_interplevel_tile", stream);
+#define ILT_LAUNCH(T, INC)                                                                                  \
+    do {                                                                                                    \
+        MT_CUDA(cudaFuncSetAttribute(k_interplevel_tile<T, INC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)L.total));                                                        \
+        k_interplevel_tile<T, INC><<<grid_t, 256, L.total, s>>>(                                            \
+            p, nvar, vert, (int)nz, ny, nx, y0, x0, by, bx, levels, (int)nlev, levels_order, direction, rf,  \
+            TC, (int)L.w2, (int)L.lev, (int)L.kp, (int)L.mono, (int)L.col);                                 \
+    } while (0)
+            if (dtype == MT_F64) {
+                if (flags & MT_IL_INCLUSIVE) ILT_LAUNCH(double, true);
+                else ILT_LAUNCH(double, false);
+            } else {
+                if (flags & MT_IL_INCLUSIVE) ILT_LAUNCH(float, true);
+                else ILT_LAUNCH(float, false);
+            }
+#undef ILT_LAUNCH
+            MT_LAUNCH_CHECK();
+            return MT_OK;
+        }
+    }
+    const unsigned grid = mt::grid_for((int64_t)by * bx, 128, 16);
     mt::ProfScope prof("k_interplevel", stream);
 #define IL_LAUNCH(T, INC)                                                                          \
     k_interplevel<T, INC><<<grid, 128, 0, s>>>(p, nvar, vert, (int)nz, ny, nx, y0, x0, by, bx, levels, \

@@ -79,18 +79,44 @@ __device__ __forceinline__ unsigned long long absbits(double d)
     return (unsigned long long)__double_as_longlong(fabs(d));
 }
 
-// One fixed-point sweep: Tc <- step(T,P,qv,Tc_prev) where Tc_prev = T for the first sweep.
+// g[i] = log(A*0.622/P/qv) + (Cp/Rd)*log(T), the sweep-invariant part (thermo.cuh)
 __global__ void __launch_bounds__(256)
-k_tc_iter(const double *__restrict__ T, const double *__restrict__ P, const double *__restrict__ qv,
-          double *__restrict__ Tc, int64_t n, int iter, unsigned long long *__restrict__ maxbits)
+k_tc_prepare(const double *__restrict__ T, const double *__restrict__ P, const double *__restrict__ qv,
+             double *__restrict__ g, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        g[i] = Tc_g(__ldg(T + i), __ldg(P + i), __ldg(qv + i));
+}
+
+// One fixed-point sweep: Tc <- B/(g - a*log(Tc_prev)) where Tc_prev = T for the first sweep.
+// Two points per thread and iteration (16-byte loads/stores, two independent log/divide chains).
+__global__ void __launch_bounds__(256)
+k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__restrict__ Tc, int64_t n,
+          int iter, unsigned long long *__restrict__ maxbits, int vec_ok)
 {
     if (iter > 0 && __longlong_as_double((long long)maxbits[iter - 1]) < 0.1) return;  // converged
     unsigned long long m = 0ull;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+    const int64_t npair = vec_ok ? (n >> 1) : 0;  // vec_ok: all pointers 16-byte aligned
+    const double2 *__restrict__ T2 = reinterpret_cast<const double2 *>(T);
+    const double2 *__restrict__ g2 = reinterpret_cast<const double2 *>(g);
+    double2 *__restrict__ Tc2 = reinterpret_cast<double2 *>(Tc);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npair;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const double t = __ldg(T + i);
-        const double prev = iter == 0 ? t : Tc[i];
-        const double cur = Tc_step(t, __ldg(P + i), __ldg(qv + i), prev);
+        const double2 prev = iter == 0 ? __ldg(T2 + i) : Tc2[i];
+        const double2 gg = __ldg(g2 + i);
+        double2 cur;
+        cur.x = Tc_step_g(gg.x, prev.x);
+        cur.y = Tc_step_g(gg.y, prev.y);
+        Tc2[i] = cur;
+        const unsigned long long b0 = absbits(cur.x - prev.x), b1 = absbits(cur.y - prev.y);
+        m = b0 > m ? b0 : m;
+        m = b1 > m ? b1 : m;
+    }
+    for (int64_t i = 2 * npair + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {  // odd tail / unaligned fallback
+        const double prev = iter == 0 ? T[i] : Tc[i];
+        const double cur = Tc_step_g(g[i], prev);
         Tc[i] = cur;
         const unsigned long long b = absbits(cur - prev);
         m = b > m ? b : m;
@@ -111,7 +137,8 @@ __global__ void k_tc_count(unsigned long long *maxbits)
 // ---- fused cyl_td main pass: one read of T,p,qv(,qc,qr), every requested output, and the first
 //      Tc sweep.
 __global__ void __launch_bounds__(256)
-k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restrict__ maxbits)
+k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restrict__ maxbits,
+          double *__restrict__ gbuf)
 {
     unsigned long long m = 0ull;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -140,7 +167,9 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
         if (out.rho) __stcs(out.rho + i, rho(P, Tv));
         if (out.moist_dTdz) __stcs(out.moist_dTdz + i, moist_dTdz(T, qvs));
         if (out.Tc) {
-            const double cur = Tc_step(T, P, qv, T);
+            const double g = Tc_g(T, P, qv);
+            gbuf[i] = g;
+            const double cur = Tc_step_g(g, T);
             out.Tc[i] = cur;
             const unsigned long long b = absbits(cur - T);
             m = b > m ? b : m;
@@ -161,13 +190,14 @@ k_td_theta_e(const double *__restrict__ T, const double *__restrict__ P, const d
     }
 }
 
-int tc_tail(const double *T, const double *P, const double *qv, double *Tc, int64_t n,
-            unsigned long long *bits, int first_iter, cudaStream_t s)
+int tc_tail(const double *T, const double *g, double *Tc, int64_t n, unsigned long long *bits,
+            int first_iter, cudaStream_t s)
 {
-    const unsigned grid = mt::grid_for(n, 256, 8);
+    const unsigned grid = mt::grid_for((n + 1) / 2, 256, 8);
+    const int vec_ok = (((uintptr_t)T | (uintptr_t)g | (uintptr_t)Tc) % 16 == 0) ? 1 : 0;
     for (int it = first_iter; it < 10; ++it) {
         mt::ProfScope prof("k_tc_iter", (mt_stream_t)s);
-        k_tc_iter<<<grid, 256, 0, s>>>(T, P, qv, Tc, n, it, bits);
+        k_tc_iter<<<grid, 256, 0, s>>>(T, g, Tc, n, it, bits, vec_ok);
         MT_LAUNCH_CHECK();
     }
     k_tc_count<<<1, 1, 0, s>>>(bits);
@@ -207,7 +237,13 @@ int mt_calc_tc(const double *T, const double *P, const double *qv, double *Tc, i
     MT_REQUIRE(T && P && qv && Tc && scratch && n > 0, "mt_calc_tc: null pointer or empty array");
     cudaStream_t s = (cudaStream_t)stream;
     MT_CUDA(cudaMemsetAsync(scratch, 0, 16 * sizeof(double), s));
-    return tc_tail(T, P, qv, Tc, n, reinterpret_cast<unsigned long long *>(scratch), 0, s);
+    double *g = scratch + 16;
+    {
+        mt::ProfScope prof("k_tc_prepare", stream);
+        k_tc_prepare<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(T, P, qv, g, n);
+        MT_LAUNCH_CHECK();
+    }
+    return tc_tail(T, g, Tc, n, reinterpret_cast<unsigned long long *>(scratch), 0, s);
 }
 
 int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *scratch,
@@ -215,17 +251,17 @@ int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *s
 {
     MT_REQUIRE(in && out && in->T && in->p && in->qv && n > 0, "mt_cyl_td: T, p, qv are required");
     MT_REQUIRE(!out->Th_e || out->Tc, "mt_cyl_td: Th_e needs a Tc output buffer");
-    MT_REQUIRE(!out->Tc || scratch, "mt_cyl_td: Tc needs the 16-double scratch");
+    MT_REQUIRE(!out->Tc || scratch, "mt_cyl_td: Tc needs the (16 + n)-double scratch");
     cudaStream_t s = (cudaStream_t)stream;
     auto bits = reinterpret_cast<unsigned long long *>(scratch);
     if (out->Tc) MT_CUDA(cudaMemsetAsync(scratch, 0, 16 * sizeof(double), s));
     {
         mt::ProfScope prof("k_td_main", stream);
-        k_td_main<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits);
+        k_td_main<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits, scratch ? scratch + 16 : nullptr);
         MT_LAUNCH_CHECK();
     }
     if (out->Tc) {
-        int rc = tc_tail(in->T, in->p, in->qv, out->Tc, n, bits, 1, s);
+        int rc = tc_tail(in->T, scratch + 16, out->Tc, n, bits, 1, s);
         if (rc != MT_OK) return rc;
     }
     if (out->Th_e) {

@@ -169,8 +169,8 @@ class calc_thermaldynamic:
                 raise ValueError(f'unknown thermodynamic output {k!r}')
             bufs[k] = self._new()
             setattr(tout, k, bufs[k].data_ptr())
-        scratch = D.empty((16,))
         n = self._d('T').numel()
+        scratch = D.empty((16 + n,))
         _lib.check(_lib.load().mt_cyl_td(tin, tout, n, D.ptr(scratch), D.stream()), 'mt_cyl_td')
         for k, b in bufs.items():
             self._put(k, b)

@@ -90,7 +90,7 @@ class CylStepPipeline:
         self.td_out = {k: g._new() for k in self.td_names}
         self.dyn_names = list(dyn_outputs or [])
         self.dyn_out = {k: g._new(dtype=t.uint8 if k == "strain_region" else None) for k in self.dyn_names}
-        self.scratch = D.empty((16,))
+        self.scratch = D.empty((16 + self.n * g.Nz,))
         self.direction = -1
         if not resident:   # persistent device staging for the uploaded boxes
             shp = (self.nz, y1 - y0, x1 - x0)
