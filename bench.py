@@ -397,6 +397,9 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
         "k_interplevel_tile": 8.0 * box * (nz * (V + 1) + nlev * V),
         # 8*(L*N + L*U) per variable + the plan (32 B/point) once per variable slice
         "k_gather2d_lf": V * 8.0 * (nlev * n + nlev * U) + V * 32.0 * n,
+        "k_gather2d_lf_bulk": V * 8.0 * (nlev * n + nlev * U) + V * 32.0 * n,
+        # NaN fast path of calc_Tc: reads g, Tc; writes Tc (the remaining sweeps stay in registers)
+        "k_tc_rest_nan": 8.0 * NPTS * 3,
         # reads T,p,qv,qc,qr; writes 12 outputs (incl. the first Tc sweep) + the sweep-invariant g
         "k_td_main": 8.0 * NPTS * (5 + 13),
         # reads g, Tc; writes Tc
@@ -408,10 +411,15 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
         per = tot / cnt
         launches_per_step = cnt / steps
         eff_cnt = cnt
-        if name == "k_tc_iter":   # sweeps after convergence return at once: count only executed ones
+        nan_mode = "k_tc_rest_nan" in kern and kern["k_tc_rest_nan"][1] / kern["k_tc_rest_nan"][0] > 0.02
+        if name == "k_tc_iter" and not nan_mode:   # sweeps after convergence return at once
             eff_cnt = steps * max(tc_iters - 1, 1)
             per = tot / eff_cnt
         a = alg.get(name)
+        if name == "k_tc_iter" and nan_mode:
+            a = None   # every sweep was taken over by k_tc_rest_nan: these launches return at once
+        if name == "k_tc_rest_nan" and not nan_mode:
+            a = None
         rows.append({"kernel": name, "launches_per_step": launches_per_step, "ms_per_step": tot / steps,
                      "avg_ms_per_launch": per,
                      "achieved_gbs": (a / (per * 1e-3) / 1e9) if a else None, "alg_bytes_per_launch": a})
@@ -425,7 +433,8 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
             "peak_source": which, "unit": "GB/s",
             "frac": (top["achieved_gbs"] / peak) if top["achieved_gbs"] else None, "traffic": traffic,
             "unique_source_columns": U, "box_columns": box, "kernels": rows,
-            "step_alg_bytes": sum(alg[k] * (max(tc_iters - 1, 1) if k == "k_tc_iter" else 1) for k in alg),
+            "step_alg_bytes": sum(r["alg_bytes_per_launch"] * r["launches_per_step"] for r in rows
+                                  if r["alg_bytes_per_launch"]),
             "note": "per-launch CUDA events (mt_profile_*) over the same steps, re-run after the timed region"}
 
 

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256)
 k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__restrict__ Tc, int64_t n,
           int iter, unsigned long long *__restrict__ maxbits, int vec_ok)
 {
+    if (maxbits[14]) return;                                                            // k_tc_rest_nan did it
     if (iter > 0 && __longlong_as_double((long long)maxbits[iter - 1]) < 0.1) return;  // converged
     unsigned long long m = 0ull;
     const int64_t npair = vec_ok ? (n >> 1) : 0;  // vec_ok: all pointers 16-byte aligned
@@ -122,6 +123,42 @@ k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__
         m = b > m ? b : m;
     }
     block_max_to(m, maxbits + iter);
+}
+
+// NaN fast path.  If the max |diff| of sweep `first-1` is NaN, some point is NaN for good (a NaN
+// iterate stays NaN), so np.max stays NaN and the reference runs all 10 sweeps no matter what
+// (terrain-masked data).  The remaining sweeps are then certain and are done
+// in registers in ONE pass (read g, Tc; write Tc) instead of one HBM pass per sweep.
+__global__ void __launch_bounds__(256)
+k_tc_rest_nan(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, int first,
+              unsigned long long *__restrict__ maxbits, int vec_ok)
+{
+    const double prev_max = __longlong_as_double((long long)maxbits[first - 1]);
+    if (!(prev_max != prev_max)) return;  // not NaN: the per-sweep kernels decide
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int it = first; it < 10; ++it) maxbits[it] = maxbits[first - 1];  // NaN for k_tc_count
+        maxbits[14] = 1ull;
+    }
+    const int64_t npair = vec_ok ? (n >> 1) : 0;
+    const double2 *__restrict__ g2 = reinterpret_cast<const double2 *>(g);
+    double2 *__restrict__ Tc2 = reinterpret_cast<double2 *>(Tc);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npair;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double2 t = Tc2[i];
+        const double2 gg = __ldg(g2 + i);
+        for (int it = first; it < 10; ++it) {
+            t.x = Tc_step_g(gg.x, t.x);
+            t.y = Tc_step_g(gg.y, t.y);
+        }
+        Tc2[i] = t;
+    }
+    for (int64_t i = 2 * npair + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double t = Tc[i];
+        const double gg = g[i];
+        for (int it = first; it < 10; ++it) t = Tc_step_g(gg, t);
+        Tc[i] = t;
+    }
 }
 
 __global__ void k_tc_count(unsigned long long *maxbits)
@@ -195,6 +232,17 @@ int tc_tail(const double *T, const double *g, double *Tc, int64_t n, unsigned lo
 {
     const unsigned grid = mt::grid_for((n + 1) / 2, 256, 8);
     const int vec_ok = (((uintptr_t)T | (uintptr_t)g | (uintptr_t)Tc) % 16 == 0) ? 1 : 0;
+    if (first_iter == 0) {  // sweep 0 first: it decides whether the NaN fast path applies
+        mt::ProfScope prof("k_tc_iter", (mt_stream_t)s);
+        k_tc_iter<<<grid, 256, 0, s>>>(T, g, Tc, n, 0, bits, vec_ok);
+        MT_LAUNCH_CHECK();
+        first_iter = 1;
+    }
+    {
+        mt::ProfScope prof("k_tc_rest_nan", (mt_stream_t)s);
+        k_tc_rest_nan<<<grid, 256, 0, s>>>(g, Tc, n, first_iter, bits, vec_ok);
+        MT_LAUNCH_CHECK();
+    }
     for (int it = first_iter; it < 10; ++it) {
         mt::ProfScope prof("k_tc_iter", (mt_stream_t)s);
         k_tc_iter<<<grid, 256, 0, s>>>(T, g, Tc, n, it, bits, vec_ok);
