@@ -172,43 +172,75 @@ __global__ void k_tc_count(unsigned long long *maxbits)
 }
 
 // ---- fused cyl_td main pass: one read of T,p,qv(,qc,qr), every requested output, and the first
-//      Tc sweep.
+//      Tc sweep.  The kernel is FP64-pipe bound (ncu: fp64 pipe 47 %, dram 30 %), so the
+//      transcendental chains share their logarithms and avoid divisions where the result is a
+//      tolerance-class output (exp/log/pow already differ from NumPy by ulps):
+//        lP = log P, lT = log T, lq = log qv, lv = log vapor
+//        Th   = T*exp(kappa*(log 1e5 - lP))                      (T*(1e5/P)**kappa)
+//        g    = log(A*0.622) - lP - lq + (Cp/Rd)*lT              (log(A*0.622/P/qv) + a*log T)
+//        Td   : ln(es/611.2) = lv - log 611.2
+//      The pure-arithmetic outputs (vapor, Tv, rho) keep the reference's exact operation order.
+struct TdPoint {
+    double Th, es, qvs, vap, RH, Td, Th_es, Tv, rho, dTdz, g, Tc1;
+};
+
+__device__ __forceinline__ TdPoint td_point(double T, double P, double qv)
+{
+    constexpr double log_1e5 = 11.512925464970229;       // log(100000)
+    constexpr double log_A622 = 25.781840139430972;      // log(2.53e11*0.622)
+    constexpr double log_611_2 = 6.415424237852311;      // log(611.2)
+    TdPoint r;
+    const double lP = log(P), lT = log(T), lq = log(qv);
+    r.Th = T * exp(kappa * (log_1e5 - lP));
+    r.es = sat_vapor(T);
+    r.qvs = sat_qv_from_es(r.es, P);
+    r.vap = qv_to_vapor(P, qv);                           // exact class, :168
+    r.RH = r.vap / r.es;
+    const double lnes = log(r.vap) - log_611_2;
+    r.Td = 243.5 * lnes / (17.67 - lnes) + 273.15;
+    const double lq_T = (Lv / Cp) * r.qvs / T;            // Lv*qvs/Cp/T
+    r.Th_es = r.Th * exp(lq_T);
+    r.Tv = Tv_from_qv(T, qv);                             // exact class, :335
+    r.rho = rho(P, r.Tv);                                 // exact class, :364
+    const double a = Lv * r.qvs / (Rd * T);               // Lv*qvs/Rd/T
+    r.dTdz = -g * ((1 + a) / (Cp + a * (Lv * 0.622) / T));  // :486
+    r.g = log_A622 - lP - lq + CpRd * lT;
+    r.Tc1 = B / (r.g - CpRd * lT);                        // first sweep: Tc2 = T
+    return r;
+}
+
 __global__ void __launch_bounds__(256)
 k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restrict__ maxbits,
           double *__restrict__ gbuf)
 {
+    // one point per thread and iteration: 60 registers / 4 CTAs per SM measured 25 % faster than
+    // two points per thread (117 registers) -- profiles/experiments_r01.md
     unsigned long long m = 0ull;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const double T = __ldg(in.T + i), P = __ldg(in.p + i), qv = __ldg(in.qv + i);
-        const double Th = theta(T, P);
-        const double es = sat_vapor(T);
-        const double qvs = sat_qv_from_es(es, P);
-        const double vap = qv_to_vapor(P, qv);  // thermaldynamic_calculation.py:36-37
-        if (out.Th) __stcs(out.Th + i, Th);
-        if (out.vapor_s) __stcs(out.vapor_s + i, es);
-        if (out.qvs) __stcs(out.qvs + i, qvs);
-        if (out.vapor) __stcs(out.vapor + i, vap);
-        if (out.RH) __stcs(out.RH + i, vap / es);
-        if (out.Td) __stcs(out.Td + i, Td_from_vapor(vap));
-        if (out.Th_es) __stcs(out.Th_es + i, exp_factor(Th, qvs, T));
+        const TdPoint r = td_point(T, P, qv);
+        if (out.Th) __stcs(out.Th + i, r.Th);
+        if (out.vapor_s) __stcs(out.vapor_s + i, r.es);
+        if (out.qvs) __stcs(out.qvs + i, r.qvs);
+        if (out.vapor) __stcs(out.vapor + i, r.vap);
+        if (out.RH) __stcs(out.RH + i, r.RH);
+        if (out.Td) __stcs(out.Td + i, r.Td);
+        if (out.Th_es) __stcs(out.Th_es + i, r.Th_es);
         if (out.Th_v) {
             double ql = 0.0;  // :66-78: qc+qr, qc, qr or the default 0
             if (in.qc && in.qr) ql = __ldg(in.qc + i) + __ldg(in.qr + i);
             else if (in.qc) ql = __ldg(in.qc + i);
             else if (in.qr) ql = __ldg(in.qr + i);
-            __stcs(out.Th_v + i, theta_v(Th, qv, ql));
+            __stcs(out.Th_v + i, theta_v(r.Th, qv, ql));
         }
-        const double Tv = Tv_from_qv(T, qv);
-        if (out.Tv) __stcs(out.Tv + i, Tv);
-        if (out.rho) __stcs(out.rho + i, rho(P, Tv));
-        if (out.moist_dTdz) __stcs(out.moist_dTdz + i, moist_dTdz(T, qvs));
+        if (out.Tv) __stcs(out.Tv + i, r.Tv);
+        if (out.rho) __stcs(out.rho + i, r.rho);
+        if (out.moist_dTdz) __stcs(out.moist_dTdz + i, r.dTdz);
         if (out.Tc) {
-            const double g = Tc_g(T, P, qv);
-            gbuf[i] = g;
-            const double cur = Tc_step_g(g, T);
-            out.Tc[i] = cur;
-            const unsigned long long b = absbits(cur - T);
+            gbuf[i] = r.g;
+            out.Tc[i] = r.Tc1;
+            const unsigned long long b = absbits(r.Tc1 - T);
             m = b > m ? b : m;
         }
     }
