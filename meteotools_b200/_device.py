@@ -61,8 +61,17 @@ def to_device(a, dtype=np.float64):
         return a.contiguous()
     a = np.asarray(a)
     if dtype == np.float64 and a.dtype == np.float32:
-        return cast_f64(t.from_numpy(np.ascontiguousarray(a)).cuda())
-    return t.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+        return cast_f64(_from_numpy(np.ascontiguousarray(a)).cuda())
+    return _from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+def _from_numpy(a):
+    """torch.from_numpy without the 'array is not writable' warning: grid fields are handed out
+    as read-only views on purpose and are only ever READ here (H2D copy)."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch().from_numpy(a)
 
 
 def cast_f64(x):

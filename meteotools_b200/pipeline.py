@@ -196,3 +196,85 @@ class CylStepPipeline:
         for pool, nd in ((self.out3d, 3), (self.td_out, 3), (self.dyn_out, 3), (self.out2d, 2)):
             for k, v in pool.items():
                 self.g._put(k, v, nd)
+
+
+class LevelShardDyn:
+    """cyl_d / car_d of ONE time step on ONE level shard: ``stage_a()``, then the caller
+    exchanges one halo level of ``halo_fields`` with the neighbouring shards, then ``stage_b()``.
+
+    kind      "car" or "cyl"
+    local     dict name -> CUDA tensor (nz_own, nt, nr) C-order ("ZTR") with the shard's OWNED levels
+              of u, v, w, p, T, qv (, Th, qc, qr, qi, qs, qg, qh)
+    f2d       (nt, nr) Coriolis tensor or None
+    spacings  (dz, dt, dr)  i.e. (dz, dy, dx) or (dz, dtheta, dr)
+    shard     (lo, hi, halo_lo, halo_hi) from ``level_shard``
+    tables    cyl only: dict(r=, sin_t=, cos_t=) CUDA tensors
+    The one-sided FD2 formulas are used only at the global first / last level; everywhere else
+    stage B differentiates across the halo levels.
+    """
+
+    def __init__(self, kind, local, f2d, spacings, shard, nz_global, outputs, tables=None):
+        t = D.require_cuda()
+        self.lib, self.kind, self.outputs = _lib.load(), kind, list(outputs)
+        lo, hi, hlo, hhi = shard
+        self.hlo, self.hhi, self.nz_own = hlo, hhi, hi - lo
+        any_field = next(iter(local.values()))
+        nt, nr = int(any_field.shape[1]), int(any_field.shape[2])
+        nzl = self.nz_own + hlo + hhi
+
+        def padded(x):   # owned levels placed between the halo slots
+            buf = t.empty((nzl, nt, nr), dtype=t.float64, device="cuda")
+            buf[hlo:hlo + self.nz_own].copy_(x)
+            return buf
+        self.fields = {k: padded(v) for k, v in local.items()}
+        self._keep = (f2d, tables)
+        g = _lib.mt_grid_t()
+        g.nz, g.nt, g.nr, g.layout = nzl, nt, nr, _lib.MT_LAYOUT_ZTR
+        g.dz, g.dt, g.dr = (float(s) for s in spacings)
+        if kind == "cyl":
+            g.r, g.sin_t, g.cos_t = (tables[k].data_ptr() for k in ("r", "sin_t", "cos_t"))
+        g.halo_lo, g.halo_hi = hlo, hhi
+        g.is_bottom, g.is_top = int(lo == 0), int(hi == nz_global)
+        din = _lib.mt_dyn_in_t()
+        for k in ("u", "v", "w", "p", "T", "Th", "qv"):
+            setattr(din, k, self.fields[k].data_ptr() if k in self.fields else None)
+        din.f = f2d.data_ptr() if f2d is not None else None
+        hyd = [k for k in _lib.HYDRO if k in self.fields]
+        for i in range(6):
+            din.q[i] = self.fields[hyd[i]].data_ptr() if i < len(hyd) else None
+        names = _lib.CYL_D_OUT if kind == "cyl" else _lib.CAR_D_OUT
+        dout = (_lib.mt_cyl_d_out_t if kind == "cyl" else _lib.mt_car_d_out_t)()
+        self.outs = {}
+        stage_a_needed = ["Th_rho", "rho"] + (["vr", "vt"] if kind == "cyl" else [])
+        for k in list(dict.fromkeys(self.outputs + stage_a_needed)):
+            if k not in names:
+                raise ValueError(f"unknown output {k!r}")
+            self.outs[k] = t.empty((nzl, nt, nr), dtype=t.uint8 if k == "strain_region" else t.float64,
+                                   device="cuda")
+            setattr(dout, k, self.outs[k].data_ptr())
+        self._g, self._din, self._dout = g, din, dout
+        self._call = self.lib.mt_cyl_d if kind == "cyl" else self.lib.mt_car_d
+        # the z-differentiated fields: one halo level of each is exchanged between the stages
+        self.halo_fields = [self.outs["Th_rho"], self.fields["w"]] + \
+            ([self.outs["vr"], self.outs["vt"]] if kind == "cyl" else [self.fields["v"]])
+
+    def stage_a(self):
+        _lib.check(self._call(self._g, self._din, self._dout, _lib.MT_STAGE_A, D.stream()), "stage A")
+
+    def stage_b(self):
+        _lib.check(self._call(self._g, self._din, self._dout, _lib.MT_STAGE_B, D.stream()), "stage B")
+
+    def result(self):
+        return {k: self.outs[k][self.hlo:self.hlo + self.nz_own] for k in self.outputs}
+
+
+def dyn_level_sharded(kind, local, f2d, spacings, shard, nz_global, outputs, rank, world, tables=None,
+                      dist=None):
+    """Distributed form of ``LevelShardDyn``: stage A, NCCL halo exchange with rank+-1, stage B."""
+    job = LevelShardDyn(kind, local, f2d, spacings, shard, nz_global, outputs, tables)
+    job.stage_a()
+    if world > 1:
+        D.torch().cuda.current_stream().synchronize()
+        halo_exchange_levels(job.halo_fields, shard[2], shard[3], rank, world, dist)
+    job.stage_b()
+    return job.result()

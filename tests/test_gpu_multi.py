@@ -1,0 +1,68 @@
+"""Level-sharded cyl_d / car_d on ONE GPU: the shards of several ranks are emulated
+in one process (stage A everywhere, halo levels copied by hand exactly as
+pipeline.halo_exchange_levels would send them, stage B everywhere) and must reproduce the
+unsharded result bit for bit -- including the levels next to every shard boundary."""
+import numpy as np
+import pytest
+
+from conftest import assert_same
+from golden.make_golden import CAR, CAR_OUT, CYL, CYL_OUT
+
+pytestmark = pytest.mark.gpu
+
+
+def _emulate(kind, fields, f2d, spacings, outputs, world, tables=None):
+    import torch
+    from meteotools_b200.pipeline import LevelShardDyn, level_shard
+    nz = next(iter(fields.values())).shape[0]
+    jobs = []
+    for r in range(world):
+        shard = level_shard(nz, r, world)
+        local = {k: torch.from_numpy(v[shard[0]:shard[1]].copy()).cuda() for k, v in fields.items()}
+        jobs.append((shard, LevelShardDyn(kind, local, f2d, spacings, shard, nz, outputs, tables)))
+    for _, j in jobs:
+        j.stage_a()
+    for r, (shard, j) in enumerate(jobs):       # what halo_exchange_levels does, by hand
+        lo, hi, hlo, hhi = shard
+        for idx, f in enumerate(j.halo_fields):
+            if hlo:
+                nb = jobs[r - 1][1]
+                f[0].copy_(nb.halo_fields[idx][nb.hlo + nb.nz_own - 1])
+            if hhi:
+                nb = jobs[r + 1][1]
+                f[-1].copy_(nb.halo_fields[idx][nb.hlo])
+    for _, j in jobs:
+        j.stage_b()
+    res = [j.result() for _, j in jobs]
+    return {k: torch.cat([x[k] for x in res]).cpu().numpy() for k in outputs}
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_car_d_level_sharded(golden_grids, world):
+    import torch
+    g = golden_grids
+    fields = {k[len("g_car_"):]: v for k, v in g.items() if k.startswith("g_car_") and v.ndim == 3}
+    f2d = torch.from_numpy(g["g_car_f"]).cuda()
+    outs = [k for k in CAR_OUT if k not in ("Th",)]
+    got = _emulate("car", fields, f2d, (CAR["dz"], CAR["dy"], CAR["dx"]), outs, world)
+    ref = _emulate("car", fields, f2d, (CAR["dz"], CAR["dy"], CAR["dx"]), outs, 1)
+    for k in outs:
+        assert_same(got[k], ref[k], f"car {k} world={world}")
+    for k in ("zeta_r", "zeta_t", "div", "wind_speed"):      # and the reference itself
+        assert_same(got[k], g[f"o_car_{k}"], f"car {k} vs reference")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_cyl_d_level_sharded(golden_grids, world):
+    import torch
+    g = golden_grids
+    fields = {k[len("g_cyl_"):]: v for k, v in g.items() if k.startswith("g_cyl_") and v.ndim == 3}
+    f2d = torch.from_numpy(g["g_cyl_f"]).cuda()
+    r = np.arange(0, CYL["Nr"] * float(CYL["dr"]), float(CYL["dr"]))
+    th = np.arange(0, CYL["Ntheta"] * float(CYL["dtheta"]), float(CYL["dtheta"]))
+    tables = dict(r=torch.from_numpy(r).cuda(), sin_t=torch.from_numpy(np.sin(th)).cuda(),
+                  cos_t=torch.from_numpy(np.cos(th)).cuda())
+    outs = ["zeta_r", "zeta_t", "zeta_z", "div", "vr", "vt", "shear_deform", "kinetic_energy"]
+    got = _emulate("cyl", fields, f2d, (CYL["dz"], CYL["dtheta"], CYL["dr"]), outs, world, tables)
+    for k in outs:
+        assert_same(got[k], g[f"o_cyl_{k}"], f"cyl {k} world={world}")
