@@ -12,6 +12,8 @@
 // Stages are separately launchable so that a level-sharded multi-GPU run can exchange the one
 // halo level of the z-differentiated stage-A fields between them.
 // Every expression keeps the reference's order of evaluation (bit-exact for pure arithmetic).
+#include <type_traits>
+
 #include "fd.cuh"
 #include "thermo.cuh"
 
@@ -129,125 +131,210 @@ struct StageBOut {
     uint8_t *strain_region;
 };
 
-template <int LAYOUT, bool CYL>
-__global__ void __launch_bounds__(256)
-k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o)
+// Stage B marches along the SLOWEST memory axis (z for "ZTR", theta for "TRZ"): one thread per
+// position of the (contiguous) plane keeps the previous / current / next plane values of the four
+// differentiated fields in registers, so every plane is read from HBM once even when a plane is
+// far larger than the L2 (S5: 32 MB per field and level); the two in-plane directions come from
+// neighbouring threads' lines through L1.  The march axis is cut into segments (grid.y) only to
+// create enough threads for small planes (S3: 18 000 positions x 360 theta).
+struct Roll {
+    double p, c, n;
+};
+
+// FD2 along the march axis from the rolling registers; `far(k)` loads element k of the axis and
+// is needed only by the one-sided formulas at the global ends (differential.py:32,34).
+template <class Far>
+__device__ __forceinline__ double dmarch(const Roll &r, int i, int n, bool first, bool last, double delta,
+                                         Far far)
 {
-    const int64_t total = (int64_t)L.nz * L.nt * L.nr;
-    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total;
-         m += (int64_t)gridDim.x * blockDim.x) {
-        int iz, it, ir;
-        L.decode(m, iz, it, ir);
-        if (iz < g.own_lo || iz >= g.own_hi) continue;
-        const int nz = L.nz, nt = L.nt, nr = L.nr;
-        const int64_t sz = L.sz, st = L.st, sr = L.sr;
-        // axis accessors: element j along one axis through the point m
-#define AX_Z(F) [&](int k) { return __ldg((F) + m + (int64_t)(k - iz) * sz); }
-#define AX_T(F) [&](int k) { return __ldg((F) + m + (int64_t)(k - it) * st); }
-#define AX_R(F) [&](int k) { return __ldg((F) + m + (int64_t)(k - ir) * sr); }
-        const bool want_zr = o.zeta_r || o.PV;
-        const bool want_zt = o.zeta_t || o.PV;
-        const bool want_zz = o.zeta_z || o.abs_zeta_z || o.PV || o.filamentation_time || o.strain_region;
-        const bool want_def = o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
-        const bool want_div = o.div_hori || o.div;
-        double zeta_r = 0, zeta_t = 0, zeta_z = 0, abs_zz = 0;
+    if (i == 0 && first) return (-3 * r.c + 4 * r.n - far(2)) / 2 / delta;
+    if (i == n - 1 && last) return (3 * r.c - 4 * r.p + far(n - 3)) / 2 / delta;
+    return (r.n - r.p) / 2 / delta;
+}
+
+// SHELL = false: the marching kernel proper, INTERIOR points only (centred differences, no
+//                 branches, modest register count);
+// SHELL = true:  one thread per point of the outermost shell (global first / last index of any
+//                 axis), general body with the one-sided formulas; planes are loaded directly.
+template <int LAYOUT, bool CYL, bool SHELL>
+__global__ void __launch_bounds__(128, SHELL ? 4 : 6)
+k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
+{
+    constexpr bool ZTR = LAYOUT == MT_LAYOUT_ZTR;
+    const int nz = L.nz, nt = L.nt, nr = L.nr;
+    const int n0 = ZTR ? nz : nt;   // march axis (slowest in memory)
+    const int n2 = ZTR ? nr : nz;   // contiguous axis
+    const int64_t plane = (int64_t)(ZTR ? nt : nr) * n2;
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= plane) return;
+    const int i1 = (int)(p / n2), i2 = (int)(p - (int64_t)i1 * n2);
+    int m_lo = 0, m_hi = n0;
+    bool first = true, last = true;
+    if (ZTR) {  // a level shard marches over its owned levels and reads the halo levels
+        m_lo = g.own_lo, m_hi = g.own_hi, first = g.bottom, last = g.top;
+    } else if (i2 < g.own_lo || i2 >= g.own_hi) {
+        return;  // TRZ: z is the contiguous axis; halo levels produce no output
+    }
+    const int s_lo = m_lo + (int)blockIdx.y * (SHELL ? 1 : seg_len);
+    const int s_hi = min(m_hi, s_lo + (SHELL ? 1 : seg_len));
+    if (s_lo >= s_hi) return;
+    if (SHELL) {  // keep only the shell: most threads leave here
+        const int iz = ZTR ? s_lo : i2, it = ZTR ? i1 : s_lo, ir = ZTR ? i2 : i1;
+        const bool z_edge = (iz == 0 && g.bottom) || (iz == nz - 1 && g.top);
+        if (!z_edge && it > 0 && it < nt - 1 && ir > 0 && ir < nr - 1) return;
+    }
+
+    const bool want_zr = o.zeta_r || o.PV;
+    const bool want_zt = o.zeta_t || o.PV;
+    const bool want_zz = o.zeta_z || o.abs_zeta_z || o.PV || o.filamentation_time || o.strain_region;
+    const bool want_def = o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
+    const bool want_div = o.div_hori || o.div;
+    const bool use_ab = want_zr || want_zt || want_zz || want_def || want_div || o.agradient_force;
+    const bool use_w = in.w && (want_zr || want_zt || o.div);
+    const bool use_t = o.PV != nullptr;
+
+    int64_t m = (int64_t)s_lo * plane + p;
+    Roll ra = {0, 0, 0}, rb = {0, 0, 0}, rw = {0, 0, 0}, rt = {0, 0, 0};
+    auto prime = [&](const double *F, Roll &r) {
+        r.n = __ldg(F + m);
+        r.c = s_lo > 0 ? __ldg(F + m - plane) : 0.0;
+    };
+    if (use_ab) prime(in.a, ra), prime(in.b, rb);
+    if (use_w) prime(in.w, rw);
+    if (use_t) prime(in.thr, rt);
+
+    for (int i0 = s_lo; i0 < s_hi; ++i0, m += plane) {
+        auto roll = [&](const double *F, Roll &r) {
+            r.p = r.c, r.c = r.n;
+            r.n = (i0 + 1 < n0) ? __ldg(F + m + plane) : 0.0;
+        };
+        if (use_ab) roll(in.a, ra), roll(in.b, rb);
+        if (use_w) roll(in.w, rw);
+        if (use_t) roll(in.thr, rt);
+        const int iz = ZTR ? i0 : i2, it = ZTR ? i1 : i0, ir = ZTR ? i2 : i1;
+        const int64_t sr = ZTR ? 1 : nz;
         const double rr = CYL ? __ldg(g.r + ir) : 1.0;
-        double da_dt = 0, db_dt = 0;  // d(vr|u)/dtheta|dy , d(vt|v)/dtheta|dy
-        if (want_zz || want_def || want_div) {
-            da_dt = mt::fd2(AX_T(in.a), it, nt, g.dt);
-            db_dt = mt::fd2(AX_T(in.b), it, nt, g.dt);
-        }
-        double db_dz = 0;
-        if (want_zr || (!CYL && want_zt)) db_dz = mt::fd2_shard(AX_Z(in.b), iz, nz, g.dz, g.bottom, g.top);
-        if (want_zr) {
-            const double dw_dt = mt::fd2(AX_T(in.w), it, nt, g.dt);
-            // cyl :387-388  FD2(w,dtheta,1)/r - FD2(vt,dz,0) ; car :250  FD2(w,dy,1) - FD2(v,dz,0)
-            zeta_r = CYL ? dw_dt / rr - db_dz : dw_dt - db_dz;
-            if (o.zeta_r) __stcs(o.zeta_r + m, zeta_r);
-        }
-        if (want_zt) {
-            const double dw_dr = mt::fd2(AX_R(in.w), ir, nr, g.dr);
-            if (CYL) {
-                const double da_dz = mt::fd2_shard(AX_Z(in.a), iz, nz, g.dz, g.bottom, g.top);
-                zeta_t = da_dz - dw_dr;  // :389-390
-            } else {
-                zeta_t = db_dz - dw_dr;  // cartesian_grid.py:251 (sic: v, not u)
+        // INTERIOR points (all but the outermost shell) only ever need centred differences: they
+        // take a branch-free instantiation of the body; the shell takes the general one with the
+        // one-sided formulas.  Same expressions, same order of evaluation in both.
+        auto body = [&](auto interior_tag) {
+            constexpr bool IN = decltype(interior_tag)::value;
+            auto dz = [&](const double *F, const Roll &r) -> double {
+                if (ZTR) {
+                    if (IN) return (r.n - r.p) / 2 / g.dz;
+                    return dmarch(r, i0, n0, first, last, g.dz, [&](int k) { return __ldg(F + p + (int64_t)k * plane); });
+                }
+                if (IN) return (__ldg(F + m + 1) - __ldg(F + m - 1)) / 2 / g.dz;
+                return mt::fd2_shard([&](int k) { return __ldg(F + m + (k - iz)); }, iz, nz, g.dz, g.bottom, g.top);
+            };
+            auto dt = [&](const double *F, const Roll &r) -> double {
+                if (ZTR) {
+                    if (IN) return (__ldg(F + m + nr) - __ldg(F + m - nr)) / 2 / g.dt;
+                    return mt::fd2([&](int k) { return __ldg(F + m + (int64_t)(k - it) * nr); }, it, nt, g.dt);
+                }
+                if (IN) return (r.n - r.p) / 2 / g.dt;
+                return dmarch(r, i0, n0, true, true, g.dt, [&](int k) { return __ldg(F + p + (int64_t)k * plane); });
+            };
+            auto dr = [&](const double *F) -> double {
+                if (IN) return (__ldg(F + m + sr) - __ldg(F + m - sr)) / 2 / g.dr;
+                return mt::fd2([&](int k) { return __ldg(F + m + (int64_t)(k - ir) * sr); }, ir, nr, g.dr);
+            };
+            // FD2 along r of  F * r  (vt*r, :391) and of  r * F  (r*vr, :408)
+            auto dr_times_r = [&](const double *F, bool r_first) -> double {
+                auto v = [&](int k) {
+                    const double fv = __ldg(F + m + (int64_t)(k - ir) * sr), rk = __ldg(g.r + k);
+                    return r_first ? rk * fv : fv * rk;
+                };
+                if (IN) return (v(ir + 1) - v(ir - 1)) / 2 / g.dr;
+                return mt::fd2(v, ir, nr, g.dr);
+            };
+
+            double zeta_r = 0, zeta_t = 0, zeta_z = 0, abs_zz = 0;
+            double da_dt = 0, db_dt = 0;  // d(vr|u)/dtheta|dy , d(vt|v)/dtheta|dy
+            if (want_zz || want_def || want_div) {
+                da_dt = dt(in.a, ra);
+                db_dt = dt(in.b, rb);
             }
-            if (o.zeta_t) __stcs(o.zeta_t + m, zeta_t);
-        }
-        double da_dr = 0, db_dr = 0;
-        if (!CYL && (want_zz || want_def || want_div)) {
-            da_dr = mt::fd2(AX_R(in.a), ir, nr, g.dr);
-            db_dr = mt::fd2(AX_R(in.b), ir, nr, g.dr);
-        }
-        if (want_zz) {
-            if (CYL) {
-                auto vt_r = [&](int k) { return __ldg(in.b + m + (int64_t)(k - ir) * sr) * __ldg(g.r + k); };
-                zeta_z = mt::fd2(vt_r, ir, nr, g.dr) / rr - da_dt / rr;  // :391-392
-            } else {
-                zeta_z = db_dr - da_dt;  // :252 FD2(v,dx,2) - FD2(u,dy,1)
+            double db_dz = 0;
+            if (want_zr || (!CYL && want_zt)) db_dz = dz(in.b, rb);
+            if (want_zr) {
+                const double dw_dt = dt(in.w, rw);
+                // cyl :387-388  FD2(w,dtheta,1)/r - FD2(vt,dz,0) ; car :250  FD2(w,dy,1) - FD2(v,dz,0)
+                zeta_r = CYL ? dw_dt / rr - db_dz : dw_dt - db_dz;
+                if (o.zeta_r) __stcs(o.zeta_r + m, zeta_r);
             }
-            if (o.zeta_z) __stcs(o.zeta_z + m, zeta_z);
-            if (o.abs_zeta_z || o.PV) {
-                abs_zz = zeta_z + __ldg(in.f + (int64_t)it * nr + ir);  // :400
-                if (o.abs_zeta_z) __stcs(o.abs_zeta_z + m, abs_zz);
+            if (want_zt) {
+                const double dw_dr = dr(in.w);
+                if (CYL) zeta_t = dz(in.a, ra) - dw_dr;  // :389-390
+                else zeta_t = db_dz - dw_dr;             // cartesian_grid.py:251 (sic: v, not u)
+                if (o.zeta_t) __stcs(o.zeta_t + m, zeta_t);
             }
-        }
-        if (want_div) {
-            double dh;
-            if (CYL) {
-                auto r_vr = [&](int k) { return __ldg(g.r + k) * __ldg(in.a + m + (int64_t)(k - ir) * sr); };
-                dh = mt::fd2(r_vr, ir, nr, g.dr) / rr + db_dt / rr;  // :408-409
-            } else {
-                dh = da_dr + db_dt;  // :266-267
+            double da_dr = 0, db_dr = 0;
+            if (!CYL && (want_zz || want_def || want_div)) {
+                da_dr = dr(in.a);
+                db_dr = dr(in.b);
             }
-            if (o.div_hori) __stcs(o.div_hori + m, dh);
-            if (o.div) __stcs(o.div + m, dh + mt::fd2_shard(AX_Z(in.w), iz, nz, g.dz, g.bottom, g.top));
-        }
-        if (o.PV) {
-            const double dthr_dr = mt::fd2(AX_R(in.thr), ir, nr, g.dr);
-            const double dthr_dt = mt::fd2(AX_T(in.thr), it, nt, g.dt);
-            const double dthr_dz = mt::fd2_shard(AX_Z(in.thr), iz, nz, g.dz, g.bottom, g.top);
-            const double r_part = zeta_r * dthr_dr;                                  // :463 / :319
-            const double t_part = CYL ? zeta_t * dthr_dt / rr : zeta_t * dthr_dt;    // :464-465 / :320
-            const double z_part = abs_zz * dthr_dz;                                  // :466 / :321
-            __stcs(o.PV + m, (r_part + t_part + z_part) / __ldg(in.rho + m));
-        }
-        if (want_def) {
-            double sh, stc;
-            if (CYL) {
-                const double vr = __ldg(in.a + m), vt = __ldg(in.b + m);
-                const double dvr_dr = mt::fd2(AX_R(in.a), ir, nr, g.dr);
-                const double dvt_dr = mt::fd2(AX_R(in.b), ir, nr, g.dr);
-                sh = dvr_dr - vr / rr - db_dt / rr;   // :490-491
-                stc = dvt_dr - vt / rr + da_dt / rr;  // :492-493
-            } else {
-                sh = da_dr - db_dt;   // :344-345 FD2(u,dx) - FD2(v,dy)
-                stc = db_dr + da_dt;  // :346-347 FD2(v,dx) + FD2(u,dy)
+            if (want_zz) {
+                if (CYL) zeta_z = dr_times_r(in.b, false) / rr - da_dt / rr;  // :391-392
+                else zeta_z = db_dr - da_dt;                                   // :252 FD2(v,dx,2) - FD2(u,dy,1)
+                if (o.zeta_z) __stcs(o.zeta_z + m, zeta_z);
+                if (o.abs_zeta_z || o.PV) {
+                    abs_zz = zeta_z + __ldg(in.f + (int64_t)it * nr + ir);  // :400
+                    if (o.abs_zeta_z) __stcs(o.abs_zeta_z + m, abs_zz);
+                }
             }
-            if (o.shear_deform) __stcs(o.shear_deform + m, sh);
-            if (o.stretch_deform) __stcs(o.stretch_deform + m, stc);
-            if (o.filamentation_time || o.strain_region) {
-                const double s2 = sh * sh + stc * stc, z2 = zeta_z * zeta_z;
-                const bool strain = s2 > z2;  // :504-505
-                if (o.strain_region) o.strain_region[m] = strain ? 1 : 0;
-                if (o.filamentation_time)
-                    __stcs(o.filamentation_time + m, strain ? 2 * (1.0 / sqrt(s2 - z2)) : inf_f64());  // :501-508, x**-0.5 as 1/sqrt(x): <= 1 ulp
+            if (want_div) {
+                double dh;
+                if (CYL) dh = dr_times_r(in.a, true) / rr + db_dt / rr;  // :408-409
+                else dh = da_dr + db_dt;                                  // :266-267
+                if (o.div_hori) __stcs(o.div_hori + m, dh);
+                if (o.div) __stcs(o.div + m, dh + dz(in.w, rw));
             }
-        }
-        if (CYL && (o.radial_PG_force || o.agradient_force)) {
-            const double pg = -mt::fd2(AX_R(in.p), ir, nr, g.dr) / __ldg(in.rho + m);  // :343
-            if (o.radial_PG_force) __stcs(o.radial_PG_force + m, pg);
-            if (o.agradient_force) {
-                const double vt = __ldg(in.b + m);
-                const double cor = __ldg(in.f + (int64_t)it * nr + ir) * vt;  // :341
-                const double cen = vt * vt / rr;                             // :342
-                __stcs(o.agradient_force + m, cor + cen + pg);               // :344-346
+            if (o.PV) {
+                const double dthr_dr = dr(in.thr);
+                const double dthr_dt = dt(in.thr, rt);
+                const double dthr_dz = dz(in.thr, rt);
+                const double r_part = zeta_r * dthr_dr;                                  // :463 / :319
+                const double t_part = CYL ? zeta_t * dthr_dt / rr : zeta_t * dthr_dt;    // :464-465 / :320
+                const double z_part = abs_zz * dthr_dz;                                  // :466 / :321
+                __stcs(o.PV + m, (r_part + t_part + z_part) / __ldg(in.rho + m));
             }
+            if (want_def) {
+                double sh, stc;
+                if (CYL) {
+                    sh = dr(in.a) - ra.c / rr - db_dt / rr;   // :490-491
+                    stc = dr(in.b) - rb.c / rr + da_dt / rr;  // :492-493
+                } else {
+                    sh = da_dr - db_dt;   // :344-345 FD2(u,dx) - FD2(v,dy)
+                    stc = db_dr + da_dt;  // :346-347 FD2(v,dx) + FD2(u,dy)
+                }
+                if (o.shear_deform) __stcs(o.shear_deform + m, sh);
+                if (o.stretch_deform) __stcs(o.stretch_deform + m, stc);
+                if (o.filamentation_time || o.strain_region) {
+                    const double s2 = sh * sh + stc * stc, z2 = zeta_z * zeta_z;
+                    const bool strain = s2 > z2;  // :504-505
+                    if (o.strain_region) o.strain_region[m] = strain ? 1 : 0;
+                    if (o.filamentation_time)  // :501-508, x**-0.5 as 1/sqrt(x): <= 1 ulp
+                        __stcs(o.filamentation_time + m, strain ? 2 * (1.0 / sqrt(s2 - z2)) : inf_f64());
+                }
+            }
+            if (CYL && (o.radial_PG_force || o.agradient_force)) {
+                const double pg = -dr(in.p) / __ldg(in.rho + m);  // :343
+                if (o.radial_PG_force) __stcs(o.radial_PG_force + m, pg);
+                if (o.agradient_force) {
+                    const double vt = rb.c;
+                    const double cor = __ldg(in.f + (int64_t)it * nr + ir) * vt;  // :341
+                    const double cen = vt * vt / rr;                             // :342
+                    __stcs(o.agradient_force + m, cor + cen + pg);               // :344-346
+                }
+            }
+        };
+        if (SHELL) {
+            body(std::false_type{});
+        } else {
+            const bool z_edge = (iz == 0 && g.bottom) || (iz == nz - 1 && g.top);
+            if (!z_edge && it > 0 && it < nt - 1 && ir > 0 && ir < nr - 1) body(std::true_type{});
         }
-#undef AX_Z
-#undef AX_T
-#undef AX_R
     }
 }
 
@@ -353,10 +440,28 @@ int run_sets(const mt_grid_t *g, const mt_dyn_in_t *in, const StageAOut &a, cons
     }
     if ((stages & 2) && need_b) {
         mt::ProfScope prof(CYL ? "k_stage_b_cyl" : "k_stage_b_car", (mt_stream_t)s);
-        if (g->layout == MT_LAYOUT_ZTR)
-            k_stage_b<MT_LAYOUT_ZTR, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_ZTR>((int)g->nz, (int)g->nt, (int)g->nr), p, bi, bo);
-        else
-            k_stage_b<MT_LAYOUT_TRZ, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_TRZ>((int)g->nz, (int)g->nt, (int)g->nr), p, bi, bo);
+        const bool ztr = g->layout == MT_LAYOUT_ZTR;
+        const int64_t plane = ztr ? g->nt * g->nr : g->nr * g->nz;
+        const int64_t n_march = ztr ? (g->nz - g->halo_lo - g->halo_hi) : g->nt;
+        // enough segments of the march axis for ~2 full waves of 128-thread CTAs
+        int64_t want_threads = (int64_t)mt::sm_count() * 2048 * 2;
+        int64_t nseg = (want_threads + plane - 1) / plane;
+        if (nseg > n_march / 4) nseg = n_march / 4;
+        if (nseg < 1) nseg = 1;
+        const int seg_len = (int)((n_march + nseg - 1) / nseg);
+        dim3 gridb((unsigned)((plane + 127) / 128), (unsigned)((n_march + seg_len - 1) / seg_len));
+        dim3 grids((unsigned)((plane + 127) / 128), (unsigned)n_march);
+        if (ztr) {
+            Lay<MT_LAYOUT_ZTR> lay((int)g->nz, (int)g->nt, (int)g->nr);
+            k_stage_b<MT_LAYOUT_ZTR, CYL, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);
+            MT_LAUNCH_CHECK();
+            k_stage_b<MT_LAYOUT_ZTR, CYL, true><<<grids, 128, 0, s>>>(lay, p, bi, bo, 1);
+        } else {
+            Lay<MT_LAYOUT_TRZ> lay((int)g->nz, (int)g->nt, (int)g->nr);
+            k_stage_b<MT_LAYOUT_TRZ, CYL, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);
+            MT_LAUNCH_CHECK();
+            k_stage_b<MT_LAYOUT_TRZ, CYL, true><<<grids, 128, 0, s>>>(lay, p, bi, bo, 1);
+        }
         MT_LAUNCH_CHECK();
     }
     return MT_OK;
