@@ -397,7 +397,9 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
         "k_interplevel_tile": 8.0 * box * (nz * (V + 1) + nlev * V),
         # 8*(L*N + L*U) per variable + the plan (32 B/point) once per variable slice
         "k_gather2d_lf": V * 8.0 * (nlev * n + nlev * U) + V * 32.0 * n,
-        "k_gather2d_lf_bulk": V * 8.0 * (nlev * n + nlev * U) + V * 32.0 * n,
+        # fused set_data (SURVEY 8d formula B): touched source columns of V fields + the coordinate,
+        # outputs, plan
+        "k_setdata_fused": 8.0 * nz * U * (V + 1) + 8.0 * nlev * n * V + 32.0 * n,
         # NaN fast path of calc_Tc: reads g, Tc; writes Tc (the remaining sweeps stay in registers)
         "k_tc_rest_nan": 8.0 * NPTS * 3,
         # reads T,p,qv,qc,qr; writes 12 outputs (incl. the first Tc sweep) + the sweep-invariant g

@@ -166,6 +166,22 @@ int mt_setdata(const void *const *fields, int nvar, const void *vert, int dtype,
                int64_t n, const int32_t *hgt_idx, double *const *out, int64_t o_lev, int64_t o_n,
                int flags, void *workspace, int64_t workspace_bytes, mt_stream_t stream);
 
+/* Fully fused variant of mt_setdata for level-fastest outputs (out[v][i*o_n + lev]): one kernel,
+ * the level-interpolated columns stay in shared memory.  The caller supplies, once per plan, the
+ * targets bucketed by source tile: `order` (n_valid target indices sorted by tile) and `items`
+ * (nitems x 4 int32: tile_x, tile_y in full-source indices, start into `order`, count <= 128);
+ * a target belongs to the tile that contains its (x0, y0) corner, tiles are tile_w x tile_h cells
+ * (16x4 or 16x2).  `nflagged` = number of NaN / sentinel targets (they only get the fill value).
+ * `counter`: one int32 of device scratch (work-item counter).  fields/vert describe the uploaded
+ * region exactly as in mt_setdata. */
+int mt_setdata_fused(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz,
+                     int64_t ny, int64_t nx, int64_t org_y, int64_t org_x, const double *levels,
+                     int64_t nlev, int direction, const int32_t *plan_ix, const double *plan_w,
+                     int64_t n, const int32_t *order, const int32_t *items, int64_t nitems,
+                     int tile_w, int tile_h, int64_t nflagged, const int32_t *hgt_idx,
+                     double *const *out, int64_t o_n, int flags, int32_t *counter,
+                     mt_stream_t stream);
+
 /* terrain index of the cylindrical grid (cylindrical_grid.py:141-170): hgt (nt x nr, C-order)
  * -> hgt_idx int32 incl. the edge/corner fix-up.  Cartesian mask (cartesian_grid.py:127-136):
  * var[k,j,i] = NaN where z[k] <= hgt[j,i]. */

@@ -103,6 +103,9 @@ _SIGS = {
     "mt_setdata": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                            c_dbl, c_dbl, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_vp,
                            c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_i64, c_vp]),
+    "mt_setdata_fused": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                 c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_vp, c_vp,
+                                 c_i64, c_int, c_vp, c_vp]),
     "mt_terrain_index_cyl": (c_int, [c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_vp]),
     "mt_terrain_mask_cyl": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "mt_terrain_mask_car": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),

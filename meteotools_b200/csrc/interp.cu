@@ -74,7 +74,7 @@ struct VarPtrs {
 // Layer-fastest source  src[(y*lenx_s + x)*L + l]  (generic s_y, s_x, s_l == 1) and layer-fastest
 // output out[i*L + l] (o_l == 1, o_n == L or any).  One warp per point; lane handles VEC layers.
 // Optional terrain mask: hgt_idx[i] > l  ->  NaN  (cylindrical_grid.py:171-181).
-template <int VEC, int PPW>
+template <int VEC>
 __global__ void __launch_bounds__(256)
 k_gather2d_lf(VarPtrs vp, int layers, int64_t s_y, int64_t s_x, const int4 *__restrict__ pix,
               const double2 *__restrict__ pw, const double *__restrict__ xloc,
@@ -85,73 +85,62 @@ k_gather2d_lf(VarPtrs vp, int layers, int64_t s_y, int64_t s_x, const int4 *__re
     const int warps_per_block = blockDim.x >> 5;
     const double *__restrict__ src = vp.src[blockIdx.y];
     double *__restrict__ out = vp.out[blockIdx.y];
-    // PPW points in flight per warp (4*PPW independent 16-byte gathers per lane); PPW = 1 measured
-    // best (profiles/experiments_r01.md)
+    // targets are dealt round-robin over the grid, so that the output rows of a CTA's eight warps
+    // form one contiguous 3840-byte run (sequential output order measured faster than any
+    // source-locality order: profiles/experiments_r01.md)
     const int64_t stride = (int64_t)gridDim.x * warps_per_block;
-    const int64_t i_begin = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5);
-    for (int64_t i0 = i_begin; i0 < n; i0 += PPW * stride) {
-        int4 ix[PPW];
-        double2 w[PPW];
-        int terrain[PPW];
-        bool live[PPW];
-#pragma unroll
-        for (int q = 0; q < PPW; ++q) {
-            const int64_t i = i0 + q * stride;
-            live[q] = i < n;
-            if (!live[q]) continue;
-            if (pix) {
-                ix[q] = pix[i];
-                w[q] = pw[i];
-            } else {
-                plan2d_point(xloc[i], yloc[i], dx, dy, lenx, leny, ix[q], w[q]);
-            }
-            terrain[q] = hgt_idx ? hgt_idx[i] : 0;
-        }
-        if (VEC == 2) {
-            for (int l = lane * 2; l < layers; l += 64) {
-                double2 a[PPW], b[PPW], c[PPW], d[PPW];
-#pragma unroll
-                for (int q = 0; q < PPW; ++q) {
-                    if (!live[q] || ix[q].x < 0) continue;
-                    const double *row0 = src + ix[q].z * s_y + l, *row1 = src + ix[q].w * s_y + l;
-                    a[q] = *reinterpret_cast<const double2 *>(row0 + ix[q].x * s_x);
-                    b[q] = *reinterpret_cast<const double2 *>(row0 + ix[q].y * s_x);
-                    c[q] = *reinterpret_cast<const double2 *>(row1 + ix[q].x * s_x);
-                    d[q] = *reinterpret_cast<const double2 *>(row1 + ix[q].y * s_x);
-                }
-#pragma unroll
-                for (int q = 0; q < PPW; ++q) {
-                    if (!live[q]) continue;
-                    double2 r;
-                    if (ix[q].x < 0) {
-                        r.x = r.y = (ix[q].x == -1) ? MT_SENTINEL : nan_f64();
-                    } else {
-                        r.x = bilerp(a[q].x, b[q].x, c[q].x, d[q].x, w[q].x, w[q].y);
-                        r.y = bilerp(a[q].y, b[q].y, c[q].y, d[q].y, w[q].x, w[q].y);
-                        if (terrain[q] > l) r.x = nan_f64();
-                        if (terrain[q] > l + 1) r.y = nan_f64();
-                    }
-                    __stcs(reinterpret_cast<double2 *>(out + (i0 + q * stride) * o_n + l), r);
-                }
-            }
+    int64_t i = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5);
+    if (i >= n) return;
+    auto load_plan = [&](int64_t k, int4 &ix, double2 &w, int &terrain) {
+        if (pix) {
+            ix = pix[k];
+            w = pw[k];
         } else {
-            for (int l = lane; l < layers; l += 32) {
-#pragma unroll
-                for (int q = 0; q < PPW; ++q) {
-                    if (!live[q]) continue;
-                    double r;
-                    if (ix[q].x < 0) {
-                        r = (ix[q].x == -1) ? MT_SENTINEL : nan_f64();
-                    } else {
-                        const double *row0 = src + ix[q].z * s_y + l, *row1 = src + ix[q].w * s_y + l;
-                        r = bilerp(row0[ix[q].x * s_x], row0[ix[q].y * s_x], row1[ix[q].x * s_x],
-                                   row1[ix[q].y * s_x], w[q].x, w[q].y);
-                        if (terrain[q] > l) r = nan_f64();
-                    }
-                    __stcs(out + (i0 + q * stride) * o_n + l, r);
+            plan2d_point(xloc[k], yloc[k], dx, dy, lenx, leny, ix, w);
+        }
+        terrain = hgt_idx ? hgt_idx[k] : 0;
+    };
+    int4 ix;
+    double2 w;
+    int terrain;
+    load_plan(i, ix, w, terrain);
+    while (i < n) {
+        // software pipeline: the next point's plan entry is requested before this point's four
+        // corner gathers, so an iteration costs one memory round trip instead of two
+        const int64_t inext = i + stride;
+        int4 nix = ix;
+        double2 nw = w;
+        int nter = terrain;
+        if (inext < n) load_plan(inext, nix, nw, nter);
+        double *o = out + i * o_n;
+        if (ix.x < 0) {
+            const double fill = (ix.x == -1) ? MT_SENTINEL : nan_f64();
+            for (int l = lane; l < layers; l += 32) o[l] = fill;
+        } else {
+            const double *row0 = src + ix.z * s_y, *row1 = src + ix.w * s_y;
+            const int64_t c0 = ix.x * s_x, c1 = ix.y * s_x;
+            if (VEC == 2) {
+                for (int l = lane * 2; l < layers; l += 64) {
+                    const double2 a = *reinterpret_cast<const double2 *>(row0 + c0 + l);
+                    const double2 b = *reinterpret_cast<const double2 *>(row0 + c1 + l);
+                    const double2 c = *reinterpret_cast<const double2 *>(row1 + c0 + l);
+                    const double2 d = *reinterpret_cast<const double2 *>(row1 + c1 + l);
+                    double2 r;
+                    r.x = bilerp(a.x, b.x, c.x, d.x, w.x, w.y);
+                    r.y = bilerp(a.y, b.y, c.y, d.y, w.x, w.y);
+                    if (terrain > l) r.x = nan_f64();
+                    if (terrain > l + 1) r.y = nan_f64();
+                    __stcs(reinterpret_cast<double2 *>(o + l), r);
+                }
+            } else {
+                for (int l = lane; l < layers; l += 32) {
+                    double r = bilerp(row0[c0 + l], row0[c1 + l], row1[c0 + l], row1[c1 + l], w.x, w.y);
+                    if (terrain > l) r = nan_f64();
+                    __stcs(o + l, r);
                 }
             }
         }
+        i = inext, ix = nix, w = nw, terrain = nter;
     }
 }
 
@@ -369,10 +358,10 @@ int mt_gather2d_lf(const double *const *src, double *const *out, int nvar, int64
     auto pix = reinterpret_cast<const int4 *>(plan_ix);
     auto pw = reinterpret_cast<const double2 *>(plan_w);
     if (vec)
-        k_gather2d_lf<2, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        k_gather2d_lf<2><<<grid, 256, 0, (cudaStream_t)stream>>>(
             vp, (int)layers, s_y, s_x, pix, pw, xloc, yloc, dx, dy, (int)lenx, (int)leny, n, o_n, hgt_idx);
     else
-        k_gather2d_lf<1, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        k_gather2d_lf<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
             vp, (int)layers, s_y, s_x, pix, pw, xloc, yloc, dx, dy, (int)lenx, (int)leny, n, o_n, hgt_idx);
     MT_LAUNCH_CHECK();
     return MT_OK;

@@ -578,3 +578,313 @@ int mt_terrain_mask_car(double *var, int64_t nz, int64_t n, int64_t s_z, int64_t
 }
 
 }  // extern "C"
+
+// =====================================================================================
+// Fully fused set_data (F1): vertical interpolation + bilinear gather + terrain mask in ONE
+// kernel, the level-interpolated columns never leave shared memory.
+//
+// Work is organised by SOURCE tile: the targets are bucketed (once per grid, host side) by the
+// TW x TH block of source cells their (x0, y0) corner falls into; a work item is (tile, <= 128
+// of its targets).  A CTA takes items from an atomic counter and, per item,
+//   1. stages the (TW+1) x (TH+1) coordinate columns [nz][NC] with cp.async, checks monotonicity
+//      (warp vote per column) and brackets every (column, level) pair (kp, w2) in shared memory;
+//   2. for every variable (double-buffered cp.async ring): builds the level-interpolated
+//      columns lev[NC][nlev] in shared memory, then one warp per target reads its four corner
+//      columns (16-byte conflict-free loads), does the three lerps of fastcompute.f90:100-102 and
+//      streams the 480-byte result row to HBM.
+// HBM traffic = touched source columns (x ~1.3 tile halo, mostly L2 hits) + outputs: the
+// [by][bx][nlev] intermediate of the two-kernel path (write 522 MB + read 429 MB on S2) is gone.
+// Arithmetic and its order are identical to k_interplevel_tile + k_gather2d_lf.
+// =====================================================================================
+namespace {
+
+struct FusedMeta {   // one staged target of the current item
+    double fx, fy;
+    int target, terrain;
+    unsigned char c00, c10, c01, c11;
+    int pad;
+};
+
+template <typename T, bool INCLUSIVE, int TW, int TH>
+__global__ void __launch_bounds__(512)
+k_setdata_fused(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz, int64_t ny, int64_t nx,
+                int64_t org_y, int64_t org_x, const double *__restrict__ levels, int nlev, int direction,
+                int round_f32, const int4 *__restrict__ pix, const double2 *__restrict__ pw,
+                const int32_t *__restrict__ order, const int4 *__restrict__ items, int nitems,
+                int *__restrict__ counter, const int32_t *__restrict__ hgt_idx, int64_t o_n, int off_lev,
+                int off_w2, int off_kp, int off_meta, int off_misc)
+{
+    constexpr int NCX = TW + 1, NC = NCX * (TH + 1);
+    constexpr int PITCH = NC | 1;   // odd: the per-lane varying level index spreads over the banks
+    constexpr int MAXT = 128;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *tiles = reinterpret_cast<T *>(smem_raw);                                   // [2][nz][PITCH]
+    double *lev = reinterpret_cast<double *>(smem_raw + off_lev);                 // [NC][nlev]
+    double *w2s = reinterpret_cast<double *>(smem_raw + off_w2);                  // [NC][nlev]
+    unsigned char *kps = smem_raw + off_kp;                                       // [NC][nlev]
+    FusedMeta *meta = reinterpret_cast<FusedMeta *>(smem_raw + off_meta);         // [MAXT]
+    double *lev_s = reinterpret_cast<double *>(smem_raw + off_misc);              // [nlev]
+    long long *coloff = reinterpret_cast<long long *>(lev_s + nlev);              // [NC], -1: outside
+    int *s_item = reinterpret_cast<int *>(coloff + NC);
+    unsigned char *mono_s = reinterpret_cast<unsigned char *>(s_item + 4);        // [NC]
+    const int tile_elems = nz * PITCH;
+
+    const int64_t plane = ny * nx;
+    const int decreasing = direction >= 0 ? direction
+                                          : (ld<T>(vert, 0) > ld<T>(vert, (int64_t)(nz - 1) * plane) ? 1 : 0);
+    const int im = decreasing ? 0 : 1, ip = decreasing ? 1 : 0;
+    const double sgn = decreasing ? -1.0 : 1.0;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    for (int l = tid; l < nlev; l += nthr) lev_s[l] = levels[l];
+
+    while (true) {
+        __syncthreads();  // everything of the previous item is consumed
+        if (tid == 0) s_item[0] = atomicAdd(counter, 1);
+        __syncthreads();
+        const int item = s_item[0];
+        if (item >= nitems) break;
+        const int4 it = items[item];  // tile_x, tile_y (full-source indices), start, count
+        if (tid < NC) {
+            const int cy = tid / NCX, cx = tid - cy * NCX;
+            const int64_t y = it.y + cy - org_y, x = it.x + cx - org_x;
+            coloff[tid] = (y >= 0 && y < ny && x >= 0 && x < nx) ? y * nx + x : -1;
+        }
+        for (int j = tid; j < it.w; j += nthr) {  // stage the item's targets once for all variables
+            const int target = order[it.z + j];
+            const int4 ix = pix[target];
+            const double2 w = pw[target];
+            FusedMeta m;
+            m.fx = w.x, m.fy = w.y, m.target = target;
+            m.terrain = hgt_idx ? hgt_idx[target] : 0;
+            m.c00 = (unsigned char)((ix.z - it.y) * NCX + (ix.x - it.x));
+            m.c10 = (unsigned char)((ix.z - it.y) * NCX + (ix.y - it.x));
+            m.c01 = (unsigned char)((ix.w - it.y) * NCX + (ix.x - it.x));
+            m.c11 = (unsigned char)((ix.w - it.y) * NCX + (ix.y - it.x));
+            m.pad = 0;
+            meta[j] = m;
+        }
+        __syncthreads();
+        auto prefetch = [&](int t) {  // t = 0: coordinate, t = v+1: variable v
+            const T *src = reinterpret_cast<const T *>(t == 0 ? vert : ptrs.field[t - 1]);
+            T *dst = tiles + (t & 1) * tile_elems;
+            for (int e = tid; e < nz * NC; e += nthr) {
+                const int k = e / NC, c = e - k * NC;
+                const long long off = coloff[c];
+                if (off >= 0) cp_async_elem(dst + k * PITCH + c, src + (int64_t)k * plane + off);
+            }
+            cp_async_commit();
+        };
+        prefetch(0);
+        prefetch(1);
+        cp_async_wait<1>();
+        __syncthreads();
+        const T *vt = tiles;
+        // monotone (in the chosen direction) per column: warp vote over the level pairs
+        for (int c = warp; c < NC; c += nwarps) {
+            bool ok = true;
+            if (coloff[c] >= 0)
+                for (int k = lane; k + 1 < nz; k += 32)
+                    ok = ok && (sgn * (double)vt[(k + 1) * PITCH + c] >= sgn * (double)vt[k * PITCH + c]);
+            ok = __all_sync(0xffffffffu, ok);
+            if (lane == 0) mono_s[c] = ok ? 1 : 0;
+        }
+        __syncthreads();
+        // brackets: warp per column, lanes over levels
+        for (int c = warp; c < NC; c += nwarps) {
+            if (coloff[c] < 0) continue;
+            const bool mono = mono_s[c] != 0;
+            for (int l = lane; l < nlev; l += 32) {
+                const double want = lev_s[l];
+                int kp = -1;
+                if (mono) {
+                    const double ww = sgn * want;  // upper bound: first K with vv[K] > ww
+                    int lo = 0, hi = nz;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sgn * (double)vt[mid * PITCH + c] > ww) hi = mid;
+                        else lo = mid + 1;
+                    }
+                    const int K = lo;
+                    if (K >= 1 && K <= nz - 1) {
+                        if (INCLUSIVE) kp = K;
+                        else if (sgn * (double)vt[(K - 1) * PITCH + c] < ww) kp = K;
+                    } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * PITCH + c] == ww) {
+                        kp = nz - 1;
+                    }
+                } else {
+                    for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
+                        const double vlo = (double)vt[(q - im) * PITCH + c], vhi = (double)vt[(q - ip) * PITCH + c];
+                        const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
+                        if (hit) {
+                            kp = q;
+                            break;
+                        }
+                    }
+                }
+                double w2 = 0.0;
+                if (kp >= 0) {
+                    const double vlo = (double)vt[(kp - im) * PITCH + c], vhi = (double)vt[(kp - ip) * PITCH + c];
+                    w2 = (want - vlo) / (vhi - vlo);
+                }
+                kps[c * nlev + l] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
+                w2s[c * nlev + l] = w2;
+            }
+        }
+        for (int v = 0; v < nvar; ++v) {
+            const int t = v + 1;
+            __syncthreads();  // brackets visible; ring slot (t+1)&1 and `lev` fully consumed
+            if (t + 1 <= nvar) {
+                prefetch(t + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();  // tile t has landed for every thread
+            const T *ft = tiles + (t & 1) * tile_elems;
+            for (int c = warp; c < NC; c += nwarps) {  // level-interpolated columns
+                if (coloff[c] < 0) continue;
+                for (int l = lane; l < nlev; l += 32) {
+                    const int kp = kps[c * nlev + l];
+                    double r;
+                    if (kp == 255) {
+                        r = nan_f64();
+                    } else {
+                        const double w2 = w2s[c * nlev + l];
+                        const double w1 = 1.0 - w2;
+                        r = w1 * (double)ft[(kp - im) * PITCH + c] + w2 * (double)ft[(kp - ip) * PITCH + c];
+                        if (round_f32) r = (double)(float)r;
+                    }
+                    lev[c * nlev + l] = r;
+                }
+            }
+            __syncthreads();
+            double *__restrict__ out = ptrs.out[v];
+            for (int j = warp; j < it.w; j += nwarps) {  // bilinear: one warp per target
+                const FusedMeta m = meta[j];
+                const double *p00 = lev + m.c00 * nlev, *p10 = lev + m.c10 * nlev;
+                const double *p01 = lev + m.c01 * nlev, *p11 = lev + m.c11 * nlev;
+                double *o = out + (int64_t)m.target * o_n;
+                for (int l = lane * 2; l < nlev; l += 64) {
+                    if (l + 1 < nlev) {
+                        const double2 a = *reinterpret_cast<const double2 *>(p00 + l);
+                        const double2 b = *reinterpret_cast<const double2 *>(p10 + l);
+                        const double2 c = *reinterpret_cast<const double2 *>(p01 + l);
+                        const double2 d = *reinterpret_cast<const double2 *>(p11 + l);
+                        double2 r;
+                        r.x = (((d.x - c.x) * m.fx + c.x) - ((b.x - a.x) * m.fx + a.x)) * m.fy + ((b.x - a.x) * m.fx + a.x);
+                        r.y = (((d.y - c.y) * m.fx + c.y) - ((b.y - a.y) * m.fx + a.y)) * m.fy + ((b.y - a.y) * m.fx + a.y);
+                        if (m.terrain > l) r.x = nan_f64();
+                        if (m.terrain > l + 1) r.y = nan_f64();
+                        __stcs(reinterpret_cast<double2 *>(o + l), r);
+                    } else {
+                        const double t0 = (p10[l] - p00[l]) * m.fx + p00[l];
+                        const double t1 = (p11[l] - p01[l]) * m.fx + p01[l];
+                        double r = (t1 - t0) * m.fy + t0;
+                        if (m.terrain > l) r = nan_f64();
+                        __stcs(o + l, r);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// targets whose coordinates are NaN / the legacy sentinel: no stencil, just the fill value
+__global__ void k_fill_flagged(ILPtrs ptrs, int nvar, const int4 *__restrict__ pix, int64_t n, int nlev,
+                               int64_t o_n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int flag = pix[i].x;
+        if (flag >= 0) continue;
+        const double fill = flag == -1 ? MT_SENTINEL : nan_f64();
+        for (int v = 0; v < nvar; ++v)
+            for (int l = 0; l < nlev; ++l) ptrs.out[v][i * o_n + l] = fill;
+    }
+}
+
+}  // namespace
+
+extern "C" int mt_setdata_fused(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz,
+                                int64_t ny, int64_t nx, int64_t org_y, int64_t org_x, const double *levels,
+                                int64_t nlev, int direction, const int32_t *plan_ix, const double *plan_w,
+                                int64_t n, const int32_t *order, const int32_t *items, int64_t nitems,
+                                int tile_w, int tile_h, int64_t nflagged, const int32_t *hgt_idx,
+                                double *const *out, int64_t o_n, int flags, int32_t *counter,
+                                mt_stream_t stream)
+{
+    MT_REQUIRE(fields && vert && levels && plan_ix && plan_w && order && items && out && counter,
+               "mt_setdata_fused: null pointer");
+    MT_REQUIRE(nvar >= 1 && nvar <= MT_MAX_VARS, "mt_setdata_fused: nvar must be 1..%d", MT_MAX_VARS);
+    MT_REQUIRE(dtype == MT_F64 || dtype == MT_F32, "mt_setdata_fused: bad dtype");
+    MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 1 && nlev < 2147483647LL && o_n >= nlev && (o_n % 2 == 0 || nlev == 1),
+               "mt_setdata_fused: need 2 <= nz <= 254 and an even output pitch");
+    MT_REQUIRE((tile_w == 16 && tile_h == 4) || (tile_w == 16 && tile_h == 2), "mt_setdata_fused: tile must be 16x4 or 16x2");
+    ILPtrs p;
+    for (int v = 0; v < nvar; ++v) {
+        MT_REQUIRE(fields[v] && out[v] && ((uintptr_t)out[v] % 16 == 0), "mt_setdata_fused: bad field %d", v);
+        p.field[v] = fields[v];
+        p.out[v] = out[v];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rf = (flags & MT_IL_ROUND_F32) ? 1 : 0;
+    const auto pix = reinterpret_cast<const int4 *>(plan_ix);
+    const auto pw = reinterpret_cast<const double2 *>(plan_w);
+    if (nflagged > 0) {
+        mt::ProfScope prof("k_fill_flagged", stream);
+        k_fill_flagged<<<mt::grid_for(n, 256, 4), 256, 0, s>>>(p, nvar, pix, n, (int)nlev, o_n);
+        MT_LAUNCH_CHECK();
+    }
+    if (nitems == 0) return MT_OK;
+    MT_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), s));
+    const size_t eb = dtype == MT_F64 ? 8 : 4;
+    const int NC = (tile_w + 1) * (tile_h + 1), PITCH = NC | 1;
+    size_t off = 2 * (size_t)nz * PITCH * eb;
+    off = (off + 15) & ~size_t(15);
+    const size_t off_lev = off;
+    off += (size_t)NC * nlev * 8;
+    const size_t off_w2 = off;
+    off += (size_t)NC * nlev * 8;
+    const size_t off_kp = off;
+    off += (size_t)NC * nlev;
+    off = (off + 15) & ~size_t(15);
+    const size_t off_meta = off;
+    off += 128 * sizeof(FusedMeta);
+    const size_t off_misc = off;
+    off += (size_t)nlev * 8 + (size_t)NC * 8 + 16 + NC;
+    const size_t smem = (off + 15) & ~size_t(15);
+    MT_REQUIRE(smem <= 227 * 1024, "mt_setdata_fused: tile does not fit in shared memory (nz=%lld, nlev=%lld)",
+               (long long)nz, (long long)nlev);
+    const int ctas_per_sm = (int)(227 * 1024 / smem) < 1 ? 1 : (int)(227 * 1024 / smem);
+    int64_t grid64 = (int64_t)mt::sm_count() * ctas_per_sm;
+    if (grid64 > nitems) grid64 = nitems;
+    const unsigned grid = (unsigned)grid64;
+    const int threads = ctas_per_sm >= 2 ? 256 : 512;
+    mt::ProfScope prof("k_setdata_fused", stream);
+#define SF_LAUNCH(T, INC, TW, TH)                                                                                \
+    do {                                                                                                         \
+        MT_CUDA(cudaFuncSetAttribute(k_setdata_fused<T, INC, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                                \
+        k_setdata_fused<T, INC, TW, TH><<<grid, threads, smem, s>>>(                                             \
+            p, nvar, vert, (int)nz, ny, nx, org_y, org_x, levels, (int)nlev, direction, rf, pix, pw, order,      \
+            reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n, (int)off_lev, (int)off_w2, \
+            (int)off_kp, (int)off_meta, (int)off_misc);                                                          \
+    } while (0)
+#define SF_DISPATCH(T, INC)                   \
+    do {                                      \
+        if (tile_h == 4) SF_LAUNCH(T, INC, 16, 4); \
+        else SF_LAUNCH(T, INC, 16, 2);        \
+    } while (0)
+    if (dtype == MT_F64) {
+        if (flags & MT_IL_INCLUSIVE) SF_DISPATCH(double, true);
+        else SF_DISPATCH(double, false);
+    } else {
+        if (flags & MT_IL_INCLUSIVE) SF_DISPATCH(float, true);
+        else SF_DISPATCH(float, false);
+    }
+#undef SF_DISPATCH
+#undef SF_LAUNCH
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}

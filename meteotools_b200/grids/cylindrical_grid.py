@@ -178,6 +178,20 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 batch = group[b0:b0 + _lib.MT_MAX_VARS]
                 srcs = [stage(s, use32) for _, s in batch]
                 outs = [self._new() for _ in batch]
+                import os
+                fused = trz and nz <= 254 and self.Nz % 2 == 0 and os.environ.get("MT_SETDATA", "split") == "fused"
+                if fused:   # one kernel, no intermediate in HBM
+                    th_ = 2 if os.environ.get("MT_SETDATA_TILE") == "16x2" else 4
+                    order_t, items_t, nitems, nflag, counter = self._fused_items_for(plan, 16, th_)
+                    _lib.check(lib.mt_setdata_fused(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, sny,
+                                                    snx, oy, ox, D.ptr(levels), self.Nz, direction,
+                                                    D.ptr(plan[0]), D.ptr(plan[1]), n, D.ptr(order_t),
+                                                    D.ptr(items_t), nitems, 16, th_, nflag, D.ptr(hgt_idx),
+                                                    D.ptr_array(outs), self.Nz, flags, D.ptr(counter),
+                                                    D.stream()), 'mt_setdata_fused')
+                    for (name, _), o in zip(batch, outs):
+                        self._put(name, o)
+                    continue
                 wsb = lib.mt_setdata_workspace_bytes(len(batch), self.Nz, y0, y1, x0, x1)
                 ws = D.empty(((wsb + 7) // 8,))
                 _lib.check(lib.mt_setdata(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, sny, snx,
@@ -202,7 +216,46 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                                                     D.ptr(ix), D.ptr(w), D.stream()), 'mt_interp2d_plan')
             plan = (ix, w, key)
             self.__dict__['_plan'] = plan
+            self.__dict__.pop('_fused_items', None)
         return plan
+
+    def _fused_items_for(self, plan, tile_w=16, tile_h=4, max_targets=128):
+        """Targets bucketed by source tile for ``mt_setdata_fused`` (built once per plan on the
+        host: an argsort of n keys): (order, items, nitems, nflagged, counter)."""
+        cached = self.__dict__.get('_fused_items')
+        if cached is not None and cached[0] == (plan[2], tile_w, tile_h):
+            return cached[1]
+        ix = D.to_host(plan[0]).astype(np.int64)
+        valid = ix[:, 0] >= 0
+        idx = np.nonzero(valid)[0]
+        nflagged = int(ix.shape[0] - idx.size)
+        if idx.size:
+            x0, y0 = ix[idx, 0], ix[idx, 2]
+            bx0, by0 = int(x0.min()), int(y0.min())
+            tx, ty = (x0 - bx0) // tile_w, (y0 - by0) // tile_h
+            ntx = int(tx.max()) + 1
+            key = ty * ntx + tx
+            srt = np.argsort(key, kind='stable')
+            skey = key[srt]
+            starts = np.flatnonzero(np.r_[True, skey[1:] != skey[:-1]])
+            ends = np.r_[starts[1:], skey.size]
+            rows = []
+            for s0, e0 in zip(starts, ends):
+                k = int(skey[s0])
+                t_x, t_y = bx0 + (k % ntx) * tile_w, by0 + (k // ntx) * tile_h
+                for c0 in range(s0, e0, max_targets):
+                    rows.append((t_x, t_y, c0, min(max_targets, e0 - c0)))
+            items = np.array(rows, dtype=np.int32)
+            items = items[np.argsort(-items[:, 3], kind='stable')]   # big items first: short tail
+            order = idx[srt].astype(np.int32)
+        else:
+            items, order = np.zeros((0, 4), np.int32), np.zeros((1,), np.int32)
+        t = D.torch()
+        res = (t.from_numpy(order).cuda(), t.from_numpy(np.ascontiguousarray(items)).cuda() if len(items) else
+               t.zeros((1, 4), dtype=t.int32, device='cuda'), int(len(items)), nflagged,
+               t.zeros((1,), dtype=t.int32, device='cuda'))
+        self.__dict__['_fused_items'] = ((plan[2], tile_w, tile_h), res)
+        return res
 
     def set_terrain(self):  # :139-176
         hgt = self.device('hgt')

@@ -92,6 +92,12 @@ class CylStepPipeline:
         self.dyn_out = {k: g._new(dtype=t.uint8 if k == "strain_region" else None) for k in self.dyn_names}
         self.scratch = D.empty((16 + self.n * g.Nz,))
         self.direction = -1
+        import os
+        self.fused = g.Nz % 2 == 0 and self.nz <= 254 and os.environ.get("MT_SETDATA", "split") == "fused"
+        if self.fused:
+            self.tile_h = 2 if os.environ.get("MT_SETDATA_TILE") == "16x2" else 4
+            self.f_order, self.f_items, self.f_nitems, self.f_nflag, self.f_counter = \
+                g._fused_items_for(self.plan, 16, self.tile_h)
         if not resident:   # persistent device staging for the uploaded boxes
             shp = (self.nz, y1 - y0, x1 - x0)
             self.stage3d = {k: t.empty(shp, dtype=self.t_dtype, device="cuda") for k in self.names3d}
@@ -163,7 +169,15 @@ class CylStepPipeline:
         if self.has_hgt:
             _lib.check(lib.mt_terrain_index_cyl(D.ptr(self.out2d["hgt"]), g.Ntheta, g.Nr, g.z_start, g.dz,
                                                 D.ptr(self.hgt_idx), s), "mt_terrain_index_cyl")
-        _lib.check(lib.mt_setdata(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype, self.nz,
+        if self.fused:
+            _lib.check(lib.mt_setdata_fused(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype,
+                                            self.nz, sny, snx, oy, ox, D.ptr(self.levels), g.Nz, self.direction,
+                                            D.ptr(self.plan[0]), D.ptr(self.plan[1]), self.n, D.ptr(self.f_order),
+                                            D.ptr(self.f_items), self.f_nitems, 16, self.tile_h, self.f_nflag,
+                                            D.ptr(self.hgt_idx), self._out_ptrs, g.Nz, self.flags,
+                                            D.ptr(self.f_counter), s), "mt_setdata_fused")
+        else:
+          _lib.check(lib.mt_setdata(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype, self.nz,
                                   sny, snx, oy, ox, self.ny, self.nx, self.dx, self.dy, y0, y1, x0, x1,
                                   D.ptr(self.levels), g.Nz, self.order, self.direction, D.ptr(self.xd),
                                   D.ptr(self.yd), D.ptr(self.plan[0]), D.ptr(self.plan[1]), self.n,

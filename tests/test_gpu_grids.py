@@ -180,6 +180,26 @@ def test_set_data_cyl_golden(golden_setdata):
         cyl3.set_data(dx, dx, g["s_z3d"], u=g["s_u"])
 
 
+def test_set_data_fused_kernel_matches_split(golden_setdata, monkeypatch):
+    """The opt-in single-kernel set_data (MT_SETDATA=fused, mt_setdata_fused) gives the same bits
+    as the default two-kernel path, terrain mask and float32 rounding included."""
+    g = golden_setdata
+    from meteotools_b200.grids import cylindrical_grid
+    dx = float(g["s_dx"])
+    for tile in ("16x4", "16x2"):
+        monkeypatch.setenv("MT_SETDATA", "fused")
+        monkeypatch.setenv("MT_SETDATA_TILE", tile)
+        cyl = cylindrical_grid(dict(SD))
+        cyl.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+        cyl.set_data(dx, dx, g["s_z3d"], u=g["s_u"], T=g["s_T"], f=g["s_f"], hgt=g["s_hgt"])
+        assert_same(cyl.u, g["o_sd_cyl_u"], f"fused {tile} u")
+        assert_same(cyl.T, g["o_sd_cyl_T"], f"fused {tile} T")
+        u32, z32 = g["s_u"].astype(np.float32), g["s_z3d"].astype(np.float32)
+        cyl.set_data(dx, dx, z32, u=u32)
+        ref = oracle.interp2D_fast_layers(dx, dx, g["o_sd_xTR"], g["o_sd_yTR"], oracle.interplevel(u32, z32, cyl.z))
+        assert_same(cyl.u, ref, f"fused {tile} float32")
+
+
 def test_set_data_car_golden(golden_setdata):
     g = golden_setdata
     from meteotools_b200.grids import cartesian_grid
