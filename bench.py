@@ -333,7 +333,10 @@ def main():
     roof = roofline(kern, pipe, cyl, tc_iters, args.steps)
     clk = clocks.stop()
 
-    # ---------------- e2e: public grid API, host (pinned) buffers ---------------------------------
+    # ---------------- e2e: public API, host (pinned) buffers ------------------------------------
+    # (a) one step at a time through the grid methods; (b) a stream of time steps through
+    # pipeline.TimeStepStream, which overlaps step k's D2H with step k+1's H2D (full-duplex PCIe).
+    # Every step uploads its source boxes and downloads its 13 thermodynamic outputs in both.
     del pipe, dev3d, devz
     torch.cuda.empty_cache()
     td_names = list(_lib.TD_OUT)
@@ -349,15 +352,29 @@ def main():
     for _ in range(args.e2e_steps):
         res = e2e_step()
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    e2e_single_s = (time.perf_counter() - t0) / args.e2e_steps
+    assert all(res[k].shape == (CYL["Nz"], CYL["Ntheta"], CYL["Nr"]) for k in td_names)
+    del res
+    from meteotools_b200.pipeline import TimeStepStream
+    ts = TimeStepStream(cyl, (NZ, NY, NX), DX, DX, NAMES3D, names2d=("f",), hgt=True, outputs=td_names)
+    n_stream = max(4 * args.e2e_steps, 8)
+    for _ in ts.process([step] * 3):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    got = 0
+    for _, r in ts.process([step] * n_stream):
+        got += 1
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_stream
+    assert got == n_stream and r["Th_e"].shape == (CYL["Nz"], CYL["Ntheta"], CYL["Nr"])
     if world > 1:
-        te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        te = torch.tensor([e2e_s, e2e_single_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
+        e2e_s, e2e_single_s = float(te[0].item()), float(te[1].item())
     y0, y1, x0, x1 = cyl._target_box(NX, NY, DX, DX)
     h2d = (len(NAMES3D) + 1) * NZ * (y1 - y0) * (x1 - x0) * 8 + 2 * NY * NX * 8
     d2h = len(td_names) * NPTS * 8
-    assert all(res[k].shape == (CYL["Nz"], CYL["Ntheta"], CYL["Nr"]) for k in td_names)
 
     if rank == 0:
         out = {
@@ -366,8 +383,12 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(),
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": world * NPTS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                    "path": "cylindrical_grid.set_data + calc_all_thermaldynamic + to_host (pinned host buffers)"},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": n_stream,
+                    "path": "pipeline.TimeStepStream.process (pinned host arrays in -> pinned host arrays out, "
+                            "two slots: D2H of step k overlaps H2D of step k+1)",
+                    "single_step": {"value": world * NPTS / e2e_single_s, "ms_per_step": e2e_single_s * 1e3,
+                                    "path": "cylindrical_grid.set_data + calc_all_thermaldynamic + to_host, "
+                                            "one step at a time"}},
             "roofline": roof, "tc_iterations": tc_iters,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -400,28 +421,20 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
         # fused set_data (SURVEY 8d formula B): touched source columns of V fields + the coordinate,
         # outputs, plan
         "k_setdata_fused": 8.0 * nz * U * (V + 1) + 8.0 * nlev * n * V + 32.0 * n,
-        # NaN fast path of calc_Tc: reads g, Tc; writes Tc (the remaining sweeps stay in registers)
-        "k_tc_rest_nan": 8.0 * NPTS * 3,
+        # remaining Tc sweeps (in registers when NaN is present) + theta_e: reads g, Tc, Th, qv;
+        # writes Tc, Th_e
+        "k_tc_finish": 8.0 * NPTS * 6,
         # reads T,p,qv,qc,qr; writes 12 outputs (incl. the first Tc sweep) + the sweep-invariant g
         "k_td_main": 8.0 * NPTS * (5 + 13),
         # reads g, Tc; writes Tc
         "k_tc_iter": 8.0 * NPTS * 3,
-        "k_td_theta_e": 8.0 * NPTS * 4,
     }
     rows = []
     for name, (cnt, tot) in kern.items():
         per = tot / cnt
         launches_per_step = cnt / steps
         eff_cnt = cnt
-        nan_mode = "k_tc_rest_nan" in kern and kern["k_tc_rest_nan"][1] / kern["k_tc_rest_nan"][0] > 0.02
-        if name == "k_tc_iter" and not nan_mode:   # sweeps after convergence return at once
-            eff_cnt = steps * max(tc_iters - 1, 1)
-            per = tot / eff_cnt
         a = alg.get(name)
-        if name == "k_tc_iter" and nan_mode:
-            a = None   # every sweep was taken over by k_tc_rest_nan: these launches return at once
-        if name == "k_tc_rest_nan" and not nan_mode:
-            a = None
         rows.append({"kernel": name, "launches_per_step": launches_per_step, "ms_per_step": tot / steps,
                      "avg_ms_per_launch": per,
                      "achieved_gbs": (a / (per * 1e-3) / 1e9) if a else None, "alg_bytes_per_launch": a})

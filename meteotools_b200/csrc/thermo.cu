@@ -6,6 +6,8 @@
 // max |diff| (as the bit pattern of a non-negative double, for which unsigned integer order ==
 // floating order and every NaN sorts above +inf) into scratch[i]; iteration i+1 starts by
 // reading scratch[i] and returns immediately when it is < 0.1 (or was never written: 0).
+#include <cooperative_groups.h>
+
 #include "thermo.cuh"
 
 namespace {
@@ -95,7 +97,6 @@ __global__ void __launch_bounds__(256)
 k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__restrict__ Tc, int64_t n,
           int iter, unsigned long long *__restrict__ maxbits, int vec_ok)
 {
-    if (maxbits[14]) return;                                                            // k_tc_rest_nan did it
     if (iter > 0 && __longlong_as_double((long long)maxbits[iter - 1]) < 0.1) return;  // converged
     unsigned long long m = 0ull;
     const int64_t npair = vec_ok ? (n >> 1) : 0;  // vec_ok: all pointers 16-byte aligned
@@ -125,50 +126,84 @@ k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__
     block_max_to(m, maxbits + iter);
 }
 
-// NaN fast path.  If the max |diff| of sweep `first-1` is NaN, some point is NaN for good (a NaN
-// iterate stays NaN), so np.max stays NaN and the reference runs all 10 sweeps no matter what
-// (terrain-masked data).  The remaining sweeps are then certain and are done
-// in registers in ONE pass (read g, Tc; write Tc) instead of one HBM pass per sweep.
+// Everything after the first sweep in ONE cooperative launch (replaces nine per-sweep launches,
+// the iteration counter and the theta_e kernel):
+//  * NaN fast path.  If the max |diff| of sweep `first-1` is NaN, some point is NaN for good (a NaN
+//    iterate stays NaN), so np.max stays NaN and the reference runs all 10 sweeps no matter what
+//    (terrain-masked data).  The remaining sweeps are then certain and are done
+//    in registers in one pass over HBM.  Only log(Tc) is iterated, L' = log B - log(g - a L)
+//    (one log per sweep, no division); Tc = B / (g - a L) is formed once at the end.
+//  * otherwise: one grid-stride sweep per iteration, block max -> atomicMax, grid.sync(), stop as
+//    soon as the global max |Tc - Tc2| < 0.1 -- the reference's test, evaluated on the device.
+//  * finally theta_e = Th * exp(Lv*qv/Cp/Tc) (:456) when requested, from the Tc just produced.
 __global__ void __launch_bounds__(256)
-k_tc_rest_nan(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, int first,
-              unsigned long long *__restrict__ maxbits, int vec_ok)
+k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, int first,
+            unsigned long long *__restrict__ maxbits, int vec_ok, const double *__restrict__ Th,
+            const double *__restrict__ qv, double *__restrict__ Th_e)
 {
+    namespace cg = cooperative_groups;
+    constexpr double logB = 8.597851094433691;  // log(5420)
     const double prev_max = __longlong_as_double((long long)maxbits[first - 1]);
-    if (!(prev_max != prev_max)) return;  // not NaN: the per-sweep kernels decide
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int it = first; it < 10; ++it) maxbits[it] = maxbits[first - 1];  // NaN for k_tc_count
-        maxbits[14] = 1ull;
-    }
-    const int64_t npair = vec_ok ? (n >> 1) : 0;
-    const double2 *__restrict__ g2 = reinterpret_cast<const double2 *>(g);
-    double2 *__restrict__ Tc2 = reinterpret_cast<double2 *>(Tc);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npair;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        double2 t = Tc2[i];
-        const double2 gg = __ldg(g2 + i);
-        for (int it = first; it < 10; ++it) {
-            t.x = Tc_step_g(gg.x, t.x);
-            t.y = Tc_step_g(gg.y, t.y);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    if (prev_max != prev_max) {  // NaN: all remaining sweeps, in registers
+        if (tid == 0) {
+            for (int it = first; it < 10; ++it) maxbits[it] = maxbits[first - 1];
+            reinterpret_cast<double *>(maxbits)[15] = 10.0;
         }
-        Tc2[i] = t;
+        auto finish = [&](double t, double gg) {
+            double L = log(t), D = gg - CpRd * L;
+            for (int it = first + 1; it < 10; ++it) {
+                L = logB - log(D);
+                D = gg - CpRd * L;
+            }
+            return B / D;
+        };
+        const int64_t npair = vec_ok ? (n >> 1) : 0;
+        const double2 *__restrict__ g2 = reinterpret_cast<const double2 *>(g);
+        double2 *__restrict__ Tc2 = reinterpret_cast<double2 *>(Tc);
+        for (int64_t i = tid; i < npair; i += nthr) {
+            double2 t = Tc2[i];
+            const double2 gg = __ldg(g2 + i);
+            t.x = finish(t.x, gg.x);
+            t.y = finish(t.y, gg.y);
+            Tc2[i] = t;
+            if (Th_e) {
+                const double2 th = __ldg(reinterpret_cast<const double2 *>(Th) + i);
+                const double2 q = __ldg(reinterpret_cast<const double2 *>(qv) + i);
+                __stcs(reinterpret_cast<double2 *>(Th_e) + i,
+                       make_double2(exp_factor(th.x, q.x, t.x), exp_factor(th.y, q.y, t.y)));
+            }
+        }
+        for (int64_t i = 2 * npair + tid; i < n; i += nthr) {
+            const double t = finish(Tc[i], g[i]);
+            Tc[i] = t;
+            if (Th_e) __stcs(Th_e + i, exp_factor(__ldg(Th + i), __ldg(qv + i), t));
+        }
+        return;
     }
-    for (int64_t i = 2 * npair + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        double t = Tc[i];
-        const double gg = g[i];
-        for (int it = first; it < 10; ++it) t = Tc_step_g(gg, t);
-        Tc[i] = t;
+    cg::grid_group grid = cg::this_grid();
+    int count = first;  // sweeps executed so far
+    if (!(prev_max < 0.1)) {
+        for (int it = first; it < 10; ++it) {
+            unsigned long long m = 0ull;
+            for (int64_t i = tid; i < n; i += nthr) {
+                const double prev = Tc[i];
+                const double cur = Tc_step_g(__ldg(g + i), prev);
+                Tc[i] = cur;
+                const unsigned long long b = absbits(cur - prev);
+                m = b > m ? b : m;
+            }
+            block_max_to(m, maxbits + it);
+            grid.sync();
+            count = it + 1;
+            if (__longlong_as_double((long long)maxbits[it]) < 0.1) break;
+        }
     }
-}
-
-__global__ void k_tc_count(unsigned long long *maxbits)
-{
-    int count = 0;
-    for (int i = 0; i < 10; ++i) {
-        count = i + 1;
-        if (__longlong_as_double((long long)maxbits[i]) < 0.1) break;
-    }
-    reinterpret_cast<double *>(maxbits)[15] = (double)count;
+    if (tid == 0) reinterpret_cast<double *>(maxbits)[15] = (double)count;
+    if (Th_e)
+        for (int64_t i = tid; i < n; i += nthr)
+            __stcs(Th_e + i, exp_factor(__ldg(Th + i), __ldg(qv + i), Tc[i]));
 }
 
 // ---- fused cyl_td main pass: one read of T,p,qv(,qc,qr), every requested output, and the first
@@ -247,40 +282,30 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
     if (out.Tc) block_max_to(m, maxbits);
 }
 
-__global__ void __launch_bounds__(256)
-k_td_theta_e(const double *__restrict__ T, const double *__restrict__ P, const double *__restrict__ qv,
-             const double *__restrict__ Th, const double *__restrict__ Tc, double *__restrict__ Th_e,
-             int64_t n)
+// sweeps first..9 (+ theta_e): one cooperative launch sized to what is co-resident
+int tc_tail(const double *T, const double *g, double *Tc, int64_t n, unsigned long long *bits, int first_iter,
+            const double *Th, const double *qv, double *Th_e, cudaStream_t s)
 {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const double th = Th ? __ldg(Th + i) : theta(__ldg(T + i), __ldg(P + i));
-        __stcs(Th_e + i, exp_factor(th, __ldg(qv + i), __ldg(Tc + i)));
-    }
-}
-
-int tc_tail(const double *T, const double *g, double *Tc, int64_t n, unsigned long long *bits,
-            int first_iter, cudaStream_t s)
-{
-    const unsigned grid = mt::grid_for((n + 1) / 2, 256, 8);
-    const int vec_ok = (((uintptr_t)T | (uintptr_t)g | (uintptr_t)Tc) % 16 == 0) ? 1 : 0;
-    if (first_iter == 0) {  // sweep 0 first: it decides whether the NaN fast path applies
+    const int vec_ok = (((uintptr_t)T | (uintptr_t)g | (uintptr_t)Tc | (uintptr_t)Th | (uintptr_t)qv |
+                         (uintptr_t)Th_e) % 16 == 0) ? 1 : 0;
+    if (first_iter == 0) {  // sweep 0 decides whether the NaN fast path applies
         mt::ProfScope prof("k_tc_iter", (mt_stream_t)s);
-        k_tc_iter<<<grid, 256, 0, s>>>(T, g, Tc, n, 0, bits, vec_ok);
+        k_tc_iter<<<mt::grid_for((n + 1) / 2, 256, 8), 256, 0, s>>>(T, g, Tc, n, 0, bits, vec_ok);
         MT_LAUNCH_CHECK();
         first_iter = 1;
     }
-    {
-        mt::ProfScope prof("k_tc_rest_nan", (mt_stream_t)s);
-        k_tc_rest_nan<<<grid, 256, 0, s>>>(g, Tc, n, first_iter, bits, vec_ok);
-        MT_LAUNCH_CHECK();
+    static thread_local int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        MT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tc_finish, 256, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    for (int it = first_iter; it < 10; ++it) {
-        mt::ProfScope prof("k_tc_iter", (mt_stream_t)s);
-        k_tc_iter<<<grid, 256, 0, s>>>(T, g, Tc, n, it, bits, vec_ok);
-        MT_LAUNCH_CHECK();
-    }
-    k_tc_count<<<1, 1, 0, s>>>(bits);
+    int64_t want = ((n + 1) / 2 + 255) / 256;
+    int64_t cap = (int64_t)mt::sm_count() * blocks_per_sm;
+    const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+    void *args[] = {(void *)&g, (void *)&Tc, (void *)&n, (void *)&first_iter, (void *)&bits, (void *)&vec_ok,
+                    (void *)&Th, (void *)&qv, (void *)&Th_e};
+    mt::ProfScope prof("k_tc_finish", (mt_stream_t)s);
+    MT_CUDA(cudaLaunchCooperativeKernel((const void *)k_tc_finish, dim3(grid), dim3(256), args, 0, s));
     MT_LAUNCH_CHECK();
     return MT_OK;
 }
@@ -323,14 +348,14 @@ int mt_calc_tc(const double *T, const double *P, const double *qv, double *Tc, i
         k_tc_prepare<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(T, P, qv, g, n);
         MT_LAUNCH_CHECK();
     }
-    return tc_tail(T, g, Tc, n, reinterpret_cast<unsigned long long *>(scratch), 0, s);
+    return tc_tail(T, g, Tc, n, reinterpret_cast<unsigned long long *>(scratch), 0, nullptr, nullptr, nullptr, s);
 }
 
 int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *scratch,
               mt_stream_t stream)
 {
     MT_REQUIRE(in && out && in->T && in->p && in->qv && n > 0, "mt_cyl_td: T, p, qv are required");
-    MT_REQUIRE(!out->Th_e || out->Tc, "mt_cyl_td: Th_e needs a Tc output buffer");
+    MT_REQUIRE(!out->Th_e || (out->Tc && out->Th), "mt_cyl_td: Th_e needs the Tc and Th output buffers");
     MT_REQUIRE(!out->Tc || scratch, "mt_cyl_td: Tc needs the (16 + n)-double scratch");
     cudaStream_t s = (cudaStream_t)stream;
     auto bits = reinterpret_cast<unsigned long long *>(scratch);
@@ -341,14 +366,10 @@ int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *s
         MT_LAUNCH_CHECK();
     }
     if (out->Tc) {
-        int rc = tc_tail(in->T, scratch + 16, out->Tc, n, bits, 1, s);
+        // Th_e needs Th: taken from the output buffer when requested, else recomputed is not
+        // possible here -> Th is required as an output whenever Th_e is
+        int rc = tc_tail(in->T, scratch + 16, out->Tc, n, bits, 1, out->Th, in->qv, out->Th_e, s);
         if (rc != MT_OK) return rc;
-    }
-    if (out->Th_e) {
-        mt::ProfScope prof("k_td_theta_e", stream);
-        k_td_theta_e<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(in->T, in->p, in->qv, out->Th, out->Tc,
-                                                             out->Th_e, n);
-        MT_LAUNCH_CHECK();
     }
     return MT_OK;
 }

@@ -157,8 +157,9 @@ class calc_thermaldynamic:
         if not self._has('T', 'p', 'qv'):
             raise AttributeError('T, p and qv must be set first')
         names = list(outputs) if outputs is not None else list(_lib.TD_OUT)
-        if 'Th_e' in names and 'Tc' not in names:
-            names.append('Tc')
+        for dep in ('Tc', 'Th'):   # Th_e is produced from the Tc and Th buffers of the same call
+            if 'Th_e' in names and dep not in names:
+                names.append(dep)
         tin = _lib.mt_td_in_t()
         for k in _lib.TD_IN:
             setattr(tin, k, self._d(k).data_ptr() if self._has(k) else None)

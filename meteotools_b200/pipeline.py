@@ -85,8 +85,9 @@ class CylStepPipeline:
         self.out2d = {k: g._new(2) for k in self.names2d + (["hgt"] if hgt else [])}
         self.hgt_idx = D.empty((g.Ntheta, g.Nr), t.int32) if hgt else None
         self.td_names = list(td_outputs or [])
-        if "Th_e" in self.td_names and "Tc" not in self.td_names:
-            self.td_names.append("Tc")
+        for dep in ("Tc", "Th"):
+            if "Th_e" in self.td_names and dep not in self.td_names:
+                self.td_names.append(dep)
         self.td_out = {k: g._new() for k in self.td_names}
         self.dyn_names = list(dyn_outputs or [])
         self.dyn_out = {k: g._new(dtype=t.uint8 if k == "strain_region" else None) for k in self.dyn_names}
@@ -292,3 +293,66 @@ def dyn_level_sharded(kind, local, f2d, spacings, shard, nz_global, outputs, ran
         halo_exchange_levels(job.halo_fields, shard[2], shard[3], rank, world, dist)
     job.stage_b()
     return job.result()
+
+
+class TimeStepStream:
+    """Process a sequence of WRF time steps end to end (host arrays in, host arrays out) with the
+    PCIe traffic of consecutive steps overlapped: two ``CylStepPipeline`` slots, each on its own
+    CUDA stream; while step k's results travel device->host, step k+1's source boxes already
+    travel host->device (PCIe is full duplex) and its kernels run.  Results are identical to
+    calling ``cylindrical_grid.set_data`` + ``calc_all_thermaldynamic`` per step.
+
+        ts = TimeStepStream(grid, (nz, ny, nx), dx, dy, names3d, names2d=("f",), outputs=[...])
+        for k, result in ts.process(steps):      # steps: iterable of dict(z3d=, vars3d=, f=, hgt=)
+            ...                                  # result: dict name -> (Nz, Ntheta, Nr) ndarray
+    """
+
+    def __init__(self, grid, src_shape, dx, dy, names3d, names2d=("f",), hgt=True, outputs=None,
+                 dtype=np.float64, dyn_outputs=None, slots=2):
+        t = D.require_cuda()
+        self.t = t
+        self.outputs = list(outputs) if outputs is not None else list(_lib.TD_OUT)
+        self.slots = []
+        for _ in range(slots):
+            pipe = CylStepPipeline(grid, src_shape, dx, dy, names3d, names2d=names2d, hgt=hgt, dtype=dtype,
+                                   td_outputs=[o for o in self.outputs if o in _lib.TD_OUT] or None,
+                                   dyn_outputs=dyn_outputs, resident=False)
+            pool = {**pipe.out3d, **pipe.td_out, **pipe.dyn_out}
+            host = {k: t.empty(pool[k].shape, dtype=pool[k].dtype, pin_memory=True) for k in self.outputs}
+            self.slots.append(dict(pipe=pipe, pool=pool, host=host, stream=t.cuda.Stream(), event=None, key=None))
+
+    def _collect(self, slot):
+        slot["event"].synchronize()
+        res = {k: h.numpy().transpose(2, 0, 1) for k, h in slot["host"].items()}
+        key, slot["event"], slot["key"] = slot["key"], None, None
+        return key, res
+
+    def process(self, steps):
+        """Generator over (step_key, results).  Result arrays are views of the slot's pinned
+        buffers: they stay valid until ``len(slots)`` further steps have been issued."""
+        i = 0
+        for key, step in (steps.items() if isinstance(steps, dict) else enumerate(steps)):
+            slot = self.slots[i % len(self.slots)]
+            i += 1
+            if slot["event"] is not None:
+                yield self._collect(slot)
+            with self.t.cuda.stream(slot["stream"]):
+                v2d = {"f": step["f"]} if "f" in slot["pipe"].out2d else {}
+                if slot["pipe"].has_hgt:
+                    v2d["hgt"] = step["hgt"]
+                for k in slot["pipe"].out2d:
+                    if k not in v2d:
+                        v2d[k] = step[k]
+                slot["pipe"].upload(step["z3d"], step["vars3d"], v2d)
+                slot["pipe"].run()
+                for k, h in slot["host"].items():
+                    h.copy_(slot["pool"][k], non_blocking=True)
+                ev = self.t.cuda.Event()
+                ev.record(slot["stream"])
+            slot["event"], slot["key"] = ev, key
+        # drain in issue order
+        n = len(self.slots)
+        for j in range(n):
+            slot = self.slots[(i + j) % n]
+            if slot["event"] is not None:
+                yield self._collect(slot)

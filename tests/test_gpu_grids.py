@@ -251,3 +251,35 @@ def test_interplevel_device(golden_setdata):
     assert_same(run(fld, vert, lev, 1), oracle.interplevel(fld, vert, lev), "non-monotone")
     assert_same(run(fld, vert, lev, 1, _lib.MT_IL_INCLUSIVE), oracle.interplevel(fld, vert, lev, inclusive=True),
                 "non-monotone inclusive")
+
+
+def test_time_step_stream_matches_grid_api(golden_setdata):
+    """pipeline.TimeStepStream (two overlapped slots, host in -> host out) == the grid methods."""
+    from meteotools_b200.grids import cylindrical_grid
+    from meteotools_b200.pipeline import TimeStepStream
+    g = golden_setdata
+    dx = float(g["s_dx"])
+    z3d, hgt = g["s_z3d"], g["s_hgt"]
+    p3d = 1e5 * np.exp(-z3d / 8000.0)
+    rng = np.random.default_rng(21)
+
+    def make(k):
+        T = g["s_T"] + 280.0 + k
+        return dict(z3d=z3d, hgt=hgt, f=g["s_f"],
+                    vars3d=dict(T=T, p=p3d + k, qv=1e-3 + 1e-4 * np.abs(g["s_u"]) + 1e-5 * k,
+                                qc=1e-4 * np.abs(g["s_u"]), qr=1e-4 * np.abs(g["s_T"])))
+    steps = [make(k) for k in range(5)]
+    cyl = cylindrical_grid(dict(SD))
+    cyl.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    outs = ["Th", "Tc", "Th_e", "rho", "vapor"]
+    ts = TimeStepStream(cyl, z3d.shape, dx, dx, ["T", "p", "qv", "qc", "qr"], names2d=("f",), hgt=True, outputs=outs)
+    seen = []
+    for k, res in ts.process(steps):
+        ref = cylindrical_grid(dict(SD))
+        ref.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+        ref.set_data(dx, dx, z3d, hgt=hgt, f=g["s_f"], **steps[k]["vars3d"])
+        ref.calc_all_thermaldynamic()
+        for name in outs:
+            assert_same(res[name], getattr(ref, name), f"step {k} {name}")
+        seen.append(k)
+    assert seen == list(range(5))
