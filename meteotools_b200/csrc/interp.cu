@@ -76,18 +76,18 @@ struct VarPtrs {
 // Optional terrain mask: hgt_idx[i] > l  ->  NaN  (cylindrical_grid.py:171-181).
 template <int VEC>
 __global__ void __launch_bounds__(256)
-k_gather2d_lf(VarPtrs vp, int layers, int64_t s_y, int64_t s_x, const int4 *__restrict__ pix,
+k_gather2d_lf(VarPtrs vp, int nvar, int layers, int64_t s_y, int64_t s_x, const int4 *__restrict__ pix,
               const double2 *__restrict__ pw, const double *__restrict__ xloc,
               const double *__restrict__ yloc, double dx, double dy, int lenx, int leny, int64_t n,
               int64_t o_n, const int32_t *__restrict__ hgt_idx)
 {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    const double *__restrict__ src = vp.src[blockIdx.y];
-    double *__restrict__ out = vp.out[blockIdx.y];
     // targets are dealt round-robin over the grid, so that the output rows of a CTA's eight warps
-    // form one contiguous 3840-byte run (sequential output order measured faster than any
-    // source-locality order: profiles/experiments_r01.md)
+    // form one contiguous 3840-byte run per variable (sequential output order measured faster
+    // than any source-locality order: profiles/experiments_r01.md); a warp handles its point for
+    // ALL variables, so the plan entry is read once and the gathers of different variables are
+    // independent loads in flight
     const int64_t stride = (int64_t)gridDim.x * warps_per_block;
     int64_t i = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -105,38 +105,44 @@ k_gather2d_lf(VarPtrs vp, int layers, int64_t s_y, int64_t s_x, const int4 *__re
     int terrain;
     load_plan(i, ix, w, terrain);
     while (i < n) {
-        // software pipeline: the next point's plan entry is requested before this point's four
-        // corner gathers, so an iteration costs one memory round trip instead of two
+        // software pipeline: the next point's plan entry is requested before this point's gathers
         const int64_t inext = i + stride;
         int4 nix = ix;
         double2 nw = w;
         int nter = terrain;
         if (inext < n) load_plan(inext, nix, nw, nter);
-        double *o = out + i * o_n;
         if (ix.x < 0) {
             const double fill = (ix.x == -1) ? MT_SENTINEL : nan_f64();
-            for (int l = lane; l < layers; l += 32) o[l] = fill;
+            for (int v = 0; v < nvar; ++v)
+                for (int l = lane; l < layers; l += 32) vp.out[v][i * o_n + l] = fill;
         } else {
-            const double *row0 = src + ix.z * s_y, *row1 = src + ix.w * s_y;
-            const int64_t c0 = ix.x * s_x, c1 = ix.y * s_x;
+            const int64_t a00 = ix.z * s_y + ix.x * s_x, a10 = ix.z * s_y + ix.y * s_x;
+            const int64_t a01 = ix.w * s_y + ix.x * s_x, a11 = ix.w * s_y + ix.y * s_x;
             if (VEC == 2) {
                 for (int l = lane * 2; l < layers; l += 64) {
-                    const double2 a = *reinterpret_cast<const double2 *>(row0 + c0 + l);
-                    const double2 b = *reinterpret_cast<const double2 *>(row0 + c1 + l);
-                    const double2 c = *reinterpret_cast<const double2 *>(row1 + c0 + l);
-                    const double2 d = *reinterpret_cast<const double2 *>(row1 + c1 + l);
-                    double2 r;
-                    r.x = bilerp(a.x, b.x, c.x, d.x, w.x, w.y);
-                    r.y = bilerp(a.y, b.y, c.y, d.y, w.x, w.y);
-                    if (terrain > l) r.x = nan_f64();
-                    if (terrain > l + 1) r.y = nan_f64();
-                    __stcs(reinterpret_cast<double2 *>(o + l), r);
+#pragma unroll 2
+                    for (int v = 0; v < nvar; ++v) {
+                        const double *__restrict__ src = vp.src[v] + l;
+                        const double2 a = *reinterpret_cast<const double2 *>(src + a00);
+                        const double2 b = *reinterpret_cast<const double2 *>(src + a10);
+                        const double2 c = *reinterpret_cast<const double2 *>(src + a01);
+                        const double2 d = *reinterpret_cast<const double2 *>(src + a11);
+                        double2 r;
+                        r.x = bilerp(a.x, b.x, c.x, d.x, w.x, w.y);
+                        r.y = bilerp(a.y, b.y, c.y, d.y, w.x, w.y);
+                        if (terrain > l) r.x = nan_f64();
+                        if (terrain > l + 1) r.y = nan_f64();
+                        __stcs(reinterpret_cast<double2 *>(vp.out[v] + i * o_n + l), r);
+                    }
                 }
             } else {
                 for (int l = lane; l < layers; l += 32) {
-                    double r = bilerp(row0[c0 + l], row0[c1 + l], row1[c0 + l], row1[c1 + l], w.x, w.y);
-                    if (terrain > l) r = nan_f64();
-                    __stcs(o + l, r);
+                    for (int v = 0; v < nvar; ++v) {
+                        const double *__restrict__ src = vp.src[v] + l;
+                        double r = bilerp(src[a00], src[a10], src[a01], src[a11], w.x, w.y);
+                        if (terrain > l) r = nan_f64();
+                        __stcs(vp.out[v] + i * o_n + l, r);
+                    }
                 }
             }
         }
@@ -353,16 +359,16 @@ int mt_gather2d_lf(const double *const *src, double *const *out, int nvar, int64
     }
     // grid: 16 CTAs per SM was the best of {5,8,16,24,32}; one point per warp iteration beat 2 and 4
     // points in flight and a cp.async.bulk (TMA) ring -- profiles/experiments_r01.md
-    dim3 grid(mt::grid_for(n, 8, 16), (unsigned)nvar);
+    const unsigned grid = mt::grid_for(n, 8, 4);  // 4 CTAs/SM best of {2,4,5,8,16}
     mt::ProfScope prof("k_gather2d_lf", stream);
     auto pix = reinterpret_cast<const int4 *>(plan_ix);
     auto pw = reinterpret_cast<const double2 *>(plan_w);
     if (vec)
         k_gather2d_lf<2><<<grid, 256, 0, (cudaStream_t)stream>>>(
-            vp, (int)layers, s_y, s_x, pix, pw, xloc, yloc, dx, dy, (int)lenx, (int)leny, n, o_n, hgt_idx);
+            vp, nvar, (int)layers, s_y, s_x, pix, pw, xloc, yloc, dx, dy, (int)lenx, (int)leny, n, o_n, hgt_idx);
     else
         k_gather2d_lf<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
-            vp, (int)layers, s_y, s_x, pix, pw, xloc, yloc, dx, dy, (int)lenx, (int)leny, n, o_n, hgt_idx);
+            vp, nvar, (int)layers, s_y, s_x, pix, pw, xloc, yloc, dx, dy, (int)lenx, (int)leny, n, o_n, hgt_idx);
     MT_LAUNCH_CHECK();
     return MT_OK;
 }

@@ -178,12 +178,12 @@ class CylStepPipeline:
                                             D.ptr(self.hgt_idx), self._out_ptrs, g.Nz, self.flags,
                                             D.ptr(self.f_counter), s), "mt_setdata_fused")
         else:
-          _lib.check(lib.mt_setdata(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype, self.nz,
-                                  sny, snx, oy, ox, self.ny, self.nx, self.dx, self.dy, y0, y1, x0, x1,
-                                  D.ptr(self.levels), g.Nz, self.order, self.direction, D.ptr(self.xd),
-                                  D.ptr(self.yd), D.ptr(self.plan[0]), D.ptr(self.plan[1]), self.n,
-                                  D.ptr(self.hgt_idx), self._out_ptrs, 1, g.Nz, self.flags, D.ptr(self.ws),
-                                  self.wsb, s), "mt_setdata")
+            _lib.check(lib.mt_setdata(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype, self.nz,
+                                      sny, snx, oy, ox, self.ny, self.nx, self.dx, self.dy, y0, y1, x0, x1,
+                                      D.ptr(self.levels), g.Nz, self.order, self.direction, D.ptr(self.xd),
+                                      D.ptr(self.yd), D.ptr(self.plan[0]), D.ptr(self.plan[1]), self.n,
+                                      D.ptr(self.hgt_idx), self._out_ptrs, 1, g.Nz, self.flags, D.ptr(self.ws),
+                                      self.wsb, s), "mt_setdata")
         if self.td_names:
             _lib.check(lib.mt_cyl_td(self._tin, self._tout, self.n * g.Nz, D.ptr(self.scratch), s), "mt_cyl_td")
         if self.dyn_names:
