@@ -181,6 +181,7 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
     const int im = decreasing ? 0 : 1, ip = decreasing ? 1 : 0;
     const double sgn = decreasing ? -1.0 : 1.0;
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     for (int l = tid; l < nlev; l += nthr) lev_s[l] = levels[l];
 
     const int64_t ntiles = (ncol + TC - 1) / TC;
@@ -221,8 +222,11 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
             mono_s[tid] = mono ? 1 : 0;
         }
         __syncthreads();
-        for (int e = tid; e < tc * nlev; e += nthr) {  // bracket every (column, level) pair
-            const int j = e / nlev, lev = e - j * nlev;
+        // bracket every (column, level) pair: a warp per column, lanes over the levels (no integer
+        // division in the hot loops: ncu showed this kernel issue-bound, 54 % issue slots)
+        for (int j = warp; j < tc; j += nwarps)
+        for (int lev = lane; lev < nlev; lev += 32) {
+            const int e = j * nlev + lev;
             const double want = lev_s[lev];
             int kp = -1;
             if (mono_s[j]) {
@@ -270,8 +274,9 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
             __syncthreads();  // tile t has landed for every thread
             const T *ft = tiles + (t & 1) * tile_elems;
             double *__restrict__ o = ptrs.out[v] + c0 * nlev;
-            for (int e = tid; e < tc * nlev; e += nthr) {
-                const int j = e / nlev;
+            for (int j = warp; j < tc; j += nwarps)
+            for (int lev = lane; lev < nlev; lev += 32) {
+                const int e = j * nlev + lev;
                 const int kp = kps[e];
                 double r;
                 if (kp == 255) {
