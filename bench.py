@@ -264,6 +264,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=2, help="time steps in flight in the device-resident leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -295,18 +296,33 @@ def main():
     dev3d = {k: torch.from_numpy(v).cuda() for k, v in step["vars3d"].items()}
     dev2d = {"f": torch.from_numpy(step["f"]).cuda(), "hgt": torch.from_numpy(step["hgt"]).cuda()}
     devz = torch.from_numpy(step["z3d"]).cuda()
-    pipe = CylStepPipeline(cyl, (NZ, NY, NX), DX, DX, NAMES3D, names2d=("f",), hgt=True, resident=True)
-    pipe.bind_device(devz, dev3d, dev2d, direction=0)
+    # Two pipeline slots on two CUDA streams: consecutive time steps are independent, so step k+1's
+    # memory-bound ingest kernels may overlap step k's FP64-bound thermodynamics (--streams 1: off)
+    nslots = max(1, args.streams)
+    pipes = [CylStepPipeline(cyl, (NZ, NY, NX), DX, DX, NAMES3D, names2d=("f",), hgt=True, resident=True)
+             for _ in range(nslots)]
+    streams = [torch.cuda.Stream() for _ in range(nslots)]
+    for p_ in pipes:
+        p_.bind_device(devz, dev3d, dev2d, direction=0)
+    pipe = pipes[0]
+
+    def run_steps(k):
+        main = torch.cuda.current_stream()
+        for s_ in streams:
+            s_.wait_stream(main)
+        for i in range(k):
+            with torch.cuda.stream(streams[i % nslots]):
+                pipes[i % nslots].run()
+        for s_ in streams:
+            main.wait_stream(s_)
     clocks = Clocks(local)   # sampled over warm-up + timed region + roofline pass (same kernels)
     clocks.start()
-    for _ in range(args.warmup):
-        pipe.run()
+    run_steps(args.warmup * nslots)
     barrier()
     launches0 = lib.mt_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        pipe.run()
+    run_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
     launches = lib.mt_launch_count() - launches0
@@ -337,7 +353,7 @@ def main():
     # (a) one step at a time through the grid methods; (b) a stream of time steps through
     # pipeline.TimeStepStream, which overlaps step k's D2H with step k+1's H2D (full-duplex PCIe).
     # Every step uploads its source boxes and downloads its 13 thermodynamic outputs in both.
-    del pipe, dev3d, devz
+    del pipe, pipes, dev3d, devz
     torch.cuda.empty_cache()
     td_names = list(_lib.TD_OUT)
 
@@ -381,7 +397,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(),
-            "clocks": clk, "gpu_launches": int(launches),
+            "clocks": clk, "gpu_launches": int(launches), "steps_in_flight": nslots,
             "e2e": {"value": world * NPTS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": n_stream,
                     "path": "pipeline.TimeStepStream.process (pinned host arrays in -> pinned host arrays out, "
