@@ -182,6 +182,35 @@ int mt_setdata_fused(const void *const *fields, int nvar, const void *vert, int 
                      double *const *out, int64_t o_n, int flags, int32_t *counter,
                      mt_stream_t stream);
 
+/* set_data as one warp-specialised TMA kernel (csrc/setdata_tma.cu): same contract as
+ * mt_setdata_fused, with these differences.  Each field is read through a 3-D TMA tensor map with
+ * a {16, 5, nz} box, and the TMA unit needs every box to start on a 16-byte boundary, hence:
+ *   - source rows must start 16-byte aligned: `row_pitch` (elements between consecutive rows,
+ *     >= nx; the plane pitch is ny*row_pitch) times the element size must be a multiple of 16;
+ *   - tiles are MT_TMA_TILE_W_F64 x MT_TMA_TILE_H source cells for float64 sources and
+ *     MT_TMA_TILE_W_F32 x MT_TMA_TILE_H for float32 sources (the 16-column box covers the tile's
+ *     tile_w + 1 columns), and every item's tile_x - org_x must be a multiple of 2 (float64) / 4
+ *     (float32) -- a PRECONDITION on `items` that the library cannot check without reading them
+ *     back (a violation ends in cudaErrorIllegalInstruction).
+ * `direction` must be 0 or 1 (decided by the caller from column (0,0) of the full coordinate
+ * array).  mt_setdata_tma_supported() tells whether a shape can take this path (otherwise use
+ * mt_setdata: same results, two kernels). */
+#define MT_TMA_TILE_W_F64 14
+#define MT_TMA_TILE_W_F32 12
+#define MT_TMA_TILE_H 4
+int mt_setdata_tma_supported(int dtype, int64_t nz, int64_t nlev, int64_t row_pitch);
+int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz,
+                   int64_t ny, int64_t nx, int64_t row_pitch, int64_t org_y, int64_t org_x,
+                   const double *levels, int64_t nlev, int direction, const int32_t *plan_ix,
+                   const double *plan_w, int64_t n, const int32_t *order, const int32_t *items,
+                   int64_t nitems, int64_t nflagged, const int32_t *hgt_idx, double *const *out,
+                   int64_t o_n, int flags, int32_t *counter, mt_stream_t stream);
+
+/* mt_upload_box with a padded device row pitch (elements): dev is (nz, y1-y0, dev_row_pitch). */
+int mt_upload_box_pitched(const void *host, int elem_bytes, int64_t nz, int64_t ny, int64_t nx,
+                          int64_t y0, int64_t y1, int64_t x0, int64_t x1, void *dev,
+                          int64_t dev_row_pitch, mt_stream_t stream);
+
 /* terrain index of the cylindrical grid (cylindrical_grid.py:141-170): hgt (nt x nr, C-order)
  * -> hgt_idx int32 incl. the edge/corner fix-up.  Cartesian mask (cartesian_grid.py:127-136):
  * var[k,j,i] = NaN where z[k] <= hgt[j,i]. */

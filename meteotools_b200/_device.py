@@ -96,19 +96,29 @@ def to_host(x):
     return h.numpy()
 
 
+def box_pitch(width, itemsize=None):
+    """Row pitch (elements) of a staged box: a multiple of 4 elements, so that rows of float32 and
+    float64 boxes alike start 16-byte aligned and the TMA path of set_data (mt_setdata_tma) can read
+    the staging buffer through a tensor map; one pitch for both dtypes keeps mixed batches aligned."""
+    return (int(width) + 3) // 4 * 4
+
+
 def upload_box(a, y0, y1, x0, x1, out=None):
-    """Column box of a C-order (nz,ny,nx) host array -> dense device tensor (same dtype) with one
-    strided DMA (mt_upload_box); no host-side crop copy."""
+    """Column box of a C-order (nz,ny,nx) host array -> device tensor (nz, y1-y0, pitch) of the
+    same dtype, pitch = box_pitch(x1-x0) (valid columns first, the padding is never read), with
+    one strided DMA (mt_upload_box_pitched); no host-side crop copy."""
     t = require_cuda()
     a = np.asarray(a)
     if a.dtype not in (np.float32, np.float64) or not a.flags.c_contiguous:
         a = np.ascontiguousarray(a, dtype=np.float64)
     nz, ny, nx = a.shape
+    pitch = box_pitch(x1 - x0, a.dtype.itemsize)
     if out is None:
-        out = t.empty((nz, y1 - y0, x1 - x0), dtype=t.float32 if a.dtype == np.float32 else t.float64,
+        out = t.empty((nz, y1 - y0, pitch), dtype=t.float32 if a.dtype == np.float32 else t.float64,
                       device="cuda")
-    _lib.check(_lib.load().mt_upload_box(ct.c_void_p(a.ctypes.data), a.dtype.itemsize, nz, ny, nx, y0, y1,
-                                         x0, x1, ptr(out), stream()), "mt_upload_box")
+    assert tuple(out.shape) == (nz, y1 - y0, pitch), (tuple(out.shape), (nz, y1 - y0, pitch))
+    _lib.check(_lib.load().mt_upload_box_pitched(ct.c_void_p(a.ctypes.data), a.dtype.itemsize, nz, ny, nx, y0, y1,
+                                                 x0, x1, ptr(out), pitch, stream()), "mt_upload_box_pitched")
     out._mt_keepalive = a   # the async DMA reads `a` until the stream reaches this point
     return out
 

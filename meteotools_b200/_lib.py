@@ -23,6 +23,12 @@ LIB_PATH = os.path.join(path_of_meteotools, "lib",
 MT_F64, MT_F32 = 0, 1
 MT_IL_INCLUSIVE, MT_IL_ROUND_F32 = 1, 2
 MT_MAX_VARS = 16
+MT_TMA_TILE_W_F64, MT_TMA_TILE_W_F32, MT_TMA_TILE_H = 14, 12, 4   # source cells per tile of mt_setdata_tma
+
+
+def tma_tile(dtype):
+    """(tile_w, tile_h, column alignment of the tile origin) of mt_setdata_tma for MT_F64 / MT_F32."""
+    return (MT_TMA_TILE_W_F32, MT_TMA_TILE_H, 4) if dtype == MT_F32 else (MT_TMA_TILE_W_F64, MT_TMA_TILE_H, 2)
 MT_LAYOUT_ZTR, MT_LAYOUT_TRZ = 0, 1
 MT_STAGE_A, MT_STAGE_B, MT_STAGE_ALL = 1, 2, 3
 FD_KINDS = {"FD2": 0, "FD4": 1, "FD2_front": 2, "FD2_back": 3, "FD2_2": 4, "FD2_2_front": 5,
@@ -106,6 +112,12 @@ _SIGS = {
     "mt_setdata_fused": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
                                  c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_vp, c_vp,
                                  c_i64, c_int, c_vp, c_vp]),
+    "mt_setdata_tma_supported": (c_int, [c_int, c_i64, c_i64, c_i64]),
+    "mt_setdata_tma": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
+                               c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_int,
+                               c_vp, c_vp]),
+    "mt_upload_box_pitched": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                      c_vp]),
     "mt_terrain_index_cyl": (c_int, [c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_vp]),
     "mt_terrain_mask_cyl": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "mt_terrain_mask_car": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),

@@ -1,0 +1,555 @@
+// set_data as ONE warp-specialised TMA kernel (F1, SURVEY 8a rows a1 + a5 + a7 fused):
+// vertical interpolation (wrf.interplevel, grids/cylindrical_grid.py:113) -> bilinear gather
+// (interp2D_fast_layers, fastcompute.f90:60-109) -> terrain mask (cylindrical_grid.py:171-181).
+// The level-interpolated columns never leave shared memory: the [by][bx][nlev] intermediate of the
+// two-kernel path (522 MB written + 429 MB re-read on S2) does not exist.
+//
+// Work decomposition (by SOURCE tile): the targets are bucketed once per plan (host side) by the
+// 14 x 4 block of source cells that holds their (x0, y0) corner; a work item = (tile, <= 128 of its
+// targets).  A tile needs 15 x 5 source columns -> one 3-D TMA box {16, 5, nz} per field: 128-byte
+// rows, dense [nz][5][16] in shared memory.
+//
+// One persistent CTA per SM = 16 consumer warps + 1 producer warp:
+//   producer  takes items from an atomic counter, stages the item's targets (stencil corners as
+//             tile-local column ids, weights, terrain index, output row) into a 3-deep ring of
+//             shared-memory tables -- software-pipelined ONE ITEM AHEAD, one dependent global load
+//             per issued tile, so its latency never meets the consumers -- and streams the tiles
+//             coordinate, var 0, var 1, ... of consecutive items through a ring of TMA stages
+//             (full/empty mbarriers); the prefetch runs across item boundaries.
+//   consumers per item: monotonicity check + bracket search (kp, w2) on the coordinate tile, once
+//             for all variables; then per variable  B: level-interpolated columns lev[80][nlev] in
+//             shared memory (lanes over columns: conflict-free on the dense TMA layout),
+//             C: one warp per target, lanes over the contiguous level index, three lerps in the
+//             order of fastcompute.f90:100-102, one 16-byte streaming store per lane.
+// Consumers never read global memory; they only wait on mbarriers and store results.
+// Arithmetic and its order are identical to k_interplevel_tile + k_gather2d_lf (bit-exact tests).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace {
+
+using mt::nan_f64;
+
+// The TMA unit requires the global address of a box to be 16-byte aligned: tiles start at even
+// (float64) / multiple-of-4 (float32) columns and are 14 / 12 cells wide, so that the 16-column box
+// holds the tile's width + 1 columns (measured: an odd start column -> cudaErrorIllegalInstruction).
+constexpr int BX = 16, BY = MT_TMA_TILE_H + 1, NC = BX * BY;   // columns per box: 16 x 5 = 80
+static_assert(MT_TMA_TILE_W_F64 + 1 <= BX && MT_TMA_TILE_W_F64 % 2 == 0, "float64 tile width");
+static_assert(MT_TMA_TILE_W_F32 + 1 <= BX && MT_TMA_TILE_W_F32 % 4 == 0, "float32 tile width");
+constexpr int NCONS = 512, NTHREADS = NCONS + 32;
+constexpr int MAXT = 128;                               // targets per item
+constexpr int NMETA = 3;                                // target-table ring
+static_assert(BX == 16 && NC == 80, "index arithmetic below assumes a 16 x 5 column tile");
+
+struct __align__(64) TmaParams {
+    CUtensorMap maps[MT_MAX_VARS + 1];   // [0]: vertical coordinate, [v+1]: variable v
+    double *out[MT_MAX_VARS];
+};
+
+struct Meta {   // one staged target
+    double fx, fy;
+    int target, terrain;
+    unsigned char c00, c10, c01, c11;
+    int pad;
+};
+static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
+
+template <typename T, bool INCLUSIVE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, int LP, int stages,
+              int stage_bytes, int org_x, int org_y, const double *__restrict__ levels, int decreasing,
+              int round_f32, const int4 *__restrict__ pix, const double2 *__restrict__ pw,
+              const int32_t *__restrict__ order, const int4 *__restrict__ items, int nitems,
+              int *__restrict__ counter, const int32_t *__restrict__ hgt_idx, int64_t o_n, int off_w2,
+              int off_lev, int off_kp, int off_meta, int off_misc)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    // TMA destinations must be 128-byte aligned
+    unsigned char *smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    double *w2s = reinterpret_cast<double *>(smem + off_w2);                  // [nlev][NC]
+    double *lev = reinterpret_cast<double *>(smem + off_lev);                 // [NC][LP]
+    unsigned char *kps = smem + off_kp;                                       // [nlev][NC]
+    Meta *meta = reinterpret_cast<Meta *>(smem + off_meta);                   // [NMETA][MAXT]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + off_misc);           // [8]
+    uint64_t *empty = full + 8;                                               // [8]
+    int4 *s_item4 = reinterpret_cast<int4 *>(empty + 8);                      // [4]
+    int *s_itemid = reinterpret_cast<int *>(s_item4 + 4);                     // [4]
+    double *lev_s = reinterpret_cast<double *>(s_itemid + 4);                 // [nlev]
+    unsigned char *mono_s = reinterpret_cast<unsigned char *>(lev_s + nlev);  // [2][NC]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = nvar + 1;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int l = tid; l < nlev; l += NTHREADS) lev_s[l] = levels[l];
+    if (tid < 2 * NC) mono_s[tid] = 1;
+    __syncthreads();
+
+    if (warp == NCONS / 32) {
+        // =============================== producer warp ===============================
+        int q_slot = 0;
+        uint32_t q_par = 1;  // a fresh mbarrier passes a wait on parity 1: the ring starts empty
+        int n = 0;
+        // staging pipeline of the NEXT item (registers)
+        int nid = 0;
+        int4 nit = make_int4(0, 0, 0, 0);
+        int tgt[4];
+        int4 six[4];
+        double2 sw[4];
+        int ster[4];
+        auto stage_phase = [&](int ph, int slot_meta) {
+            switch (ph) {
+                case 0:
+                    if (lane == 0) nid = atomicAdd(counter, 1);
+                    break;
+                case 1:
+                    nid = __shfl_sync(0xffffffffu, nid, 0);
+                    if (nid < nitems) nit = items[nid];
+                    else nit = make_int4(0, 0, 0, 0);
+                    break;
+                case 2:
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = lane + 32 * k;
+                        tgt[k] = j < nit.w ? order[nit.z + j] : -1;
+                    }
+                    break;
+                case 3:
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (tgt[k] >= 0) {
+                            six[k] = pix[tgt[k]];
+                            sw[k] = pw[tgt[k]];
+                            ster[k] = hgt_idx ? hgt_idx[tgt[k]] : 0;
+                        }
+                    break;
+                case 4: {
+                    Meta *mt_ = meta + slot_meta * MAXT;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (tgt[k] >= 0) {
+                            Meta m;
+                            m.fx = sw[k].x, m.fy = sw[k].y, m.target = tgt[k], m.terrain = ster[k];
+                            m.c00 = (unsigned char)((six[k].z - nit.y) * BX + (six[k].x - nit.x));
+                            m.c10 = (unsigned char)((six[k].z - nit.y) * BX + (six[k].y - nit.x));
+                            m.c01 = (unsigned char)((six[k].w - nit.y) * BX + (six[k].x - nit.x));
+                            m.c11 = (unsigned char)((six[k].w - nit.y) * BX + (six[k].y - nit.x));
+                            m.pad = 0;
+                            mt_[lane + 32 * k] = m;
+                        }
+                    __syncwarp();
+                    break;
+                }
+                default: break;
+            }
+        };
+        for (int ph = 0; ph < 5; ++ph) stage_phase(ph, 0);  // first item: synchronously
+        while (true) {
+            const int id = nid;
+            const int4 it = nit;
+            if (id >= nitems) {  // end marker: complete the phase of the next stage without data
+                if (lane == 0) {
+                    mbar_wait(empty + q_slot, q_par);
+                    s_itemid[n & 3] = -1;
+                    mbar_arrive(full + q_slot);
+                }
+                break;
+            }
+            int ph = 0;
+            for (int t = 0; t < NT; ++t) {
+                if (lane == 0) {
+                    mbar_wait(empty + q_slot, q_par);
+                    if (t == 0) {
+                        s_itemid[n & 3] = id;
+                        s_item4[n & 3] = it;
+                    }
+                    mbar_expect_tx(full + q_slot, (uint32_t)(NC * nz * (int)sizeof(T)));
+                    tma_load_3d(smem + (size_t)q_slot * stage_bytes, &P.maps[t], full + q_slot, it.x - org_x,
+                                it.y - org_y, 0);
+                }
+                if (++q_slot == stages) q_slot = 0, q_par ^= 1u;
+                __syncwarp();
+                if (ph < 5) stage_phase(ph++, (n + 1) % NMETA);
+            }
+            while (ph < 5) stage_phase(ph++, (n + 1) % NMETA);
+            ++n;
+        }
+        return;
+    }
+
+    // ================================= consumers =================================
+    const int im = decreasing ? 0 : 1, ip = decreasing ? 1 : 0;
+    const double sgn = decreasing ? -1.0 : 1.0;
+    const int stage_elems = stage_bytes / (int)sizeof(T);
+    const T *raw = reinterpret_cast<const T *>(smem);
+    const int c_first = tid % NC, l_first = tid / NC;  // (level, column) walk: column fastest
+    int c_slot = 0;
+    uint32_t c_par = 0;
+    for (int n = 0;; ++n) {
+        mbar_wait(full + c_slot, c_par);
+        if (s_itemid[n & 3] < 0) break;
+        const int cnt = s_item4[n & 3].w;
+        const T *vt = raw + (size_t)c_slot * stage_elems;
+        unsigned char *mono = mono_s + (n & 1) * NC;
+        // monotone (in the chosen direction) per column: six threads per column, 1/6 of the pairs each
+        if (tid < 6 * NC) {
+            const int per = (nz - 1 + 5) / 6;
+            const int k0 = l_first * per, k1 = min(k0 + per, nz - 1);
+            bool ok = true;
+            for (int k = k0; k < k1; ++k)
+                ok = ok && (sgn * (double)vt[(k + 1) * NC + c_first] >= sgn * (double)vt[k * NC + c_first]);
+            if (!ok) mono[c_first] = 0;
+        }
+        cons_sync();
+        // brackets (kp, w2) of every (level, column) pair, shared by all variables
+        for (int c = c_first, l = l_first; l < nlev;) {
+            const double want = lev_s[l];
+            int kp = -1;
+            if (mono[c]) {
+                const double ww = sgn * want;  // upper bound: first K with sgn*v[K] > ww
+                int lo = 0, hi = nz;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sgn * (double)vt[mid * NC + c] > ww) hi = mid;
+                    else lo = mid + 1;
+                }
+                const int K = lo;
+                if (K >= 1 && K <= nz - 1) {
+                    if (INCLUSIVE) kp = K;
+                    else if (sgn * (double)vt[(K - 1) * NC + c] < ww) kp = K;
+                } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * NC + c] == ww) {
+                    kp = nz - 1;
+                }
+            } else {
+                for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
+                    const double vlo = (double)vt[(q - im) * NC + c], vhi = (double)vt[(q - ip) * NC + c];
+                    const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
+                    if (hit) {
+                        kp = q;
+                        break;
+                    }
+                }
+            }
+            double w2 = 0.0;
+            if (kp >= 0) {
+                const double vlo = (double)vt[(kp - im) * NC + c], vhi = (double)vt[(kp - ip) * NC + c];
+                w2 = (want - vlo) / (vhi - vlo);
+            }
+            kps[l * NC + c] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
+            w2s[l * NC + c] = w2;
+            c += NCONS % NC, l += NCONS / NC;  // advance by 512 pairs
+            if (c >= NC) c -= NC, ++l;
+        }
+        if (tid < NC) mono_s[((n + 1) & 1) * NC + tid] = 1;
+        cons_sync();
+        if (tid == 0) mbar_arrive(empty + c_slot);
+        if (++c_slot == stages) c_slot = 0, c_par ^= 1u;
+
+        const Meta *mt_ = meta + (n % NMETA) * MAXT;
+        for (int v = 0; v < nvar; ++v) {
+            mbar_wait(full + c_slot, c_par);
+            const T *ft = raw + (size_t)c_slot * stage_elems;
+            // B: level-interpolated columns
+            for (int c = c_first, l = l_first; l < nlev;) {
+                const int e = l * NC + c;
+                const int kp = kps[e];
+                double r;
+                if (kp == 255) {
+                    r = nan_f64();
+                } else {
+                    const double w2 = w2s[e];
+                    const double w1 = 1.0 - w2;
+                    r = w1 * (double)ft[(kp - im) * NC + c] + w2 * (double)ft[(kp - ip) * NC + c];
+                    if (round_f32) r = (double)(float)r;
+                }
+                lev[c * LP + l] = r;
+                c += NCONS % NC, l += NCONS / NC;
+                if (c >= NC) c -= NC, ++l;
+            }
+            cons_sync();
+            if (tid == 0) mbar_arrive(empty + c_slot);  // the ring slot may be refilled
+            if (++c_slot == stages) c_slot = 0, c_par ^= 1u;
+            // C: bilinear, one warp per target
+            double *__restrict__ out = P.out[v];
+            for (int j = warp; j < cnt; j += NCONS / 32) {
+                const Meta m = mt_[j];
+                const double *p00 = lev + m.c00 * LP, *p10 = lev + m.c10 * LP;
+                const double *p01 = lev + m.c01 * LP, *p11 = lev + m.c11 * LP;
+                double *o = out + (int64_t)m.target * o_n;
+                for (int l = lane * 2; l < nlev; l += 64) {
+                    const double2 a = *reinterpret_cast<const double2 *>(p00 + l);
+                    const double2 b = *reinterpret_cast<const double2 *>(p10 + l);
+                    const double2 c = *reinterpret_cast<const double2 *>(p01 + l);
+                    const double2 d = *reinterpret_cast<const double2 *>(p11 + l);
+                    const double t0x = (b.x - a.x) * m.fx + a.x, t1x = (d.x - c.x) * m.fx + c.x;  // :100-101
+                    const double t0y = (b.y - a.y) * m.fx + a.y, t1y = (d.y - c.y) * m.fx + c.y;
+                    double2 r;
+                    r.x = (t1x - t0x) * m.fy + t0x;  // :102
+                    r.y = (t1y - t0y) * m.fy + t0y;
+                    if (m.terrain > l) r.x = nan_f64();
+                    if (m.terrain > l + 1) r.y = nan_f64();
+                    __stcs(reinterpret_cast<double2 *>(o + l), r);
+                }
+            }
+            if (v + 1 < nvar) cons_sync();  // `lev` is rewritten by the next variable
+        }
+    }
+}
+
+// targets whose coordinates are NaN / the legacy sentinel: no stencil, just the fill value
+struct OutPtrs {
+    double *out[MT_MAX_VARS];
+};
+__global__ void k_fill_flagged2(OutPtrs ptrs, int nvar, const int4 *__restrict__ pix, int64_t n, int nlev,
+                                int64_t o_n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int flag = pix[i].x;
+        if (flag >= 0) continue;
+        const double fill = flag == -1 ? MT_SENTINEL : nan_f64();
+        for (int v = 0; v < nvar; ++v)
+            for (int l = 0; l < nlev; ++l) ptrs.out[v][i * o_n + l] = fill;
+    }
+}
+
+// ---- host side: tensor maps (cached per source buffer) ---------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }();
+    return fn;
+}
+
+struct MapKey {
+    const void *ptr;
+    int64_t nz, ny, nx, pitch;
+    int dtype;
+    bool operator==(const MapKey &o) const
+    {
+        return ptr == o.ptr && nz == o.nz && ny == o.ny && nx == o.nx && pitch == o.pitch && dtype == o.dtype;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const
+    {
+        size_t h = std::hash<const void *>()(k.ptr);
+        for (int64_t v : {k.nz, k.ny, k.nx, k.pitch, (int64_t)k.dtype}) h = h * 1000003u ^ std::hash<int64_t>()(v);
+        return h;
+    }
+};
+
+int tensor_map_for(const void *ptr, int dtype, int64_t nz, int64_t ny, int64_t nx, int64_t pitch, CUtensorMap *out)
+{
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, nz, ny, nx, pitch, dtype};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return MT_OK;
+    }
+    auto enc = encode_fn();
+    if (!enc) {
+        mt::set_error("mt_setdata_tma: cuTensorMapEncodeTiled is not available in this driver");
+        return MT_ECUDA;
+    }
+    const cuuint64_t eb = dtype == MT_F64 ? 8 : 4;
+    cuuint64_t gdim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+    cuuint64_t gstr[2] = {(cuuint64_t)pitch * eb, (cuuint64_t)pitch * (cuuint64_t)ny * eb};
+    cuuint32_t box[3] = {(cuuint32_t)BX, (cuuint32_t)BY, (cuuint32_t)nz};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, dtype == MT_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                           const_cast<void *>(ptr), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        mt::set_error("mt_setdata_tma: cuTensorMapEncodeTiled failed (%d) for a (%lld,%lld,%lld) array, pitch %lld",
+                      (int)r, (long long)nz, (long long)ny, (long long)nx, (long long)pitch);
+        return MT_ECUDA;
+    }
+    if (cache.size() > 512) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return MT_OK;
+}
+
+struct Layout {
+    int stages, stage_bytes, LP, off_w2, off_lev, off_kp, off_meta, off_misc;
+    size_t total;
+};
+
+bool make_layout(int dtype, int64_t nz, int64_t nlev, Layout *L)
+{
+    static const int want = [] {   // MT_TMA_STAGES=2..4: ring depth (experiments); default 3
+        const char *e = getenv("MT_TMA_STAGES");
+        const int v = e ? atoi(e) : 3;
+        return v < 2 ? 2 : (v > 4 ? 4 : v);
+    }();
+    const size_t eb = dtype == MT_F64 ? 8 : 4;
+    const size_t stage = ((size_t)NC * nz * eb + 127) & ~size_t(127);
+    const int LP = (int)((nlev % 4 == 2) ? nlev : nlev + 2);  // even; LP = 2 (mod 4): 2-way conflicts at worst
+    for (int stages = want; stages >= 2; --stages) {
+        size_t off = stage * stages;
+        const size_t off_w2 = off;
+        off += (size_t)nlev * NC * 8;
+        const size_t off_lev = off;
+        off += (size_t)NC * LP * 8;
+        const size_t off_kp = off;
+        off += (size_t)nlev * NC;
+        off = (off + 15) & ~size_t(15);
+        const size_t off_meta = off;
+        off += (size_t)NMETA * MAXT * sizeof(Meta);
+        const size_t off_misc = off;
+        off += 16 * 8 + 4 * 16 + 4 * 4 + (size_t)nlev * 8 + 2 * NC;
+        const size_t total = off + 128;  // slack for the 128-byte alignment of the base
+        if (total <= 227 * 1024) {
+            L->stages = stages, L->stage_bytes = (int)stage, L->LP = LP;
+            L->off_w2 = (int)off_w2, L->off_lev = (int)off_lev, L->off_kp = (int)off_kp;
+            L->off_meta = (int)off_meta, L->off_misc = (int)off_misc;
+            L->total = total;
+            return true;
+        }
+    }
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mt_setdata_tma_supported(int dtype, int64_t nz, int64_t nlev, int64_t row_pitch)
+{
+    if (dtype != MT_F64 && dtype != MT_F32) return 0;
+    const int64_t eb = dtype == MT_F64 ? 8 : 4;
+    if (nz < 2 || nz > 254 || nlev < 2 || nlev % 2 != 0 || (row_pitch * eb) % 16 != 0) return 0;
+    Layout L;
+    if (!make_layout(dtype, nz, nlev, &L)) return 0;
+    return encode_fn() != nullptr ? 1 : 0;
+}
+
+int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz, int64_t ny,
+                   int64_t nx, int64_t row_pitch, int64_t org_y, int64_t org_x, const double *levels,
+                   int64_t nlev, int direction, const int32_t *plan_ix, const double *plan_w, int64_t n,
+                   const int32_t *order, const int32_t *items, int64_t nitems, int64_t nflagged,
+                   const int32_t *hgt_idx, double *const *out, int64_t o_n, int flags, int32_t *counter,
+                   mt_stream_t stream)
+{
+    MT_REQUIRE(fields && vert && levels && plan_ix && plan_w && order && items && out && counter,
+               "mt_setdata_tma: null pointer");
+    MT_REQUIRE(nvar >= 1 && nvar <= MT_MAX_VARS, "mt_setdata_tma: nvar must be 1..%d", MT_MAX_VARS);
+    MT_REQUIRE(dtype == MT_F64 || dtype == MT_F32, "mt_setdata_tma: bad dtype");
+    MT_REQUIRE(direction == 0 || direction == 1, "mt_setdata_tma: direction must be 0 or 1 (decided by the caller "
+                                                 "from column (0,0) of the full coordinate array)");
+    const int64_t eb = dtype == MT_F64 ? 8 : 4;
+    MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 2 && nlev % 2 == 0 && nlev < 2147483647LL && o_n >= nlev &&
+                   o_n % 2 == 0,
+               "mt_setdata_tma: need 2 <= nz <= 254, an even number of levels and an even output pitch");
+    MT_REQUIRE(row_pitch >= nx && (row_pitch * eb) % 16 == 0 && ((uintptr_t)vert % 16) == 0,
+               "mt_setdata_tma: source rows must be 16-byte aligned (row pitch %lld elements)", (long long)row_pitch);
+    Layout L;
+    MT_REQUIRE(make_layout(dtype, nz, nlev, &L), "mt_setdata_tma: tile does not fit in shared memory (nz=%lld, nlev=%lld)",
+               (long long)nz, (long long)nlev);
+    TmaParams P;
+    int rc = tensor_map_for(vert, dtype, nz, ny, nx, row_pitch, &P.maps[0]);
+    if (rc != MT_OK) return rc;
+    OutPtrs op;
+    for (int v = 0; v < nvar; ++v) {
+        MT_REQUIRE(fields[v] && out[v] && ((uintptr_t)out[v] % 16 == 0) && ((uintptr_t)fields[v] % 16 == 0),
+                   "mt_setdata_tma: field %d is null or not 16-byte aligned", v);
+        rc = tensor_map_for(fields[v], dtype, nz, ny, nx, row_pitch, &P.maps[v + 1]);
+        if (rc != MT_OK) return rc;
+        P.out[v] = out[v];
+        op.out[v] = out[v];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const auto pix = reinterpret_cast<const int4 *>(plan_ix);
+    const auto pw = reinterpret_cast<const double2 *>(plan_w);
+    if (nflagged > 0) {
+        mt::ProfScope prof("k_fill_flagged", stream);
+        k_fill_flagged2<<<mt::grid_for(n, 256, 4), 256, 0, s>>>(op, nvar, pix, n, (int)nlev, o_n);
+        MT_LAUNCH_CHECK();
+    }
+    if (nitems == 0) return MT_OK;
+    MT_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), s));
+    int64_t grid64 = mt::sm_count();
+    if (grid64 > nitems) grid64 = nitems;
+    const unsigned grid = (unsigned)grid64;
+    const int rf = (flags & MT_IL_ROUND_F32) ? 1 : 0;
+    mt::ProfScope prof("k_setdata_tma", stream);
+#define ST_LAUNCH(T, INC)                                                                                          \
+    do {                                                                                                           \
+        MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                     (int)L.total));                                                               \
+        k_setdata_tma<T, INC><<<grid, NTHREADS, L.total, s>>>(                                                     \
+            P, nvar, (int)nz, (int)nlev, L.LP, L.stages, L.stage_bytes, (int)org_x, (int)org_y, levels, direction, \
+            rf, pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n,         \
+            L.off_w2, L.off_lev, L.off_kp, L.off_meta, L.off_misc);                                                \
+    } while (0)
+    if (dtype == MT_F64) {
+        if (flags & MT_IL_INCLUSIVE) ST_LAUNCH(double, true);
+        else ST_LAUNCH(double, false);
+    } else {
+        if (flags & MT_IL_INCLUSIVE) ST_LAUNCH(float, true);
+        else ST_LAUNCH(float, false);
+    }
+#undef ST_LAUNCH
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+}  // extern "C"

@@ -7,6 +7,7 @@
 // floating order and every NaN sorts above +inf) into scratch[i]; iteration i+1 starts by
 // reading scratch[i] and returns immediately when it is < 0.1 (or was never written: 0).
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "thermo.cuh"
 
@@ -139,7 +140,7 @@ k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__
 __global__ void __launch_bounds__(256)
 k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, int first,
             unsigned long long *__restrict__ maxbits, int vec_ok, const double *__restrict__ Th,
-            const double *__restrict__ qv, double *__restrict__ Th_e)
+            const double *__restrict__ qv, double *__restrict__ Th_e, int exact)
 {
     namespace cg = cooperative_groups;
     constexpr double logB = 8.597851094433691;  // log(5420)
@@ -151,13 +152,54 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
             for (int it = first; it < 10; ++it) maxbits[it] = maxbits[first - 1];
             reinterpret_cast<double *>(maxbits)[15] = 10.0;
         }
-        auto finish = [&](double t, double gg) {
+        const int nrest = 10 - first;  // sweeps still to run (>= 1); t below is the iterate Tc_first
+        auto finish_exact = [&](double t, double gg) {
             double L = log(t), D = gg - CpRd * L;
             for (int it = first + 1; it < 10; ++it) {
                 L = logB - log(D);
                 D = gg - CpRd * L;
             }
             return B / D;
+        };
+        // The sweeps are the fixed-point iteration L <- F(L) = log B - log(g - a L) on L = log Tc
+        // (a = Cp/Rd, contraction F' = a/D = a Tc/B ~ 0.18).  With L* the fixed point, D* = g - a L*
+        // and c = a/D*, the iterates obey EXACTLY  delta' = -log1p(-c delta)  for delta = L - L*.
+        // After the remaining sweeps delta is ~1e-9, so float32 carries it to ~1e-15 of Tc; what needs
+        // double precision is L* alone: two float32 Newton steps on h(L) = L - F(L) from log Tc_first
+        // and ONE double step (quadratic: error ~0.02 e^2) -- one double log and two double divisions
+        // per point instead of nine logs.  Measured against the literal ten sweeps: <= 3e-13 relative
+        // over T 180..330 K, P 10..1080 hPa, qv 1e-8..0.05 (tests/test_thermo_gpu.py); points outside the
+        // series' range (|c delta|, |Tc_first/Tc* - 1| >= 0.1, no convergence, non-finite) take the
+        // literal sweeps, NaN points (terrain) stay NaN.
+        auto finish = [&](double t, double gg) {
+            if (t != t || gg != gg) return mt::nan_f64();
+            const float gf = (float)gg, af = (float)CpRd, lbf = (float)logB;
+            // MUFU-based float32 log / divide (abs. error ~1e-6 on L): the double step squares it
+            float Lf = __logf((float)t);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float Df = gf - af * Lf;
+                const float hf = Lf - lbf + __logf(Df);
+                Lf = Lf - __fdividef(hf * Df, Df - af);
+            }
+            double L = (double)Lf;
+            double D = gg - CpRd * L;
+            const double h = L - logB + log(D);
+            L = L - h * D / (D - CpRd);
+            D = gg - CpRd * L;
+            const double Tcs = B / D;
+            const float c = __fdividef(af, (float)D);
+            const float d = __fdividef((float)(t - Tcs), (float)Tcs);
+            // delta_first = log1p(d)
+            float dl = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
+            const bool ok = fabs(h) < 1e-4 && fabsf(d) < 0.1f && fabsf(c * dl) < 0.1f && D > 0.0;
+            if (!ok || exact) return finish_exact(t, gg);
+            for (int k = 0; k < nrest; ++k) {
+                const float u = c * dl;  // -log1p(-u) = u + u^2/2 + u^3/3 + ...
+                dl = u * fmaf(u, fmaf(u, fmaf(u, fmaf(u, 0.2f, 0.25f), 0.33333334f), 0.5f), 1.0f);
+            }
+            const float e = fmaf(dl * dl, fmaf(dl, 0.16666667f, 0.5f), dl);  // expm1(delta)
+            return Tcs + Tcs * (double)e;
         };
         const int64_t npair = vec_ok ? (n >> 1) : 0;
         const double2 *__restrict__ g2 = reinterpret_cast<const double2 *>(g);
@@ -172,13 +214,13 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
                 const double2 th = __ldg(reinterpret_cast<const double2 *>(Th) + i);
                 const double2 q = __ldg(reinterpret_cast<const double2 *>(qv) + i);
                 __stcs(reinterpret_cast<double2 *>(Th_e) + i,
-                       make_double2(exp_factor(th.x, q.x, t.x), exp_factor(th.y, q.y, t.y)));
+                       make_double2(exp_factor1(th.x, q.x, t.x), exp_factor1(th.y, q.y, t.y)));
             }
         }
         for (int64_t i = 2 * npair + tid; i < n; i += nthr) {
             const double t = finish(Tc[i], g[i]);
             Tc[i] = t;
-            if (Th_e) __stcs(Th_e + i, exp_factor(__ldg(Th + i), __ldg(qv + i), t));
+            if (Th_e) __stcs(Th_e + i, exp_factor1(__ldg(Th + i), __ldg(qv + i), t));
         }
         return;
     }
@@ -302,8 +344,10 @@ int tc_tail(const double *T, const double *g, double *Tc, int64_t n, unsigned lo
     int64_t want = ((n + 1) / 2 + 255) / 256;
     int64_t cap = (int64_t)mt::sm_count() * blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+    static const int exact_env = (getenv("MT_TC_EXACT") && getenv("MT_TC_EXACT")[0] == '1') ? 1 : 0;
+    int exact = exact_env;  // MT_TC_EXACT=1: the literal sweeps for every point (A/B measurements)
     void *args[] = {(void *)&g, (void *)&Tc, (void *)&n, (void *)&first_iter, (void *)&bits, (void *)&vec_ok,
-                    (void *)&Th, (void *)&qv, (void *)&Th_e};
+                    (void *)&Th, (void *)&qv, (void *)&Th_e, (void *)&exact};
     mt::ProfScope prof("k_tc_finish", (mt_stream_t)s);
     MT_CUDA(cudaLaunchCooperativeKernel((const void *)k_tc_finish, dim3(grid), dim3(256), args, 0, s));
     MT_LAUNCH_CHECK();

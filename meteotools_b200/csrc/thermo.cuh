@@ -53,6 +53,9 @@ __device__ __forceinline__ double exp_factor(double th, double qv, double T)  //
 {
     return th * exp(Lv * qv / Cp / T);
 }
+// same with one division, (Lv/Cp)*qv/T: <= 2 ulp of the exponent (tolerance class), used where the
+// kernel is FP64-issue bound
+__device__ __forceinline__ double exp_factor1(double th, double qv, double T) { return th * exp((Lv / Cp) * qv / T); }
 __device__ __forceinline__ double moist_dTdz(double T, double qvs)                                              // :486
 {
     return -g * ((1 + Lv * qvs / Rd / T) / (Cp + Lv2 * qvs * 0.622 / Rd / (T * T)));

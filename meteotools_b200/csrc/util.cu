@@ -108,3 +108,23 @@ extern "C" int mt_upload_box(const void *host, int elem_bytes, int64_t nz, int64
     MT_CUDA(cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
     return MT_OK;
 }
+
+extern "C" int mt_upload_box_pitched(const void *host, int elem_bytes, int64_t nz, int64_t ny, int64_t nx,
+                                     int64_t y0, int64_t y1, int64_t x0, int64_t x1, void *dev,
+                                     int64_t dev_row_pitch, mt_stream_t stream)
+{
+    MT_REQUIRE(host && dev && (elem_bytes == 4 || elem_bytes == 8), "mt_upload_box_pitched: bad arguments");
+    MT_REQUIRE(nz > 0 && 0 <= y0 && y0 < y1 && y1 <= ny && 0 <= x0 && x0 < x1 && x1 <= nx &&
+                   dev_row_pitch >= x1 - x0,
+               "mt_upload_box_pitched: box outside the array or pitch too small");
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(host), (size_t)nx * elem_bytes, (size_t)nx * elem_bytes, (size_t)ny);
+    p.srcPos = make_cudaPos((size_t)x0 * elem_bytes, (size_t)y0, 0);
+    p.dstPtr = make_cudaPitchedPtr(dev, (size_t)dev_row_pitch * elem_bytes, (size_t)dev_row_pitch * elem_bytes,
+                                   (size_t)(y1 - y0));
+    p.dstPos = make_cudaPos(0, 0, 0);
+    p.extent = make_cudaExtent((size_t)(x1 - x0) * elem_bytes, (size_t)(y1 - y0), (size_t)nz);
+    p.kind = cudaMemcpyHostToDevice;
+    MT_CUDA(cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
+    return MT_OK;
+}

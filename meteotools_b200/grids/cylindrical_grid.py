@@ -148,8 +148,8 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         trz = self._layout == _lib.MT_LAYOUT_TRZ
         if on_dev:   # resident sources: region = the full array
             sny, snx, oy, ox = ny, nx, 0, 0
-        else:        # host sources: region = the box
-            sny, snx, oy, ox = y1 - y0, x1 - x0, y0, x0
+        else:        # host sources: region = the box, rows padded to D.box_pitch (never read)
+            sny, snx, oy, ox = y1 - y0, D.box_pitch(x1 - x0), y0, x0
 
         def stage(a, want32):
             if on_dev:
@@ -179,8 +179,23 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 srcs = [stage(s, use32) for _, s in batch]
                 outs = [self._new() for _ in batch]
                 import os
-                fused = trz and nz <= 254 and self.Nz % 2 == 0 and os.environ.get("MT_SETDATA", "split") == "fused"
-                if fused:   # one kernel, no intermediate in HBM
+                mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
+                fits = trz and nz <= 254 and self.Nz % 2 == 0
+                if fits and mode == "tma" and lib.mt_setdata_tma_supported(dtype, nz, self.Nz, snx):
+                    # one warp-specialised TMA kernel, no intermediate in HBM (csrc/setdata_tma.cu)
+                    tw_, th_, al_ = _lib.tma_tile(dtype)
+                    order_t, items_t, nitems, nflag, counter = self._fused_items_for(
+                        plan, tw_, th_, spatial=True, align=al_, org_x=ox)
+                    _lib.check(lib.mt_setdata_tma(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, sny,
+                                                  snx, snx, oy, ox, D.ptr(levels), self.Nz, direction,
+                                                  D.ptr(plan[0]), D.ptr(plan[1]), n, D.ptr(order_t),
+                                                  D.ptr(items_t), nitems, nflag, D.ptr(hgt_idx),
+                                                  D.ptr_array(outs), self.Nz, flags, D.ptr(counter),
+                                                  D.stream()), 'mt_setdata_tma')
+                    for (name, _), o in zip(batch, outs):
+                        self._put(name, o)
+                    continue
+                if fits and mode == "fused":   # first-generation fused kernel (cp.async), kept for A/B runs
                     th_ = 2 if os.environ.get("MT_SETDATA_TILE") == "16x2" else 4
                     order_t, items_t, nitems, nflag, counter = self._fused_items_for(plan, 16, th_)
                     _lib.check(lib.mt_setdata_fused(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, sny,
@@ -219,12 +234,17 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             self.__dict__.pop('_fused_items', None)
         return plan
 
-    def _fused_items_for(self, plan, tile_w=16, tile_h=4, max_targets=128):
-        """Targets bucketed by source tile for ``mt_setdata_fused`` (built once per plan on the
-        host: an argsort of n keys): (order, items, nitems, nflagged, counter)."""
-        cached = self.__dict__.get('_fused_items')
-        if cached is not None and cached[0] == (plan[2], tile_w, tile_h):
-            return cached[1]
+    def _fused_items_for(self, plan, tile_w=16, tile_h=4, max_targets=128, spatial=False, align=1, org_x=0):
+        """Targets bucketed by source tile for ``mt_setdata_tma`` / ``mt_setdata_fused`` (built once
+        per plan on the host: an argsort of n keys): (order, items, nitems, nflagged, counter).
+        ``spatial``: items stay in row-major tile order, so that CTAs working at the same time share
+        their tile halos in L2 (TMA kernel); otherwise big items first (short tail).
+        ``align``/``org_x``: tile origins satisfy (tile_x - org_x) % align == 0 (the TMA unit needs
+        16-byte aligned box starts: 2 columns for float64, 4 for float32)."""
+        cache = self.__dict__.setdefault('_fused_items', {})
+        key_ = (plan[2], tile_w, tile_h, max_targets, spatial, align, org_x)
+        if key_ in cache:
+            return cache[key_]
         ix = D.to_host(plan[0]).astype(np.int64)
         valid = ix[:, 0] >= 0
         idx = np.nonzero(valid)[0]
@@ -232,6 +252,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         if idx.size:
             x0, y0 = ix[idx, 0], ix[idx, 2]
             bx0, by0 = int(x0.min()), int(y0.min())
+            bx0 = org_x + (bx0 - org_x) // align * align
             tx, ty = (x0 - bx0) // tile_w, (y0 - by0) // tile_h
             ntx = int(tx.max()) + 1
             key = ty * ntx + tx
@@ -243,10 +264,13 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             for s0, e0 in zip(starts, ends):
                 k = int(skey[s0])
                 t_x, t_y = bx0 + (k % ntx) * tile_w, by0 + (k // ntx) * tile_h
-                for c0 in range(s0, e0, max_targets):
-                    rows.append((t_x, t_y, c0, min(max_targets, e0 - c0)))
+                nchunk = -(-(e0 - s0) // max_targets)      # equal chunks, not 128 + remainder
+                per = -(-(e0 - s0) // nchunk)
+                for c0 in range(s0, e0, per):
+                    rows.append((t_x, t_y, c0, min(per, e0 - c0)))
             items = np.array(rows, dtype=np.int32)
-            items = items[np.argsort(-items[:, 3], kind='stable')]   # big items first: short tail
+            if not spatial:
+                items = items[np.argsort(-items[:, 3], kind='stable')]   # big items first: short tail
             order = idx[srt].astype(np.int32)
         else:
             items, order = np.zeros((0, 4), np.int32), np.zeros((1,), np.int32)
@@ -254,7 +278,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         res = (t.from_numpy(order).cuda(), t.from_numpy(np.ascontiguousarray(items)).cuda() if len(items) else
                t.zeros((1, 4), dtype=t.int32, device='cuda'), int(len(items)), nflagged,
                t.zeros((1,), dtype=t.int32, device='cuda'))
-        self.__dict__['_fused_items'] = ((plan[2], tile_w, tile_h), res)
+        cache[key_] = res
         return res
 
     def set_terrain(self):  # :139-176

@@ -72,7 +72,8 @@ class CylStepPipeline:
         self.box = grid._target_box(self.nx, self.ny, self.dx, self.dy)
         y0, y1, x0, x1 = self.box
         self.resident = resident
-        self.region = (self.ny, self.nx, 0, 0) if resident else (y1 - y0, x1 - x0, y0, x0)
+        # host sources are staged box-only with rows padded to D.box_pitch (16-byte aligned rows)
+        self.region = (self.ny, self.nx, 0, 0) if resident else (y1 - y0, D.box_pitch(x1 - x0), y0, x0)
         g = grid
         self.levels = D.to_device(g.z)
         self.order = 1 if np.all(np.diff(g.z) > 0) else (-1 if np.all(np.diff(g.z) < 0) else 0)
@@ -94,13 +95,23 @@ class CylStepPipeline:
         self.scratch = D.empty((16 + self.n * g.Nz,))
         self.direction = -1
         import os
-        self.fused = g.Nz % 2 == 0 and self.nz <= 254 and os.environ.get("MT_SETDATA", "split") == "fused"
-        if self.fused:
+        mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
+        fits = g.Nz % 2 == 0 and self.nz <= 254
+        self.mode = "split"
+        if fits and mode == "tma" and self.lib.mt_setdata_tma_supported(self.mt_dtype, self.nz, g.Nz, self.region[1]):
+            self.mode = "tma"
+            tw_, th_, al_ = _lib.tma_tile(self.mt_dtype)
+            self.f_order, self.f_items, self.f_nitems, self.f_nflag, _ = \
+                g._fused_items_for(self.plan, tw_, th_, spatial=True, align=al_, org_x=self.region[3])
+        elif fits and mode == "fused":
+            self.mode = "fused"
             self.tile_h = 2 if os.environ.get("MT_SETDATA_TILE") == "16x2" else 4
-            self.f_order, self.f_items, self.f_nitems, self.f_nflag, self.f_counter = \
+            self.f_order, self.f_items, self.f_nitems, self.f_nflag, _ = \
                 g._fused_items_for(self.plan, 16, self.tile_h)
+        # the work-item counter is per pipeline: pipelines of one grid may run on different streams
+        self.f_counter = t.zeros((1,), dtype=t.int32, device="cuda")
         if not resident:   # persistent device staging for the uploaded boxes
-            shp = (self.nz, y1 - y0, x1 - x0)
+            shp = (self.nz, y1 - y0, self.region[1])
             self.stage3d = {k: t.empty(shp, dtype=self.t_dtype, device="cuda") for k in self.names3d}
             self.stage_vert = t.empty(shp, dtype=self.t_dtype, device="cuda")
             self.stage2d = {k: t.empty((self.ny, self.nx), dtype=t.float64, device="cuda")
@@ -170,7 +181,14 @@ class CylStepPipeline:
         if self.has_hgt:
             _lib.check(lib.mt_terrain_index_cyl(D.ptr(self.out2d["hgt"]), g.Ntheta, g.Nr, g.z_start, g.dz,
                                                 D.ptr(self.hgt_idx), s), "mt_terrain_index_cyl")
-        if self.fused:
+        if self.mode == "tma":
+            _lib.check(lib.mt_setdata_tma(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype,
+                                          self.nz, sny, snx, snx, oy, ox, D.ptr(self.levels), g.Nz, self.direction,
+                                          D.ptr(self.plan[0]), D.ptr(self.plan[1]), self.n, D.ptr(self.f_order),
+                                          D.ptr(self.f_items), self.f_nitems, self.f_nflag,
+                                          D.ptr(self.hgt_idx), self._out_ptrs, g.Nz, self.flags,
+                                          D.ptr(self.f_counter), s), "mt_setdata_tma")
+        elif self.mode == "fused":
             _lib.check(lib.mt_setdata_fused(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype,
                                             self.nz, sny, snx, oy, ox, D.ptr(self.levels), g.Nz, self.direction,
                                             D.ptr(self.plan[0]), D.ptr(self.plan[1]), self.n, D.ptr(self.f_order),

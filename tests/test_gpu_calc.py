@@ -85,3 +85,28 @@ def test_tc_iteration_semantics(C, golden_calc):
     got, n = C.calc_Tc(Tn, P, qv=qv, return_iterations=True)
     assert n == 10
     assert_close(got, g["o_Tc_nan"], 1e-10, "Tc with NaN")
+
+
+def test_tc_nan_path_wide_range(C):
+    """NaN present => ten certain sweeps, done as: fixed point L* by Newton (two float32 steps, one
+    double step) + the float32 recursion of the deviation (csrc/thermo.cu k_tc_finish).  Checked
+    against the literal ten sweeps of calc/thermaldynamic.py:392-402 over a far wider range than
+    any atmosphere, and on points that must take the literal fallback."""
+    rng = np.random.default_rng(11)
+    n = 400_000
+    T = rng.uniform(180, 330, n)
+    P = np.exp(rng.uniform(np.log(1e3), np.log(1.08e5), n))
+    qv = np.exp(rng.uniform(np.log(1e-8), np.log(0.05), n))
+    T[5] = np.nan
+    # pathological points: almost no contraction / log of a non-positive number in some sweep
+    T[10:14] = [300.0, 250.0, 1e-3, 5e4]
+    P[10:14] = [1e5, 1e2, 1e5, 1e5]
+    qv[10:14] = [5.0, 1e3, 1e-3, 1e-30]
+    with np.errstate(all="ignore"):
+        ref, n_ref = co.Tc(T, P, qv, return_iters=True)
+    got, n_it = C.calc_Tc(T, P, qv=qv, return_iterations=True)
+    assert n_it == n_ref == 10
+    assert_close(got, ref, 1e-10, "Tc wide range")
+    fin = np.isfinite(ref)
+    rel = np.abs(np.asarray(got)[fin] - ref[fin]) / np.abs(ref[fin])
+    assert rel.max() < 5e-12, rel.max()

@@ -180,26 +180,102 @@ def test_set_data_cyl_golden(golden_setdata):
         cyl3.set_data(dx, dx, g["s_z3d"], u=g["s_u"])
 
 
-def test_set_data_fused_kernel_matches_split(golden_setdata, monkeypatch):
-    """The opt-in single-kernel set_data (MT_SETDATA=fused, mt_setdata_fused) gives the same bits
-    as the default two-kernel path, terrain mask and float32 rounding included."""
+def test_set_data_kernel_variants_agree(golden_setdata, monkeypatch):
+    """The three CUDA implementations of set_data -- the default warp-specialised TMA kernel
+    (MT_SETDATA=tma, mt_setdata_tma), the two-kernel path (split, mt_setdata) and the first fused
+    kernel (fused, mt_setdata_fused) -- give the same bits as the reference pipeline, terrain mask
+    and float32 rounding included."""
     g = golden_setdata
+    from meteotools_b200 import _lib
     from meteotools_b200.grids import cylindrical_grid
     dx = float(g["s_dx"])
-    for tile in ("16x4", "16x2"):
-        monkeypatch.setenv("MT_SETDATA", "fused")
+    lib = _lib.load()
+    for mode, tile in (("tma", ""), ("split", ""), ("fused", "16x4"), ("fused", "16x2")):
+        monkeypatch.setenv("MT_SETDATA", mode)
         monkeypatch.setenv("MT_SETDATA_TILE", tile)
         cyl = cylindrical_grid(dict(SD))
         cyl.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
-        cyl.set_data(dx, dx, g["s_z3d"], u=g["s_u"], T=g["s_T"], f=g["s_f"], hgt=g["s_hgt"])
-        assert_same(cyl.u, g["o_sd_cyl_u"], f"fused {tile} u")
-        assert_same(cyl.T, g["o_sd_cyl_T"], f"fused {tile} T")
+        before = dict(lib_profile_names(lib, lambda: cyl.set_data(dx, dx, g["s_z3d"], u=g["s_u"], T=g["s_T"],
+                                                                   f=g["s_f"], hgt=g["s_hgt"])))
+        want = {"tma": "k_setdata_tma", "split": "k_gather2d_lf", "fused": "k_setdata_fused"}[mode]
+        assert want in before, (mode, sorted(before))
+        assert_same(cyl.u, g["o_sd_cyl_u"], f"{mode} {tile} u")
+        assert_same(cyl.T, g["o_sd_cyl_T"], f"{mode} {tile} T")
         u32, z32 = g["s_u"].astype(np.float32), g["s_z3d"].astype(np.float32)
         cyl.set_data(dx, dx, z32, u=u32)
         ref = oracle.interp2D_fast_layers(dx, dx, g["o_sd_xTR"], g["o_sd_yTR"], oracle.interplevel(u32, z32, cyl.z))
-        assert_same(cyl.u, ref, f"fused {tile} float32")
+        assert_same(cyl.u, ref, f"{mode} {tile} float32")
 
 
+def lib_profile_names(lib, fn):
+    """Kernel names (-> launch counts) recorded by the library's per-launch profiler while fn runs."""
+    import ctypes as ct
+    import torch
+    lib.mt_profile_enable(1)
+    try:
+        fn()
+        torch.cuda.synchronize()
+        buf = ct.create_string_buffer(1 << 16)
+        n = lib.mt_profile_fetch(buf, len(buf))
+        text = buf.value.decode()
+    finally:
+        lib.mt_profile_enable(0)
+    out = {}
+    for line in text.splitlines():
+        parts = line.split()
+        if parts:
+            out[parts[0]] = out.get(parts[0], 0) + 1
+    return out
+
+
+@pytest.mark.parametrize("case", ["pressure", "nonmonotone_inclusive", "resident_odd", "many_vars"])
+def test_set_data_tma_against_oracle(case, monkeypatch):
+    """mt_setdata_tma on shapes the golden file does not hold: decreasing (pressure) coordinate,
+    non-monotone columns + the inclusive bracket test, resident device sources with the cylinder
+    at an odd offset (tiles hanging over the array edge: TMA out-of-bounds fill), 16 variables."""
+    import torch
+    from meteotools_b200.grids import cylindrical_grid
+    monkeypatch.setenv("MT_SETDATA", "tma")
+    rng = np.random.default_rng({"pressure": 1, "nonmonotone_inclusive": 2, "resident_odd": 3, "many_vars": 4}[case])
+    nz, ny, nx, dx = 14, 70, 84, 2000.0
+    settings = dict(Nr=30, Ntheta=40, Nz=12, dr=1100, dtheta=2 * np.pi / 40, dz=450, z_start=150,
+                    r_start=0, theta_start=0, vertical_coord_type="z", dt=300)
+    hgt = 900.0 * rng.random((ny, nx))
+    k = np.arange(nz).reshape(-1, 1, 1)
+    z3d = hgt[None] + (7000.0 - hgt[None]) * (k / (nz - 1)) ** 1.3
+    nvar = 16 if case == "many_vars" else 2
+    fields = {f"v{i}": rng.standard_normal((nz, ny, nx)) for i in range(nvar)}
+    vert, inclusive = z3d, False
+    if case == "pressure":
+        settings.update(vertical_coord_type="p", dz=-5000, z_start=95000)   # 95000, 90000, ... Pa
+        vert = 1e5 * np.exp(-z3d / 8000.0)
+    if case == "nonmonotone_inclusive":
+        vert = z3d.copy()
+        vert[5, ::3, ::4] -= 900.0
+        vert[2, 10:20, 10:30] = 150.0 + 450.0 * 3      # exact hits of a target level
+        inclusive = True
+    cyl = cylindrical_grid(settings)
+    cx, cy = (33 * dx + 517.0, 34 * dx + 1311.0) if case != "resident_odd" else (nx * dx - 35e3, 34.5e3)
+    cyl.set_horizontal_location(cx, cy)
+    kw = dict(fields)
+    if case == "resident_odd":
+        cyl.set_data(dx, dx, torch.from_numpy(vert).cuda(), inclusive=inclusive,
+                     **{k_: torch.from_numpy(v).cuda() for k_, v in kw.items()})
+    elif case == "pressure":
+        cyl.set_data(dx, dx, vert, inclusive=inclusive, **kw)
+    else:
+        cyl.set_data(dx, dx, vert, inclusive=inclusive, hgt=hgt, **kw)
+    hidx = None
+    if case not in ("resident_odd", "pressure"):
+        hgt_c = oracle.interp2D_fast(dx, dx, cyl.xTR, cyl.yTR, hgt)
+        hidx = co.cyl_terrain_index(hgt_c, cyl.z_start, cyl.dz)
+    for name, a in fields.items():
+        levf = oracle.interplevel(a, vert, cyl.z, inclusive=inclusive)
+        ref = oracle.interp2D_fast_layers(dx, dx, cyl.xTR, cyl.yTR, levf)
+        if hidx is not None:
+            ref = co.cyl_terrain_mask(ref, hidx)
+        assert_same(getattr(cyl, name), ref, f"{case} {name}")
+        assert np.isfinite(ref).any()
 def test_set_data_car_golden(golden_setdata):
     g = golden_setdata
     from meteotools_b200.grids import cartesian_grid
