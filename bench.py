@@ -437,6 +437,7 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
         # fused set_data (SURVEY 8d formula B): touched source columns of V fields + the coordinate,
         # outputs, plan
         "k_setdata_fused": 8.0 * nz * U * (V + 1) + 8.0 * nlev * n * V + 32.0 * n,
+        "k_setdata_tma": 8.0 * nz * U * (V + 1) + 8.0 * nlev * n * V + 32.0 * n,
         # remaining Tc sweeps (in registers when NaN is present) + theta_e: reads g, Tc, Th, qv;
         # writes Tc, Th_e
         "k_tc_finish": 8.0 * NPTS * 6,

@@ -40,9 +40,14 @@ using mt::nan_f64;
 // (float64) / multiple-of-4 (float32) columns and are 14 / 12 cells wide, so that the 16-column box
 // holds the tile's width + 1 columns (measured: an odd start column -> cudaErrorIllegalInstruction).
 constexpr int BX = 16, BY = MT_TMA_TILE_H + 1, NC = BX * BY;   // columns per box: 16 x 5 = 80
+constexpr int NC_ = NC;
 static_assert(MT_TMA_TILE_W_F64 + 1 <= BX && MT_TMA_TILE_W_F64 % 2 == 0, "float64 tile width");
 static_assert(MT_TMA_TILE_W_F32 + 1 <= BX && MT_TMA_TILE_W_F32 % 4 == 0, "float32 tile width");
-constexpr int NCONS = 512, NTHREADS = NCONS + 32;
+#ifndef MT_TMA_NCONS
+#define MT_TMA_NCONS 512
+#endif
+constexpr int NCONS = MT_TMA_NCONS, NTHREADS = NCONS + 32;   // consumer threads (+ one producer warp)
+constexpr int NG = NCONS / NC_;                              // level groups of the column phases
 constexpr int MAXT = 128;                               // targets per item
 constexpr int NMETA = 3;                                // target-table ring
 static_assert(BX == 16 && NC == 80, "index arithmetic below assumes a 16 x 5 column tile");
@@ -52,13 +57,13 @@ struct __align__(64) TmaParams {
     double *out[MT_MAX_VARS];
 };
 
-struct Meta {   // one staged target
+struct Meta {   // one staged target (three 16-byte words)
     double fx, fy;
-    int target, terrain;
-    unsigned char c00, c10, c01, c11;
-    int pad;
+    long long ooff;            // target * o_n: element offset of the output row
+    int terrain, pad;
+    int b00, b10, b01, b11;    // byte offsets of the four corner columns in `lev`
 };
-static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
+static_assert(sizeof(Meta) == 48, "Meta is read as three 16-byte words");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -95,11 +100,11 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
-template <typename T, bool INCLUSIVE>
+template <typename T, bool INCLUSIVE, bool ROUND>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, int LP, int stages,
               int stage_bytes, int org_x, int org_y, const double *__restrict__ levels, int decreasing,
-              int round_f32, const int4 *__restrict__ pix, const double2 *__restrict__ pw,
+              const int4 *__restrict__ pix, const double2 *__restrict__ pw,
               const int32_t *__restrict__ order, const int4 *__restrict__ items, int nitems,
               int *__restrict__ counter, const int32_t *__restrict__ hgt_idx, int64_t o_n, int off_w2,
               int off_lev, int off_kp, int off_meta, int off_misc)
@@ -175,12 +180,12 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                     for (int k = 0; k < 4; ++k)
                         if (tgt[k] >= 0) {
                             Meta m;
-                            m.fx = sw[k].x, m.fy = sw[k].y, m.target = tgt[k], m.terrain = ster[k];
-                            m.c00 = (unsigned char)((six[k].z - nit.y) * BX + (six[k].x - nit.x));
-                            m.c10 = (unsigned char)((six[k].z - nit.y) * BX + (six[k].y - nit.x));
-                            m.c01 = (unsigned char)((six[k].w - nit.y) * BX + (six[k].x - nit.x));
-                            m.c11 = (unsigned char)((six[k].w - nit.y) * BX + (six[k].y - nit.x));
-                            m.pad = 0;
+                            m.fx = sw[k].x, m.fy = sw[k].y, m.ooff = (long long)tgt[k] * o_n;
+                            m.terrain = ster[k], m.pad = 0;
+                            m.b00 = ((six[k].z - nit.y) * BX + (six[k].x - nit.x)) * LP * 8;
+                            m.b10 = ((six[k].z - nit.y) * BX + (six[k].y - nit.x)) * LP * 8;
+                            m.b01 = ((six[k].w - nit.y) * BX + (six[k].x - nit.x)) * LP * 8;
+                            m.b11 = ((six[k].w - nit.y) * BX + (six[k].y - nit.x)) * LP * 8;
                             mt_[lane + 32 * k] = m;
                         }
                     __syncwarp();
@@ -226,65 +231,78 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     // ================================= consumers =================================
     const int im = decreasing ? 0 : 1, ip = decreasing ? 1 : 0;
     const double sgn = decreasing ? -1.0 : 1.0;
+    const int dhi = decreasing ? -NC : NC;      // element offset from the "lo" sample to the "hi" sample
+    const int klo_missing = decreasing ? 1 : 0; // any pair of valid rows: a missing bracket has w2 = NaN
     const int stage_elems = stage_bytes / (int)sizeof(T);
     const T *raw = reinterpret_cast<const T *>(smem);
-    const int c_first = tid % NC, l_first = tid / NC;  // (level, column) walk: column fastest
+    // (column, level-group) ownership of the column phases: thread -> column tid % 80, levels
+    // tid / 80, +NG, +2 NG, ... (NG * 80 of the consumer threads; no index wrap in the loops)
+    const int c_own = tid % NC, g_own = tid / NC;
+    const bool col_thread = tid < NG * NC;
     int c_slot = 0;
     uint32_t c_par = 0;
     for (int n = 0;; ++n) {
         mbar_wait(full + c_slot, c_par);
         if (s_itemid[n & 3] < 0) break;
         const int cnt = s_item4[n & 3].w;
-        const T *vt = raw + (size_t)c_slot * stage_elems;
+        const T *vt = raw + (size_t)c_slot * stage_elems + c_own;
         unsigned char *mono = mono_s + (n & 1) * NC;
         // monotone (in the chosen direction) per column: six threads per column, 1/6 of the pairs each
-        if (tid < 6 * NC) {
-            const int per = (nz - 1 + 5) / 6;
-            const int k0 = l_first * per, k1 = min(k0 + per, nz - 1);
+        if (col_thread) {
+            const int per = (nz - 1 + NG - 1) / NG;
+            const int k0 = g_own * per, k1 = min(k0 + per, nz - 1);
             bool ok = true;
-            for (int k = k0; k < k1; ++k)
-                ok = ok && (sgn * (double)vt[(k + 1) * NC + c_first] >= sgn * (double)vt[k * NC + c_first]);
-            if (!ok) mono[c_first] = 0;
+            for (int k = k0; k < k1; ++k) ok = ok && (sgn * (double)vt[(k + 1) * NC] >= sgn * (double)vt[k * NC]);
+            if (!ok) mono[c_own] = 0;
         }
         cons_sync();
-        // brackets (kp, w2) of every (level, column) pair, shared by all variables
-        for (int c = c_first, l = l_first; l < nlev;) {
-            const double want = lev_s[l];
-            int kp = -1;
-            if (mono[c]) {
-                const double ww = sgn * want;  // upper bound: first K with sgn*v[K] > ww
-                int lo = 0, hi = nz;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (sgn * (double)vt[mid * NC + c] > ww) hi = mid;
-                    else lo = mid + 1;
-                }
-                const int K = lo;
-                if (K >= 1 && K <= nz - 1) {
-                    if (INCLUSIVE) kp = K;
-                    else if (sgn * (double)vt[(K - 1) * NC + c] < ww) kp = K;
-                } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * NC + c] == ww) {
-                    kp = nz - 1;
-                }
-            } else {
-                for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
-                    const double vlo = (double)vt[(q - im) * NC + c], vhi = (double)vt[(q - ip) * NC + c];
-                    const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
-                    if (hit) {
-                        kp = q;
-                        break;
+        // brackets of every (level, column) pair, shared by all variables: klo = row of the "lo"
+        // sample (kp - im of DINTERP3DZ), w2 = its weight; no bracket -> w2 = NaN, so that
+        // w1*f + w2*f is NaN without a branch in the per-variable loop.  Tables are laid out
+        // [level pair][column][2]: the per-variable loop reads both levels of a pair with one load.
+        if (col_thread) {
+            const bool is_mono = mono[c_own] != 0;
+            for (int l = g_own * 2; l < nlev; l += 2 * NG) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double want = lev_s[l + h];
+                    int kp = -1;
+                    if (is_mono) {
+                        const double ww = sgn * want;  // upper bound: first K with sgn*v[K] > ww
+                        int lo = 0, hi = nz;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sgn * (double)vt[mid * NC] > ww) hi = mid;
+                            else lo = mid + 1;
+                        }
+                        const int K = lo;
+                        if (K >= 1 && K <= nz - 1) {
+                            if (INCLUSIVE) kp = K;
+                            else if (sgn * (double)vt[(K - 1) * NC] < ww) kp = K;
+                        } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * NC] == ww) {
+                            kp = nz - 1;
+                        }
+                    } else {
+                        for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
+                            const double vlo = (double)vt[(q - im) * NC], vhi = (double)vt[(q - ip) * NC];
+                            const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
+                            if (hit) {
+                                kp = q;
+                                break;
+                            }
+                        }
                     }
+                    double w2 = nan_f64();
+                    int klo = klo_missing;
+                    if (kp >= 0) {
+                        klo = kp - im;
+                        const double vlo = (double)vt[klo * NC], vhi = (double)vt[klo * NC + dhi];
+                        w2 = (want - vlo) / (vhi - vlo);
+                    }
+                    kps[(l * NC + c_own * 2) + h] = (unsigned char)klo;   // ((l/2)*NC + c)*2 + h
+                    w2s[(l * NC + c_own * 2) + h] = w2;
                 }
             }
-            double w2 = 0.0;
-            if (kp >= 0) {
-                const double vlo = (double)vt[(kp - im) * NC + c], vhi = (double)vt[(kp - ip) * NC + c];
-                w2 = (want - vlo) / (vhi - vlo);
-            }
-            kps[l * NC + c] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
-            w2s[l * NC + c] = w2;
-            c += NCONS % NC, l += NCONS / NC;  // advance by 512 pairs
-            if (c >= NC) c -= NC, ++l;
         }
         if (tid < NC) mono_s[((n + 1) & 1) * NC + tid] = 1;
         cons_sync();
@@ -294,47 +312,81 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
         const Meta *mt_ = meta + (n % NMETA) * MAXT;
         for (int v = 0; v < nvar; ++v) {
             mbar_wait(full + c_slot, c_par);
-            const T *ft = raw + (size_t)c_slot * stage_elems;
-            // B: level-interpolated columns
-            for (int c = c_first, l = l_first; l < nlev;) {
-                const int e = l * NC + c;
-                const int kp = kps[e];
-                double r;
-                if (kp == 255) {
-                    r = nan_f64();
-                } else {
-                    const double w2 = w2s[e];
-                    const double w1 = 1.0 - w2;
-                    r = w1 * (double)ft[(kp - im) * NC + c] + w2 * (double)ft[(kp - ip) * NC + c];
-                    if (round_f32) r = (double)(float)r;
+            // B: level-interpolated columns, one level PAIR per step (branch-free, 16-byte table
+            // load and 16-byte conflict-free store), two independent pairs per iteration
+            if (col_thread) {
+                const T *fc = raw + (size_t)c_slot * stage_elems + c_own;
+                const uchar2 *kq = reinterpret_cast<const uchar2 *>(kps) + c_own;
+                const double2 *wq = reinterpret_cast<const double2 *>(w2s) + c_own;
+                double *lv = lev + c_own * LP;
+                auto pair = [&](int lp) {   // levels 2 lp, 2 lp + 1
+                    const uchar2 k2 = kq[lp * NC];
+                    const double2 w = wq[lp * NC];
+                    const double f00 = (double)fc[k2.x * NC], f01 = (double)fc[k2.x * NC + dhi];
+                    const double f10 = (double)fc[k2.y * NC], f11 = (double)fc[k2.y * NC + dhi];
+                    double2 r;
+                    r.x = (1.0 - w.x) * f00 + w.x * f01;
+                    r.y = (1.0 - w.y) * f10 + w.y * f11;
+                    if (ROUND) r.x = (double)(float)r.x, r.y = (double)(float)r.y;
+                    return r;
+                };
+                const int npair = nlev >> 1;
+                int lp = g_own;
+                for (; lp + NG < npair; lp += 2 * NG) {
+                    const double2 ra = pair(lp), rb = pair(lp + NG);
+                    *reinterpret_cast<double2 *>(lv + 2 * lp) = ra;
+                    *reinterpret_cast<double2 *>(lv + 2 * (lp + NG)) = rb;
                 }
-                lev[c * LP + l] = r;
-                c += NCONS % NC, l += NCONS / NC;
-                if (c >= NC) c -= NC, ++l;
+                if (lp < npair) *reinterpret_cast<double2 *>(lv + 2 * lp) = pair(lp);
             }
             cons_sync();
             if (tid == 0) mbar_arrive(empty + c_slot);  // the ring slot may be refilled
             if (++c_slot == stages) c_slot = 0, c_par ^= 1u;
-            // C: bilinear, one warp per target
+            // C: bilinear, one warp per target, two consecutive targets per step; the item's targets
+            // are sorted by source cell, so a pair usually shares its four corner columns: one set
+            // of shared-memory loads then serves both
             double *__restrict__ out = P.out[v];
-            for (int j = warp; j < cnt; j += NCONS / 32) {
-                const Meta m = mt_[j];
-                const double *p00 = lev + m.c00 * LP, *p10 = lev + m.c10 * LP;
-                const double *p01 = lev + m.c01 * LP, *p11 = lev + m.c11 * LP;
-                double *o = out + (int64_t)m.target * o_n;
+            const char *levb = reinterpret_cast<const char *>(lev);
+            for (int j = 2 * warp; j < cnt; j += 2 * (NCONS / 32)) {
+                const bool two = j + 1 < cnt;
+                const Meta m0 = mt_[j];
+                const Meta m1 = mt_[two ? j + 1 : j];
+                double *o0 = out + m0.ooff, *o1 = out + m1.ooff;
+                const bool masked = (m0.terrain | m1.terrain) > 0;                       // warp-uniform
+                const bool same = m0.b00 == m1.b00 && m0.b10 == m1.b10 && m0.b01 == m1.b01 && m0.b11 == m1.b11;
                 for (int l = lane * 2; l < nlev; l += 64) {
-                    const double2 a = *reinterpret_cast<const double2 *>(p00 + l);
-                    const double2 b = *reinterpret_cast<const double2 *>(p10 + l);
-                    const double2 c = *reinterpret_cast<const double2 *>(p01 + l);
-                    const double2 d = *reinterpret_cast<const double2 *>(p11 + l);
-                    const double t0x = (b.x - a.x) * m.fx + a.x, t1x = (d.x - c.x) * m.fx + c.x;  // :100-101
-                    const double t0y = (b.y - a.y) * m.fx + a.y, t1y = (d.y - c.y) * m.fx + c.y;
-                    double2 r;
-                    r.x = (t1x - t0x) * m.fy + t0x;  // :102
-                    r.y = (t1y - t0y) * m.fy + t0y;
-                    if (m.terrain > l) r.x = nan_f64();
-                    if (m.terrain > l + 1) r.y = nan_f64();
-                    __stcs(reinterpret_cast<double2 *>(o + l), r);
+                    const double2 a0 = *reinterpret_cast<const double2 *>(levb + m0.b00 + l * 8);
+                    const double2 b0 = *reinterpret_cast<const double2 *>(levb + m0.b10 + l * 8);
+                    const double2 c0 = *reinterpret_cast<const double2 *>(levb + m0.b01 + l * 8);
+                    const double2 d0 = *reinterpret_cast<const double2 *>(levb + m0.b11 + l * 8);
+                    double2 a1 = a0, b1 = b0, c1 = c0, d1 = d0;
+                    if (!same) {
+                        a1 = *reinterpret_cast<const double2 *>(levb + m1.b00 + l * 8);
+                        b1 = *reinterpret_cast<const double2 *>(levb + m1.b10 + l * 8);
+                        c1 = *reinterpret_cast<const double2 *>(levb + m1.b01 + l * 8);
+                        d1 = *reinterpret_cast<const double2 *>(levb + m1.b11 + l * 8);
+                    }
+                    double2 r0, r1;
+                    {   // fastcompute.f90:100-102
+                        const double t0x = (b0.x - a0.x) * m0.fx + a0.x, t1x = (d0.x - c0.x) * m0.fx + c0.x;
+                        const double t0y = (b0.y - a0.y) * m0.fx + a0.y, t1y = (d0.y - c0.y) * m0.fx + c0.y;
+                        r0.x = (t1x - t0x) * m0.fy + t0x;
+                        r0.y = (t1y - t0y) * m0.fy + t0y;
+                    }
+                    {
+                        const double t0x = (b1.x - a1.x) * m1.fx + a1.x, t1x = (d1.x - c1.x) * m1.fx + c1.x;
+                        const double t0y = (b1.y - a1.y) * m1.fx + a1.y, t1y = (d1.y - c1.y) * m1.fx + c1.y;
+                        r1.x = (t1x - t0x) * m1.fy + t0x;
+                        r1.y = (t1y - t0y) * m1.fy + t0y;
+                    }
+                    if (masked) {   // terrain: level index below hgt_idx -> NaN (cylindrical_grid.py:171-181)
+                        if (m0.terrain > l) r0.x = nan_f64();
+                        if (m0.terrain > l + 1) r0.y = nan_f64();
+                        if (m1.terrain > l) r1.x = nan_f64();
+                        if (m1.terrain > l + 1) r1.y = nan_f64();
+                    }
+                    __stcs(reinterpret_cast<double2 *>(o0 + l), r0);
+                    if (two) __stcs(reinterpret_cast<double2 *>(o1 + l), r1);
                 }
             }
             if (v + 1 < nvar) cons_sync();  // `lev` is rewritten by the next variable
@@ -529,24 +581,27 @@ int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dt
     int64_t grid64 = mt::sm_count();
     if (grid64 > nitems) grid64 = nitems;
     const unsigned grid = (unsigned)grid64;
-    const int rf = (flags & MT_IL_ROUND_F32) ? 1 : 0;
+    const bool rf = (flags & MT_IL_ROUND_F32) != 0, inc = (flags & MT_IL_INCLUSIVE) != 0;
     mt::ProfScope prof("k_setdata_tma", stream);
-#define ST_LAUNCH(T, INC)                                                                                          \
+#define ST_LAUNCH(T, INC, RND)                                                                                     \
     do {                                                                                                           \
-        MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+        MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                      (int)L.total));                                                               \
-        k_setdata_tma<T, INC><<<grid, NTHREADS, L.total, s>>>(                                                     \
+        k_setdata_tma<T, INC, RND><<<grid, NTHREADS, L.total, s>>>(                                                \
             P, nvar, (int)nz, (int)nlev, L.LP, L.stages, L.stage_bytes, (int)org_x, (int)org_y, levels, direction, \
-            rf, pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n,         \
-            L.off_w2, L.off_lev, L.off_kp, L.off_meta, L.off_misc);                                                \
+            pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n, L.off_w2,   \
+            L.off_lev, L.off_kp, L.off_meta, L.off_misc);                                                          \
     } while (0)
-    if (dtype == MT_F64) {
-        if (flags & MT_IL_INCLUSIVE) ST_LAUNCH(double, true);
-        else ST_LAUNCH(double, false);
-    } else {
-        if (flags & MT_IL_INCLUSIVE) ST_LAUNCH(float, true);
-        else ST_LAUNCH(float, false);
-    }
+#define ST_DISPATCH(T)                           \
+    do {                                         \
+        if (inc && rf) ST_LAUNCH(T, true, true); \
+        else if (inc) ST_LAUNCH(T, true, false); \
+        else if (rf) ST_LAUNCH(T, false, true);  \
+        else ST_LAUNCH(T, false, false);         \
+    } while (0)
+    if (dtype == MT_F64) ST_DISPATCH(double);
+    else ST_DISPATCH(float);
+#undef ST_DISPATCH
 #undef ST_LAUNCH
     MT_LAUNCH_CHECK();
     return MT_OK;

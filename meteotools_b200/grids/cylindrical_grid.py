@@ -256,7 +256,10 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             tx, ty = (x0 - bx0) // tile_w, (y0 - by0) // tile_h
             ntx = int(tx.max()) + 1
             key = ty * ntx + tx
-            srt = np.argsort(key, kind='stable')
+            # within a tile, targets are ordered by source cell: consecutive targets then usually
+            # share their four corner columns (the TMA kernel loads them once per pair)
+            cell = ((y0 - by0) % tile_h) * tile_w + ((x0 - bx0) % tile_w)
+            srt = np.argsort(key * (tile_w * tile_h) + cell, kind='stable')
             skey = key[srt]
             starts = np.flatnonzero(np.r_[True, skey[1:] != skey[:-1]])
             ends = np.r_[starts[1:], skey.size]
