@@ -334,6 +334,37 @@ int mt_car_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_car_d_out_t *ou
 int mt_azimuthal_mean(const double *var, const mt_grid_t *g, double *sym, double *asy,
                       mt_stream_t stream);
 
+/* ---- reductions and smoothers next to the hot path (csrc/reduce.cu) ------
+ * mt_axis_wsum: weighted NaN-skipping sum along one axis of a strided 3-D view (kept axes a, b;
+ * reduced axis k), the kernel behind calc_Zaverage / calc_Raverage / calc_RZaverage
+ * (calc/averages.py:13-114):
+ *   out[a*o_a + b*o_b] = ( sum_k var[a*s_a + b*s_b + k*s_k] * w[k], NaN products skipped ) / D
+ *   mode 0: D = denom;  mode 1: D = sum of w[k] over the terms that were not skipped (nanmean). */
+int mt_axis_wsum(const double *var, int64_t n_a, int64_t n_b, int64_t n_k, int64_t s_a, int64_t s_b,
+                 int64_t s_k, const double *w, int mode, double denom, double *out, int64_t o_a,
+                 int64_t o_b, mt_stream_t stream);
+/* sym[z,r] = nanmean over theta; asy = var - sym; axisym[z,r] = sym^2 / (sym^2 + nansum(asy^2,
+ * theta) * dtheta / 2 / pi) (cylindrical_grid.py:187-235).  Any of the three outputs may be NULL;
+ * sym and axisym are (nz, nr) C-order, asy has the grid's layout.  Uses g->dt as dtheta. */
+int mt_azimuthal_stats(const double *var, const mt_grid_t *g, double *sym, double *asy, double *axisym,
+                       mt_stream_t stream);
+/* out[0] = nansum( (a*b) * weight ) over the grid (b may be NULL): weight = (wr[r]*wz[z])*fr[r]
+ * (integrated kinetic energy, cylindrical_grid.py:554-575: wr = r*dr*dtheta*dz evaluated on the
+ * host, wz / fr the 0-1 range filters) or, when w2d is given, the explicit (nt, nr) weight
+ * (calc_IKE10 :577-600, with nz = 1).  scratch: MT_NANSUM_SCRATCH doubles of device memory. */
+#define MT_NANSUM_SCRATCH 2048
+int mt_nansum_weighted(const double *a, const double *b, const mt_grid_t *g, const double *wr,
+                       const double *wz, const double *fr, const double *w2d, double *scratch,
+                       double *out, mt_stream_t stream);
+/* One Jacobi pass of the 1-c-1 smoothers of cartesian_grid.py:142-229 on a C-order (n0,n1,n2)
+ * array: out = (sum of the 2*naxes neighbours of `cur` + cur*center_weight) / denom, in the
+ * reference's order of additions; a neighbour outside the array is the frozen ghost cell, i.e. the
+ * ORIGINAL field v0 at the edge point.  naxes = 1 (axis ax_a), 2 (axes ax_a, ax_b) or 3.
+ * `cur` and `out` must not alias (passes ping-pong). */
+int mt_smooth_pass(const double *v0, const double *cur, double *out, int64_t n0, int64_t n1, int64_t n2,
+                   int naxes, int ax_a, int ax_b, double center_weight, double denom,
+                   mt_stream_t stream);
+
 /* ---- staging helpers used by the host-facing wrappers -----------------------------------------
  * out[i] = in[i] as double (f32 -> f64 upcast on the device; exact). */
 int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream);

@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(path_of_meteotools, "lib",
 MT_F64, MT_F32 = 0, 1
 MT_IL_INCLUSIVE, MT_IL_ROUND_F32 = 1, 2
 MT_MAX_VARS = 16
+MT_NANSUM_SCRATCH = 2048
 MT_TMA_TILE_W_F64, MT_TMA_TILE_W_F32, MT_TMA_TILE_H = 14, 12, 4   # source cells per tile of mt_setdata_tma
 
 
@@ -112,6 +113,11 @@ _SIGS = {
     "mt_setdata_fused": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
                                  c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_vp, c_vp,
                                  c_i64, c_int, c_vp, c_vp]),
+    "mt_axis_wsum": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_dbl, c_vp, c_i64,
+                             c_i64, c_vp]),
+    "mt_azimuthal_stats": (c_int, [c_vp, ct.POINTER(mt_grid_t), c_vp, c_vp, c_vp, c_vp]),
+    "mt_nansum_weighted": (c_int, [c_vp, c_vp, ct.POINTER(mt_grid_t), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mt_smooth_pass": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_vp]),
     "mt_setdata_tma_supported": (c_int, [c_int, c_i64, c_i64, c_i64]),
     "mt_setdata_tma": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
                                c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_int,

@@ -3,7 +3,8 @@
 ("ZTR" with t = y, r = x), kernels are the Cartesian instantiation of ``mt_car_d``.
 
 The odd vorticity components of the reference (``zeta_t = dv/dz - dw/dx``, :251) are reproduced
-as written.  Smoothers (:142-229) and range averages (:370-391) are SURVEY 8(f) "next" rows.
+as written.  Smoothers (:142-229, mt_smooth_pass) and range averages (:370-391, mt_axis_wsum) are
+the SURVEY 8(f) rows 2 and 1.
 """
 import numpy as np
 
@@ -227,12 +228,99 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
             self.calc_vorticity_z()
         self._run_car_d(['filamentation_time'], _lib.MT_STAGE_B)
 
-    def smooth1d(self, *a, **k):
-        raise NotImplementedError("smoothers are a later row (SURVEY 8f-2)")
+    # ------------------------------------------------------------------ smoothers (8f-2)
+    def _smooth(self, varname, naxes, ax_a, ax_b, center_weight, passes, dims, var):
+        """`passes` Jacobi sweeps of mt_smooth_pass over a dense C-order (n0,n1,n2) device array
+        (ping-pong buffers; the ghost cells are the ORIGINAL edge values, :159-164)."""
+        lib = _lib.load()
+        v0 = D.to_device(var).contiguous().view(*dims)
+        cur, nxt = v0, None
+        denom = float(2 * naxes + center_weight)
+        for _ in range(int(passes)):
+            nxt = D.empty(dims) if nxt is None or nxt is v0 else nxt
+            _lib.check(lib.mt_smooth_pass(D.ptr(v0), D.ptr(cur), D.ptr(nxt), dims[0], dims[1], dims[2], naxes,
+                                          ax_a, ax_b, float(center_weight), denom, D.stream()), 'mt_smooth_pass')
+            cur, nxt = nxt, (cur if cur is not v0 else None)
+        return cur
 
-    smooth2d = smooth3d = smooth1d
+    def _smooth_source(self, varname):
+        if varname in self._fields and self._fields[varname].ndim == 3:
+            return self.device(varname)           # (Nz, Ny, Nx) C order on the device already
+        return np.asarray(getattr(self, varname), dtype=np.float64)
 
-    def calc_horizontal_average(self, *a, **k):
-        raise NotImplementedError("range averages are a later row (SURVEY 8f-1)")
+    def _smooth_store(self, name, result, shape):
+        result = result.view(*shape)
+        if self._is_field_shape(shape):
+            self._put(name, result, len(shape))
+        else:
+            object.__setattr__(self, name, D.to_host(result))
 
-    calc_vertical_average = calc_horizontal_average
+    def smooth1d(self, varname, axis=0, center_weight=2, passes=1):  # :142-167
+        """1-c-1 smoothing along `axis`; result in smooth1d_<var>."""
+        var = self._smooth_source(varname)
+        shape = tuple(int(x) for x in var.shape)
+        axis %= len(shape)
+        outer = int(np.prod(shape[:axis], dtype=np.int64)) if axis > 0 else 1
+        inner = int(np.prod(shape[axis + 1:], dtype=np.int64)) if axis < len(shape) - 1 else 1
+        out = self._smooth(varname, 1, 1, 0, center_weight, passes, (outer, shape[axis], inner), var)
+        self._smooth_store(f'smooth1d_{varname}', out, shape)
+
+    def smooth2d(self, varname, axis=(1, 2), center_weight=2, passes=1):  # :169-199
+        """Five-point smoothing over the two axes `axis`; result in smooth2d_<var> (and, as in the
+        reference, smooth1d_<var> is reset to zeros of the axis-moved shape, :183)."""
+        var = self._smooth_source(varname)
+        shape = tuple(int(x) for x in var.shape)
+        a0, a1 = int(axis[0]), int(axis[1])
+        moved = (shape[a0], shape[a1]) + tuple(n for i, n in enumerate(shape) if i not in (a0, a1))
+        object.__setattr__(self, f'smooth1d_{varname}', np.zeros(moved))
+        if len(shape) == 3:
+            dims, ax = shape, (a0, a1)
+        elif len(shape) == 2:
+            dims, ax = (1,) + shape, (a0 + 1, a1 + 1)
+        else:
+            raise ValueError('smooth2d supports 2-D and 3-D variables')
+        out = self._smooth(varname, 2, ax[0], ax[1], center_weight, passes, dims, var)
+        self._smooth_store(f'smooth2d_{varname}', out, shape)
+
+    def smooth3d(self, varname, center_weight=2, passes=1):  # :201-229
+        """Seven-point smoothing; result in smooth3d_<var> (smooth1d_<var> is reset to zeros, :213)."""
+        var = self._smooth_source(varname)
+        shape = tuple(int(x) for x in var.shape)
+        if len(shape) != 3:
+            raise ValueError('smooth3d needs a 3-D variable')
+        self.__dict__.pop(f'smooth1d_{varname}', None)
+        setattr(self, f'smooth1d_{varname}', np.zeros(shape))
+        out = self._smooth(varname, 3, 0, 1, center_weight, passes, shape, var)
+        self._smooth_store(f'smooth3d_{varname}', out, shape)
+
+    # ------------------------------------------------------------------ range averages (8f-1)
+    _wsum3 = cylindrical_grid._wsum3
+    _select = staticmethod(cylindrical_grid._select)
+
+    def calc_horizontal_average(self, varname, xmin=np.nan, xmax=np.nan, ymin=np.nan, ymax=np.nan):  # :370-381
+        from ..calc.averages import calc_Zaverage
+        from ..exceptions import DimensionError
+        ndim = len(getattr(self, varname).shape)
+        if ndim == 3:
+            x_sel = self._select(self.x, xmin, xmax)
+            tmp = self._wsum3(varname, 2, x_sel.astype(np.float64), 0, float(np.sum(x_sel)))       # (Nz, Ny)
+            setattr(self, f'havg_{varname}', calc_Zaverage(tmp, self.y, 1, ymin, ymax))
+        elif ndim == 2:   # (y, x)
+            var = self.device(varname) if varname in self._fields else getattr(self, varname)
+            tmp = calc_Zaverage(var, self.x, 1, xmin, xmax)
+            setattr(self, f'havg_{varname}', calc_Zaverage(tmp, self.y, 0, ymin, ymax))
+        else:
+            raise DimensionError('varname is neither 3-D (z, y, x) nor 2-D (y, x)')
+
+    def calc_vertical_average(self, varname, zmin=np.nan, zmax=np.nan):  # :383-391
+        from ..calc.averages import calc_Zaverage
+        from ..exceptions import DimensionError
+        ndim = len(getattr(self, varname).shape)
+        if ndim == 3:
+            z_sel = self._select(self.z, zmin, zmax)
+            out = self._wsum3(varname, 0, z_sel.astype(np.float64), 0, float(np.sum(z_sel)))       # (Ny, Nx)
+            setattr(self, f'zavg_{varname}', D.to_host(out))
+        elif ndim == 1:
+            setattr(self, f'zavg_{varname}', calc_Zaverage(getattr(self, varname), self.z, 0, zmin, zmax))
+        else:
+            raise DimensionError('varname is neither 3-D (z, y, x) nor 1-D (z)')

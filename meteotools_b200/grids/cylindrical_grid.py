@@ -432,6 +432,23 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         else:
             raise AttributeError('u10 and v10 must be set first')
 
+    def calc_kinetic_energy10(self):  # :375-381 (raises when vr10 AND vt10 already exist, as written there)
+        if not self._has('vr10') or not self._has('vt10'):
+            self.calc_vr_vt10()
+            lib = _lib.load()
+            g = self._grid_struct(nz=1)
+            g.layout = _lib.MT_LAYOUT_ZTR
+            din = _lib.mt_dyn_in_t()
+            zero = D.to_device(np.zeros((self.Ntheta, self.Nr)))     # (vr10^2 + vt10^2 + 0^2)/2: same bits
+            din.u, din.v, din.w = self.device('u10').data_ptr(), self.device('v10').data_ptr(), zero.data_ptr()
+            dout = _lib.mt_cyl_d_out_t()
+            ke = self._new(2)
+            dout.kinetic_energy = ke.data_ptr()
+            _lib.check(lib.mt_cyl_d(g, din, dout, _lib.MT_STAGE_A, D.stream()), 'mt_cyl_d')
+            self._put('kinetic_energy10', ke, 2)
+        else:
+            raise AttributeError('w must be set first')
+
     def calc_kinetic_energy(self):  # :366-373
         if not self._has('vr') or not self._has('vt'):
             self.calc_vr_vt()
@@ -513,24 +530,47 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             self.calc_vorticity_z()
         self._run_cyl_d(['filamentation_time', 'strain_region'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
 
-    # ------------------------------------------------------- azimuthal statistics (a13)
-    def calc_axisymmetric_asymmetric(self, varname):  # :214-235
+    # ------------------------------------------------------- azimuthal statistics (a13, 8f-1)
+    def _azimuthal(self, varname, want_axisym):
+        """sym_/asy_(/axisymmetry_) of a 3-D (z,theta,r), 2-D (theta,r) or 1-D (theta) variable
+        through mt_azimuthal_stats (one pass over theta per (z, r))."""
         if varname not in dir(self):
             raise AttributeError(f'no variable named {varname}')
         f = self._fields.get(varname)
-        if f is None or f.ndim != 3:
-            # 2-D / 1-D variables: tiny host reductions, as the reference
-            var = np.asarray(getattr(self, varname))
-            setattr(self, f'sym_{varname}', np.nanmean(var, axis=0) if var.ndim == 2 else np.nanmean(var))
-            setattr(self, f'asy_{varname}', var - getattr(self, f'sym_{varname}'))
-            return
-        var = self.device(varname)
-        sym = D.empty((self.Nz, self.Nr))
-        asy = self._new()
-        _lib.check(_lib.load().mt_azimuthal_mean(D.ptr(var), self._grid_struct(), D.ptr(sym), D.ptr(asy),
-                                                 D.stream()), 'mt_azimuthal_mean')
-        object.__setattr__(self, f'sym_{varname}', D.to_host(sym))
-        self._put(f'asy_{varname}', asy)
+        t = D.torch()
+        if f is not None and f.ndim == 3:
+            var, g = self.device(varname), self._grid_struct()
+            sym, asy = D.empty((self.Nz, self.Nr)), self._new()
+        else:   # (theta, r) or (theta,): the same kernel with nz = 1 (and nr = 1)
+            host = np.asarray(getattr(self, varname))
+            var = self.device(varname) if f is not None else D.to_device(host)
+            g = self._grid_struct(nz=1)
+            g.layout = _lib.MT_LAYOUT_ZTR
+            if host.ndim == 1:
+                g.nr = 1
+            sym, asy = D.empty((1, int(g.nr))), t.empty_like(var)
+        axs = t.empty_like(sym) if want_axisym else None
+        _lib.check(_lib.load().mt_azimuthal_stats(D.ptr(var), g, D.ptr(sym), D.ptr(asy), D.ptr(axs), D.stream()),
+                   'mt_azimuthal_stats')
+
+        def small(x):   # (Nz, Nr) / (Nr,) / scalar, as the reference returns them
+            h = D.to_host(x)
+            if f is not None and f.ndim == 3:
+                return h
+            return h[0] if h.shape[1] > 1 or np.asarray(getattr(self, varname)).ndim == 2 else h[0, 0]
+        object.__setattr__(self, f'sym_{varname}', small(sym))
+        if f is not None:
+            self._put(f'asy_{varname}', asy, f.ndim)
+        else:
+            object.__setattr__(self, f'asy_{varname}', D.to_host(asy))
+        if want_axisym:
+            object.__setattr__(self, f'axisymmetry_{varname}', small(axs))
+
+    def calc_axisymmetric_asymmetric(self, varname):  # :214-235
+        self._azimuthal(varname, False)
+
+    def calc_axisymmetry(self, varname):  # :187-212
+        self._azimuthal(varname, True)
 
     def find_rmw_and_speed(self):  # :300-314
         if not self._has('sym_vt'):
@@ -546,7 +586,123 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         self.wspd_max_RMW = self.sym_wind_speed[np.arange(self.Nz), max_wind_r_idx]
         self.vt_max_RMW = self.sym_vt[np.arange(self.Nz), max_wind_r_idx]
 
-    def calc_horizontal_average(self, *a, **k):
-        raise NotImplementedError("range averages are a later row (SURVEY 8f-1)")
+    # ------------------------------------------------------------ range averages (8f-1)
+    def _wsum3(self, varname, axis, w, mode, denom):
+        """mt_axis_wsum over one logical axis (0: z, 1: theta, 2: r) of a 3-D field in the grid's
+        layout; returns a dense C-order CUDA tensor over the two kept axes."""
+        var = self.device(varname)
+        n = (self.Nz, self.Ntheta, self.Nr)
+        if self._layout == _lib.MT_LAYOUT_TRZ:
+            st = (1, self.Nr * self.Nz, self.Nz)
+        else:
+            st = (self.Ntheta * self.Nr, self.Nr, 1)
+        ka, kb = [i for i in range(3) if i != axis]
+        out = D.empty((n[ka], n[kb]))
+        wd = D.to_device(np.ascontiguousarray(w, dtype=np.float64))
+        _lib.check(_lib.load().mt_axis_wsum(D.ptr(var), n[ka], n[kb], n[axis], st[ka], st[kb], st[axis],
+                                            D.ptr(wd), int(mode), float(denom), D.ptr(out), n[kb], 1,
+                                            D.stream()), 'mt_axis_wsum')
+        return out
 
-    calc_vertical_average = calc_IKE = calc_IKE10 = calc_axisymmetry = calc_horizontal_average
+    @staticmethod
+    def _select(axis, vmin, vmax):
+        from ..calc.averages import convert_nan_to_default_value
+        vmin, vmax = convert_nan_to_default_value(axis, vmin, vmax)
+        return np.logical_and(axis >= vmin, axis <= vmax)
+
+    def calc_horizontal_average(self, varname, tmin=np.nan, tmax=np.nan, rmin=np.nan, rmax=np.nan,
+                                unit='rad'):  # :513-535
+        from ..calc.averages import calc_Raverage, calc_RZaverage
+        from ..exceptions import DimensionError, UnitError
+        if unit == 'deg':
+            tmin, tmax = np.deg2rad(tmin), np.deg2rad(tmax)
+        elif unit == 'rad':
+            pass
+        elif unit == 'index':
+            tmin, tmax = self.theta[tmin], self.theta[tmax]
+        else:
+            raise UnitError('invalid unit: use deg, rad or index')
+        ndim = len(getattr(self, varname).shape)
+        if ndim == 3:
+            t_sel = self._select(self.theta, tmin, tmax)
+            with np.errstate(all='ignore'):
+                tmp = self._wsum3(varname, 1, t_sel.astype(np.float64), 0, float(np.sum(t_sel)))   # (Nz, Nr)
+            setattr(self, f'havg_{varname}', calc_Raverage(tmp, self.r, 1, rmin, rmax))
+        elif ndim == 2:   # (theta, r)
+            var = self.device(varname) if varname in self._fields else getattr(self, varname)
+            setattr(self, f'havg_{varname}', calc_RZaverage(var, self.theta, self.r, rmin, rmax, tmin, tmax))
+        else:
+            raise DimensionError('varname is neither 3-D (z, theta, r) nor 2-D (theta, r)')
+
+    def calc_vertical_average(self, varname, zmin=np.nan, zmax=np.nan):  # :537-546
+        from ..calc.averages import calc_Zaverage
+        from ..exceptions import DimensionError
+        ndim = len(getattr(self, varname).shape)
+        if ndim == 3:
+            z_sel = self._select(self.z, zmin, zmax)
+            out = self._wsum3(varname, 0, z_sel.astype(np.float64), 0, float(np.sum(z_sel)))      # (Ntheta, Nr)
+            setattr(self, f'zavg_{varname}', D.to_host(out))
+        elif ndim == 1:
+            setattr(self, f'zavg_{varname}', calc_Zaverage(getattr(self, varname), self.z, 0, zmin, zmax))
+        else:
+            raise DimensionError('varname is neither 3-D (z, theta, r) nor 1-D (z)')
+
+    def create_filter_axis(self, axis, vmin, vmax):  # :548-552
+        faxis = np.ones(axis.shape)
+        faxis = np.where(axis >= vmin, faxis, 0)
+        faxis = np.where(axis <= vmax, faxis, 0)
+        return faxis
+
+    def _nansum_weighted(self, a, b, g, wr=None, wz=None, fr=None, w2d=None):
+        scratch, out = D.empty((_lib.MT_NANSUM_SCRATCH,)), D.empty((1,))
+        dev = [None if x is None else D.to_device(np.ascontiguousarray(x, dtype=np.float64))
+               for x in (wr, wz, fr, w2d)]
+        _lib.check(_lib.load().mt_nansum_weighted(D.ptr(a), D.ptr(b), g, D.ptr(dev[0]), D.ptr(dev[1]),
+                                                  D.ptr(dev[2]), D.ptr(dev[3]), D.ptr(scratch), D.ptr(out),
+                                                  D.stream()), 'mt_nansum_weighted')
+        return float(D.to_host(out)[0])
+
+    def calc_IKE(self, rmin=np.nan, rmax=np.nan, zmin=np.nan, zmax=np.nan):  # :554-575
+        if not self._has('kinetic_energy'):
+            self.calc_kinetic_energy()
+        if not self._has('rho'):
+            self.calc_rho()
+        if np.isnan(rmin):
+            rmin = self.r[0]
+        if np.isnan(rmax):
+            rmax = self.r[-1]
+        if np.isnan(zmin):
+            zmin = self.z[0]
+        if np.isnan(zmax):
+            zmax = self.z[-1]
+        filter_r = self.create_filter_axis(self.r, rmin, rmax)
+        filter_z = self.create_filter_axis(self.z, zmin, zmax)
+        wr = self.r * self.dr * self.dtheta * self.dz        # r3d*dr*dtheta*dz (:571), per radius
+        self.IKE = self._nansum_weighted(self.device('rho'), self.device('kinetic_energy'), self._grid_struct(),
+                                         wr=wr, wz=filter_z, fr=filter_r)
+
+    def calc_IKE10(self, rmax=np.nan, min_wspd10=0., rho=np.nan):  # :577-600
+        if not self._has('kinetic_energy10'):
+            self.calc_kinetic_energy10()
+        if not self._has('wind_speed10'):
+            self.calc_wind_speed10()
+        if not self._has('rho'):
+            # as written in the reference: the level nearest 10 m is only looked up when rho had
+            # to be computed here; otherwise the `rho` ARGUMENT (default NaN) is used as it is
+            self.calc_rho()
+            zidx = int(np.nanargmin(np.abs(self.z - 10.)))
+            rho3 = self.device('rho')   # (theta, r, z) memory order: level zidx as a dense (theta, r) copy
+            rho2 = D.permute3(rho3.view(-1)[zidx:], (self.Ntheta, self.Nr, 1), (self.Nr * self.Nz, self.Nz, 1))
+            if not np.isnan(rho):
+                rho2 = D.to_device(D.to_host(rho2) * 0 + rho)      # rho[zidx]*0 + rho keeps the NaNs (2-D, small)
+        else:
+            rho2 = D.to_device(np.full((self.Ntheta, self.Nr), float(rho)))
+        r2d = np.stack([self.r] * self.Ntheta)
+        if not np.isnan(rmax):
+            r2d = np.where(r2d <= rmax, r2d, 0.)
+        r2d = np.where(self.wind_speed10 > min_wspd10, r2d, 0.)
+        h = 1.
+        volume = r2d * self.dr * self.dtheta * h
+        g = self._grid_struct(nz=1)
+        g.layout = _lib.MT_LAYOUT_ZTR
+        self.IKE10 = self._nansum_weighted(rho2, self.device('kinetic_energy10'), g, w2d=volume)

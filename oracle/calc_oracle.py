@@ -340,3 +340,108 @@ def cyl_terrain_mask(var, hgt_idx):  # :171-181
 
 def car_terrain_mask(var, z, hgt):  # cartesian_grid.py:127-136
     return np.where(z.reshape(-1, 1, 1) <= hgt[None], np.nan, var)
+
+
+# --------------------------------------------------------------------------- SURVEY 8(f) rows 1-2
+# Range averages (calc/averages.py:13-114), axisymmetry (cylindrical_grid.py:187-212), integrated
+# kinetic energy (:554-600) and the 1-c-1 smoothers (cartesian_grid.py:142-229), restated with the
+# reference's NumPy calls so that the summation order (hence every bit) is NumPy's own.
+def _range(axis, lo, hi):  # averages.py:5-10 + the selection masks
+    lo = axis[0] if np.isnan(lo) else lo
+    hi = axis[-1] if np.isnan(hi) else hi
+    return np.logical_and(axis >= lo, axis <= hi)
+
+
+def Zaverage(var, z_axis, axis, zmin=np.nan, zmax=np.nan):  # averages.py:87-114
+    sel = _range(np.array(z_axis), zmin, zmax)
+    v = np.moveaxis(var, axis, -1)   # check_arrays.py:47 (pre_process_for_1Daverage)
+    return np.nansum(v * sel, axis=-1) / np.sum(sel)
+
+
+def Raverage(var, r_axis, axis, rmin=np.nan, rmax=np.nan):  # averages.py:56-84
+    r_axis = np.array(r_axis)
+    sel = _range(r_axis, rmin, rmax)
+    v = np.moveaxis(var, axis, -1)
+    return np.nansum(v * sel * r_axis, axis=-1) / np.nansum(sel * r_axis)
+
+
+def RZaverage(var, z_axis, r_axis, rmin=np.nan, rmax=np.nan, zmin=np.nan, zmax=np.nan, r_weight=True):  # :13-53
+    zs, rs = _range(z_axis, zmin, zmax), _range(r_axis, rmin, rmax)
+    tmp = np.nanmean(var[zs], axis=0)
+    if r_weight:
+        return np.nansum(tmp * rs * r_axis) / np.nansum(rs * r_axis)
+    return np.nanmean(tmp[rs])
+
+
+def axisymmetry(var, dtheta):  # cylindrical_grid.py:187-235 for (z,theta,r), (theta,r) or (theta,)
+    ax = 1 if var.ndim == 3 else 0
+    sym = np.nanmean(var, axis=ax)
+    asy = var - (sym.reshape(var.shape[0], 1, var.shape[2]) if var.ndim == 3 else sym)
+    ssq = np.nansum(asy ** 2, axis=ax) if var.ndim > 1 else np.nansum(asy ** 2)
+    return sym, asy, sym ** 2 / (sym ** 2 + ssq * dtheta / 2 / np.pi)
+
+
+def IKE(rho_, ke, r, z, dr, dtheta, dz, rmin=np.nan, rmax=np.nan, zmin=np.nan, zmax=np.nan):  # :554-575
+    rmin = r[0] if np.isnan(rmin) else rmin
+    rmax = r[-1] if np.isnan(rmax) else rmax
+    zmin = z[0] if np.isnan(zmin) else zmin
+    zmax = z[-1] if np.isnan(zmax) else zmax
+
+    def filt(axis, lo, hi):  # create_filter_axis :548-552
+        f = np.ones(axis.shape)
+        f = np.where(axis >= lo, f, 0)
+        return np.where(axis <= hi, f, 0)
+    nz, nt, nr = rho_.shape
+    volume = np.stack([np.stack([r] * nt)] * nz) * dr * dtheta * dz
+    volume *= filt(z, zmin, zmax).reshape(-1, 1, 1)
+    volume *= filt(r, rmin, rmax).reshape(1, 1, -1)
+    return np.nansum(rho_ * ke * volume)
+
+
+def IKE10(rho2d, ke10, wspd10, r, dr, dtheta, rmax=np.nan, min_wspd10=0.0):  # :577-600 (rho already 2-D / scalar)
+    r2d = np.stack([r] * ke10.shape[0])
+    if not np.isnan(rmax):
+        r2d = np.where(r2d <= rmax, r2d, 0.)
+    r2d = np.where(wspd10 > min_wspd10, r2d, 0.)
+    return np.nansum(rho2d * ke10 * (r2d * dr * dtheta * 1.))
+
+
+def smooth1d(var, axis=0, center_weight=2, passes=1):  # cartesian_grid.py:142-167
+    v = np.moveaxis(var, axis, 0)
+    shape = list(v.shape)
+    shape[0] += 2
+    tmp = np.zeros(shape)
+    tmp[1:-1], tmp[0], tmp[-1] = v, v[0], v[-1]
+    for _ in range(passes):
+        tmp[1:-1] = (tmp[:-2] + tmp[2:] + tmp[1:-1] * center_weight) / (2 + center_weight)
+    return np.moveaxis(tmp[1:-1], 0, axis)
+
+
+def smooth2d(var, axis=(1, 2), center_weight=2, passes=1):  # :169-199
+    v = np.moveaxis(var, axis[1], 0)
+    v = np.moveaxis(v, axis[0] + 1, 0)
+    shape = list(v.shape)
+    shape[0] += 2
+    shape[1] += 2
+    tmp = np.zeros(shape)
+    tmp[1:-1, 1:-1] = v
+    tmp[0, 1:-1], tmp[-1, 1:-1], tmp[1:-1, 0], tmp[1:-1, -1] = v[0, :], v[-1, :], v[:, 0], v[:, -1]
+    for _ in range(passes):
+        tmp[1:-1, 1:-1] = (tmp[:-2, 1:-1] + tmp[2:, 1:-1] + tmp[1:-1, :-2] + tmp[1:-1, 2:]
+                           + tmp[1:-1, 1:-1] * center_weight) / (4 + center_weight)
+    o = np.moveaxis(tmp[1:-1, 1:-1], 0, axis[0] + 1)
+    return np.moveaxis(o, 0, axis[1])
+
+
+def smooth3d(var, center_weight=2, passes=1):  # :201-229
+    shape = [n + 2 for n in var.shape]
+    tmp = np.zeros(shape)
+    tmp[1:-1, 1:-1, 1:-1] = var
+    tmp[0, 1:-1, 1:-1], tmp[-1, 1:-1, 1:-1] = var[0], var[-1]
+    tmp[1:-1, 0, 1:-1], tmp[1:-1, -1, 1:-1] = var[:, 0, :], var[:, -1, :]
+    tmp[1:-1, 1:-1, 0], tmp[1:-1, 1:-1, -1] = var[:, :, 0], var[:, :, -1]
+    for _ in range(passes):
+        tmp[1:-1, 1:-1, 1:-1] = (tmp[:-2, 1:-1, 1:-1] + tmp[2:, 1:-1, 1:-1] + tmp[1:-1, :-2, 1:-1]
+                                 + tmp[1:-1, 2:, 1:-1] + tmp[1:-1, 1:-1, 2:] + tmp[1:-1, 1:-1, :-2]
+                                 + tmp[1:-1, 1:-1, 1:-1] * center_weight) / (6 + center_weight)
+    return tmp[1:-1, 1:-1, 1:-1]

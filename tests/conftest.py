@@ -38,6 +38,11 @@ def golden_setdata():
     return load_golden("setdata")
 
 
+@pytest.fixture(scope="session")
+def golden_reductions():
+    return load_golden("reductions")
+
+
 def assert_same(a, b, what=""):
     """Bit-exact comparison treating NaN==NaN and checking inf signs."""
     a, b = np.asarray(a), np.asarray(b)

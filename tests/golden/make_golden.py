@@ -258,10 +258,122 @@ def gen_setdata(mt, out):
                o_interplevel_z=oracle.interplevel(fields["T"], z3d, cyl.z))
 
 
+RED_CYL = dict(Nr=14, Ntheta=12, Nz=9, dr=1000, dtheta=2 * np.pi / 12, dz=250, z_start=5, r_start=0,
+               theta_start=0, vertical_coord_type="z", dt=300)
+RED_CAR = dict(Nx=11, Ny=10, Nz=7, dx=2000, dy=2000, dz=250, z_start=100, vertical_coord_type="z",
+               SOR_parameter=1.9, max_iteration_times=10, iteration_tolerance=0.05)
+
+
+def gen_reductions(mt, out):
+    """range averages, axisymmetry, integrated kinetic energy, smoothers --
+    outputs of the unmodified reference functions / grid methods, on fields with terrain-like NaNs."""
+    from meteotools.grids import cartesian_grid, cylindrical_grid
+    C = mt.calc
+    rng = np.random.default_rng(5)
+    with np.errstate(all="ignore"):
+        # calc.averages on plain arrays
+        a = rng.standard_normal((6, 40, 5))
+        a[1, 3:9, 2] = np.nan
+        a[:, 0, 0] = np.nan
+        ax = np.cumsum(0.5 + rng.random(40))
+        out.update(r_a=a, r_ax=ax)
+        out["o_Zavg_1"] = C.calc_Zaverage(a, ax, 1, ax[4], ax[30])
+        out["o_Zavg_1_full"] = C.calc_Zaverage(a, ax, 1)
+        out["o_Ravg_1"] = C.calc_Raverage(a, ax, 1, ax[2], ax[35])
+        a0 = np.ascontiguousarray(np.moveaxis(a, 1, 0))          # (40, 6, 5): axis 0
+        out["o_Zavg_0"] = C.calc_Zaverage(a0, ax, 0, ax[4], ax[30])
+        a2 = np.ascontiguousarray(np.moveaxis(a, 1, 2))          # (6, 5, 40): contiguous axis
+        out["o_Zavg_2"] = C.calc_Zaverage(a2, ax, 2, ax[4], ax[30])
+        out["o_Ravg_2"] = C.calc_Raverage(a2, ax, 2)
+        out["o_Zavg_1d"] = C.calc_Zaverage(a[2, :, 1], ax, 0, ax[1], ax[20])
+        zr = rng.standard_normal((9, 40))
+        zr[2, 5:8] = np.nan
+        zr[:, 11] = np.nan
+        zax = np.arange(9.0) * 250 + 5
+        out.update(r_zr=zr, r_zax=zax)
+        out["o_RZavg"] = C.calc_RZaverage(zr, zax, ax, ax[3], ax[33], zax[1], zax[6])
+        out["o_RZavg_now"] = C.calc_RZaverage(zr, zax, ax, ax[3], ax[33], zax[1], zax[6], r_weight=False)
+        # cylindrical grid methods
+        cyl = cylindrical_grid(dict(RED_CYL))
+        f = synth_cyl_fields(rng, RED_CYL["Nz"], RED_CYL["Ntheta"], RED_CYL["Nr"], cyl.z)
+        for k in f:                                               # terrain-like NaNs
+            f[k][:2, 3:7, 8:] = np.nan
+        f["f"] = 5e-5 + 1e-6 * rng.standard_normal((RED_CYL["Ntheta"], RED_CYL["Nr"]))
+        f["u10"] = 8 * rng.standard_normal((RED_CYL["Ntheta"], RED_CYL["Nr"]))
+        f["v10"] = 8 * rng.standard_normal((RED_CYL["Ntheta"], RED_CYL["Nr"]))
+        for k, v in f.items():
+            setattr(cyl, k, v.copy())
+            out[f"g_rcyl_{k}"] = v
+        cyl.calc_vr_vt()
+        cyl.calc_axisymmetry("vt")
+        cyl.calc_axisymmetry("f")
+        cyl.prof = f["T"][:, 2, 3].copy()
+        cyl.ring = f["f"][:, 4].copy()
+        cyl.calc_axisymmetry("ring")
+        cyl.calc_horizontal_average("T", 0.4, 4.0, 1500., 9000.)
+        cyl.calc_horizontal_average("qv")
+        cyl.calc_horizontal_average("f", 1, 9, 2000., 11000., unit="index")
+        cyl.calc_vertical_average("T", 200., 1600.)
+        cyl.calc_vertical_average("prof", 200., 1600.)
+        cyl.calc_IKE(rmin=2000., rmax=10000., zmin=200., zmax=1800.)
+        ike_a = cyl.IKE
+        cyl.calc_IKE()
+        out["o_rcyl_IKE_range"], out["o_rcyl_IKE"] = np.float64(ike_a), np.float64(cyl.IKE)
+        for k in ("sym_vt", "asy_vt", "axisymmetry_vt", "sym_f", "asy_f", "axisymmetry_f", "sym_ring",
+                  "asy_ring", "axisymmetry_ring", "havg_T", "havg_qv", "havg_f", "zavg_T", "zavg_prof"):
+            out[f"o_rcyl_{k}"] = np.asarray(getattr(cyl, k))
+        # calc_IKE10: rho computed inside (level nearest 10 m), default and explicit rho
+        c10 = cylindrical_grid(dict(RED_CYL))
+        for k in ("u10", "v10", "p", "T", "qv"):
+            setattr(c10, k, f[k].copy())
+        c10.calc_IKE10(rmax=9000., min_wspd10=3.0)
+        out["o_rcyl_IKE10"] = np.float64(c10.IKE10)
+        out["o_rcyl_ke10"] = np.asarray(c10.kinetic_energy10)
+        c10b = cylindrical_grid(dict(RED_CYL))
+        for k in ("u10", "v10", "p", "T", "qv"):
+            setattr(c10b, k, f[k].copy())
+        c10b.calc_IKE10(rho=1.1)
+        out["o_rcyl_IKE10_rho"] = np.float64(c10b.IKE10)
+        c10b.calc_wind_speed10()                                   # rho now exists: the argument is used as is
+        del c10b.kinetic_energy10, c10b.vr10, c10b.vt10
+        c10b.calc_IKE10()
+        out["o_rcyl_IKE10_nanrho"] = np.float64(c10b.IKE10)
+        # Cartesian grid: averages and smoothers
+        car = cartesian_grid(dict(RED_CAR))
+        fc = synth_cyl_fields(rng, RED_CAR["Nz"], RED_CAR["Ny"], RED_CAR["Nx"], car.z)
+        fc["T"][:1, 2:5, 6:] = np.nan
+        fc["f"] = 5e-5 + 1e-6 * rng.standard_normal((RED_CAR["Ny"], RED_CAR["Nx"]))
+        for k in ("T", "u", "f"):
+            setattr(car, k, fc[k].copy())
+            out[f"g_rcar_{k}"] = fc[k]
+        car.calc_horizontal_average("T", 2000., 16000., 4000., 14000.)
+        car.calc_horizontal_average("f", ymin=2000.)
+        car.calc_vertical_average("T", zmax=1200.)
+        for k in ("havg_T", "havg_f", "zavg_T"):
+            out[f"o_rcar_{k}"] = np.asarray(getattr(car, k))
+        for ax_ in range(3):
+            car.smooth1d("u", axis=ax_, center_weight=2, passes=3)
+            out[f"o_rcar_smooth1d_u_{ax_}"] = np.asarray(car.smooth1d_u)
+        car.smooth1d("u", axis=1, center_weight=1.5, passes=1)
+        out["o_rcar_smooth1d_u_cw"] = np.asarray(car.smooth1d_u)
+        car.smooth1d("T", axis=0, passes=2)                       # NaNs spread by one cell per pass
+        out["o_rcar_smooth1d_T"] = np.asarray(car.smooth1d_T)
+        for axes in ((1, 2), (0, 2), (0, 1)):
+            car.smooth2d("u", axis=axes, center_weight=2, passes=4)
+            out[f"o_rcar_smooth2d_u_{axes[0]}{axes[1]}"] = np.asarray(car.smooth2d_u)
+        out["o_rcar_smooth2d_side"] = np.asarray(car.smooth1d_u)     # zeros of the moved shape (:183)
+        car.smooth2d("f", axis=(0, 1), passes=2)
+        out["o_rcar_smooth2d_f"] = np.asarray(car.smooth2d_f)
+        car.smooth3d("u", center_weight=2, passes=10)
+        out["o_rcar_smooth3d_u"] = np.asarray(car.smooth3d_u)
+        car.smooth3d("u", center_weight=0.5, passes=1)
+        out["o_rcar_smooth3d_u_cw"] = np.asarray(car.smooth3d_u)
+
+
 def main():
     mt = import_reference()
     for name, fn in (("interp", gen_interp), ("calc", gen_calc), ("grids", gen_grids),
-                     ("setdata", gen_setdata)):
+                     ("setdata", gen_setdata), ("reductions", gen_reductions)):
         out = {}
         fn(mt, out)
         path = os.path.join(HERE, f"{name}.npz")
