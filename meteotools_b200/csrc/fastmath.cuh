@@ -1,0 +1,76 @@
+// Lean double-precision log / exp for the FP64-issue-bound thermodynamic kernels (a12).
+//
+// CUDA's log/exp cost ~85 / ~65 SASS instructions each on sm_100a, more than half of them moves of
+// 64-bit polynomial constants (UMOV pairs: DFMA takes no 64-bit immediate) and special-case
+// handling.  These versions are table driven (2.5 KB of shared memory), ~20 instructions each:
+//   log x : x = 2^e m, i = top 7 mantissa bits, r_i ~ 1/m from the table, u = fma(m, r_i, -1)
+//           (|u| < 2^-8, exact to one rounding), log x = e ln2 - log r_i + log1p(u), degree-6 series;
+//   exp x : k = rint(64 x / ln2), r = x - k ln2/64 (two-term Cody-Waite), exp x = 2^(k>>6) *
+//           2^((k&63)/64) * (1 + expm1 series of degree 5).
+// Accuracy (measured against NumPy, profiles/experiments_r01.md): log <= 2 ulp for arguments away
+// from 1 (absolute error <= 3.6e-15 everywhere), exp <= 1.3e-15 relative on [-30, 10]: the outputs
+// that use them are tolerance-class (1e-10, north star).  NaN in -> NaN out WITHOUT a branch
+// (terrain-masked points are common); zero, negative, denormal, infinite or |x| >= 690 arguments
+// take CUDA's own function on a rarely taken branch.
+#pragma once
+#include "common.cuh"
+#include "fastmath_tables.inc"
+
+namespace mt {
+namespace fm {
+
+struct Tables {
+    double2 lg[128];   // (r_i, -log r_i)
+    double ex[64];     // 2^(j/64)
+};
+
+static __device__ const double2 g_log_table[128] = {MT_FM_LOG_TABLE};
+static __device__ const double g_exp_table[64] = {MT_FM_EXP_TABLE};
+
+// cooperative copy into shared memory; the caller synchronises the block afterwards
+__device__ __forceinline__ void load_tables(Tables *s)
+{
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s->lg[i] = g_log_table[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s->ex[i] = g_exp_table[i];
+}
+
+// out-of-line slow paths: taken by (almost) no thread, they must not bloat the hot loop
+static __device__ __noinline__ double slow_log(double x) { return log(x); }
+static __device__ __noinline__ double slow_exp(double x) { return exp(x); }
+
+__device__ __forceinline__ double flog(double x, const Tables *t)
+{
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const double2 rt = t->lg[(hi >> 13) & 127];
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double e = (double)((hi >> 20) - 1023);
+    const double u = fma(m, rt.x, -1.0);
+    double q = fma(u, -1.0 / 6, 0.2);
+    q = fma(u, q, -0.25);
+    q = fma(u, q, 1.0 / 3);
+    q = fma(u, q, -0.5);
+    double res = fma(e, MT_FM_LN2, rt.y) + fma(u * u, q, u);
+    if (x < 2.2250738585072014e-308 || x == inf_f64()) res = slow_log(x);   // rare: <= 0, denormal, +inf
+    return (x != x) ? x : res;
+}
+
+__device__ __forceinline__ double fexp(double x, const Tables *t)
+{
+    const double kd0 = fma(x, MT_FM_64_LN2, 6755399441055744.0);   // 1.5 * 2^52: rint in the low word
+    const int k = __double2loint(kd0);
+    const double kd = kd0 - 6755399441055744.0;
+    double r = fma(-kd, MT_FM_LN2_64_HI, x);
+    r = fma(-kd, MT_FM_LN2_64_LO, r);
+    const double ej = t->ex[k & 63];
+    double p = fma(r, 1.0 / 120, 1.0 / 24);
+    p = fma(r, p, 1.0 / 6);
+    p = fma(r, p, 0.5);
+    p = fma(r, p, 1.0);
+    double res = fma(ej, p * r, ej);
+    res = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+    if (fabs(x) >= 690.0) res = slow_exp(x);                       // rare: overflow / underflow range
+    return (x != x) ? x : res;
+}
+
+}  // namespace fm
+}  // namespace mt

@@ -9,6 +9,7 @@
 #include <cooperative_groups.h>
 #include <cstdlib>
 
+#include "fastmath.cuh"
 #include "thermo.cuh"
 
 namespace {
@@ -144,6 +145,9 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
 {
     namespace cg = cooperative_groups;
     constexpr double logB = 8.597851094433691;  // log(5420)
+    __shared__ mt::fm::Tables tb;
+    mt::fm::load_tables(&tb);
+    __syncthreads();
     const double prev_max = __longlong_as_double((long long)maxbits[first - 1]);
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
@@ -184,7 +188,7 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
             }
             double L = (double)Lf;
             double D = gg - CpRd * L;
-            const double h = L - logB + log(D);
+            const double h = L - logB + mt::fm::flog(D, &tb);
             L = L - h * D / (D - CpRd);
             D = gg - CpRd * L;
             const double Tcs = B / D;
@@ -214,13 +218,14 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
                 const double2 th = __ldg(reinterpret_cast<const double2 *>(Th) + i);
                 const double2 q = __ldg(reinterpret_cast<const double2 *>(qv) + i);
                 __stcs(reinterpret_cast<double2 *>(Th_e) + i,
-                       make_double2(exp_factor1(th.x, q.x, t.x), exp_factor1(th.y, q.y, t.y)));
+                       make_double2(th.x * mt::fm::fexp((Lv / Cp) * q.x / t.x, &tb),
+                                    th.y * mt::fm::fexp((Lv / Cp) * q.y / t.y, &tb)));
             }
         }
         for (int64_t i = 2 * npair + tid; i < n; i += nthr) {
             const double t = finish(Tc[i], g[i]);
             Tc[i] = t;
-            if (Th_e) __stcs(Th_e + i, exp_factor1(__ldg(Th + i), __ldg(qv + i), t));
+            if (Th_e) __stcs(Th_e + i, __ldg(Th + i) * mt::fm::fexp((Lv / Cp) * __ldg(qv + i) / t, &tb));
         }
         return;
     }
@@ -261,26 +266,28 @@ struct TdPoint {
     double Th, es, qvs, vap, RH, Td, Th_es, Tv, rho, dTdz, g, Tc1;
 };
 
-__device__ __forceinline__ TdPoint td_point(double T, double P, double qv)
+__device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const mt::fm::Tables *tb)
 {
+    using mt::fm::fexp;
+    using mt::fm::flog;
     constexpr double log_1e5 = 11.512925464970229;       // log(100000)
     constexpr double log_A622 = 25.781840139430972;      // log(2.53e11*0.622)
     constexpr double log_611_2 = 6.415424237852311;      // log(611.2)
     TdPoint r;
-    const double lP = log(P), lT = log(T), lq = log(qv);
-    r.Th = T * exp(kappa * (log_1e5 - lP));
-    r.es = sat_vapor(T);
+    const double lP = flog(P, tb), lT = flog(T, tb), lq = flog(qv, tb);
+    r.Th = T * fexp(kappa * (log_1e5 - lP), tb);
+    r.es = 611.2 * fexp(17.67 * (T - 273.15) / (T - 273.15 + 243.5), tb);   // :116
     r.qvs = sat_qv_from_es(r.es, P);
     r.vap = qv_to_vapor(P, qv);                           // exact class, :168
     r.RH = r.vap / r.es;
-    const double lnes = log(r.vap) - log_611_2;
+    const double lnes = flog(r.vap, tb) - log_611_2;
     r.Td = 243.5 * lnes / (17.67 - lnes) + 273.15;
-    const double lq_T = (Lv / Cp) * r.qvs / T;            // Lv*qvs/Cp/T
-    r.Th_es = r.Th * exp(lq_T);
+    const double rT = 1.0 / T;                            // shared by the three tolerance-class quotients
+    r.Th_es = r.Th * fexp((Lv / Cp) * r.qvs * rT, tb);   // Lv*qvs/Cp/T
     r.Tv = Tv_from_qv(T, qv);                             // exact class, :335
     r.rho = rho(P, r.Tv);                                 // exact class, :364
-    const double a = Lv * r.qvs / (Rd * T);               // Lv*qvs/Rd/T
-    r.dTdz = -g * ((1 + a) / (Cp + a * (Lv * 0.622) / T));  // :486
+    const double a = (Lv / Rd) * r.qvs * rT;              // Lv*qvs/Rd/T
+    r.dTdz = -g * ((1 + a) / (Cp + a * (Lv * 0.622) * rT));  // :486
     r.g = log_A622 - lP - lq + CpRd * lT;
     r.Tc1 = B / (r.g - CpRd * lT);                        // first sweep: Tc2 = T
     return r;
@@ -292,11 +299,14 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
 {
     // one point per thread and iteration: 60 registers / 4 CTAs per SM measured 25 % faster than
     // two points per thread (117 registers) -- profiles/experiments_r01.md
+    __shared__ mt::fm::Tables tb;
+    mt::fm::load_tables(&tb);
+    __syncthreads();
     unsigned long long m = 0ull;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const double T = __ldg(in.T + i), P = __ldg(in.p + i), qv = __ldg(in.qv + i);
-        const TdPoint r = td_point(T, P, qv);
+        const TdPoint r = td_point(T, P, qv, &tb);
         if (out.Th) __stcs(out.Th + i, r.Th);
         if (out.vapor_s) __stcs(out.vapor_s + i, r.es);
         if (out.qvs) __stcs(out.qvs + i, r.qvs);
