@@ -38,8 +38,14 @@ __device__ __forceinline__ void load_tables(Tables *s)
 static __device__ __noinline__ double slow_log(double x) { return log(x); }
 static __device__ __noinline__ double slow_exp(double x) { return exp(x); }
 
-__device__ __forceinline__ double flog(double x, const Tables *t)
+__device__ __forceinline__ double flog(double x0, const Tables *t)
 {
+    // NaN lanes (terrain) compute on 1.0 and get their NaN back at the end.  Without this the
+    // compiler folds "x < DBL_MIN || x == inf" and the final NaN select into ONE integer range test
+    // that is also true for NaN, and every warp holding a masked point runs the slow path
+    // (measured: 19 % of the kernel's instructions).
+    const bool isn = x0 != x0;
+    const double x = isn ? 1.0 : x0;
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const double2 rt = t->lg[(hi >> 13) & 127];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
@@ -50,8 +56,8 @@ __device__ __forceinline__ double flog(double x, const Tables *t)
     q = fma(u, q, 1.0 / 3);
     q = fma(u, q, -0.5);
     double res = fma(e, MT_FM_LN2, rt.y) + fma(u * u, q, u);
-    if (x < 2.2250738585072014e-308 || x == inf_f64()) res = slow_log(x);   // rare: <= 0, denormal, +inf
-    return (x != x) ? x : res;
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) res = slow_log(x);   // rare: <= 0, denormal, +inf
+    return isn ? x0 : res;
 }
 
 __device__ __forceinline__ double fexp(double x, const Tables *t)
@@ -70,6 +76,27 @@ __device__ __forceinline__ double fexp(double x, const Tables *t)
     res = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
     if (fabs(x) >= 690.0) res = slow_exp(x);                       // rare: overflow / underflow range
     return (x != x) ? x : res;
+}
+
+// a / b for tolerance-class quotients: MUFU.RCP64H seed (~20 bits) + two Newton steps + one multiply
+// (~8 instructions instead of ~20 for the IEEE division sequence), <= 2 ulp.  Denominators that are
+// zero, denormal, huge or infinite take the IEEE division on a rarely taken branch; NaN propagates.
+static __device__ __noinline__ double slow_div(double a, double b) { return a / b; }
+
+__device__ __forceinline__ double fdiv(double a, double b)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    double res = a * y;
+    // |b| outside [2^-1000, 2^992) incl. 0 and inf -- but not (quiet) NaN, which flows through the
+    // fast path as NaN: terrain-masked lanes must not drag their warp into the slow path
+    const unsigned hb = (unsigned)__double2hiint(b) & 0x7fffffffu;
+    if (hb - 0x01700000u >= 0x7c800000u && hb <= 0x7ff00000u) res = slow_div(a, b);
+    return res;
 }
 
 }  // namespace fm

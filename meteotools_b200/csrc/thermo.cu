@@ -189,9 +189,9 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
             double L = (double)Lf;
             double D = gg - CpRd * L;
             const double h = L - logB + mt::fm::flog(D, &tb);
-            L = L - h * D / (D - CpRd);
+            L = L - mt::fm::fdiv(h * D, D - CpRd);
             D = gg - CpRd * L;
-            const double Tcs = B / D;
+            const double Tcs = mt::fm::fdiv(B, D);
             const float c = __fdividef(af, (float)D);
             const float d = __fdividef((float)(t - Tcs), (float)Tcs);
             // delta_first = log1p(d)
@@ -218,14 +218,14 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
                 const double2 th = __ldg(reinterpret_cast<const double2 *>(Th) + i);
                 const double2 q = __ldg(reinterpret_cast<const double2 *>(qv) + i);
                 __stcs(reinterpret_cast<double2 *>(Th_e) + i,
-                       make_double2(th.x * mt::fm::fexp((Lv / Cp) * q.x / t.x, &tb),
-                                    th.y * mt::fm::fexp((Lv / Cp) * q.y / t.y, &tb)));
+                       make_double2(th.x * mt::fm::fexp(mt::fm::fdiv((Lv / Cp) * q.x, t.x), &tb),
+                                    th.y * mt::fm::fexp(mt::fm::fdiv((Lv / Cp) * q.y, t.y), &tb)));
             }
         }
         for (int64_t i = 2 * npair + tid; i < n; i += nthr) {
             const double t = finish(Tc[i], g[i]);
             Tc[i] = t;
-            if (Th_e) __stcs(Th_e + i, __ldg(Th + i) * mt::fm::fexp((Lv / Cp) * __ldg(qv + i) / t, &tb));
+            if (Th_e) __stcs(Th_e + i, __ldg(Th + i) * mt::fm::fexp(mt::fm::fdiv((Lv / Cp) * __ldg(qv + i), t), &tb));
         }
         return;
     }
@@ -274,22 +274,24 @@ __device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const
     constexpr double log_A622 = 25.781840139430972;      // log(2.53e11*0.622)
     constexpr double log_611_2 = 6.415424237852311;      // log(611.2)
     TdPoint r;
+    using mt::fm::fdiv;
     const double lP = flog(P, tb), lT = flog(T, tb), lq = flog(qv, tb);
     r.Th = T * fexp(kappa * (log_1e5 - lP), tb);
-    r.es = 611.2 * fexp(17.67 * (T - 273.15) / (T - 273.15 + 243.5), tb);   // :116
-    r.qvs = sat_qv_from_es(r.es, P);
+    const double Tc_ = T - 273.15;
+    r.es = 611.2 * fexp(fdiv(17.67 * Tc_, Tc_ + 243.5), tb);   // :116
+    r.qvs = fdiv(0.622 * r.es, P - r.es);                      // :151
     r.vap = qv_to_vapor(P, qv);                           // exact class, :168
-    r.RH = r.vap / r.es;
+    r.RH = fdiv(r.vap, r.es);
     const double lnes = flog(r.vap, tb) - log_611_2;
-    r.Td = 243.5 * lnes / (17.67 - lnes) + 273.15;
-    const double rT = 1.0 / T;                            // shared by the three tolerance-class quotients
+    r.Td = fdiv(243.5 * lnes, 17.67 - lnes) + 273.15;
+    const double rT = fdiv(1.0, T);                       // shared by the three tolerance-class quotients
     r.Th_es = r.Th * fexp((Lv / Cp) * r.qvs * rT, tb);   // Lv*qvs/Cp/T
     r.Tv = Tv_from_qv(T, qv);                             // exact class, :335
     r.rho = rho(P, r.Tv);                                 // exact class, :364
     const double a = (Lv / Rd) * r.qvs * rT;              // Lv*qvs/Rd/T
-    r.dTdz = -g * ((1 + a) / (Cp + a * (Lv * 0.622) * rT));  // :486
+    r.dTdz = -g * fdiv(1 + a, Cp + a * (Lv * 0.622) * rT);  // :486
     r.g = log_A622 - lP - lq + CpRd * lT;
-    r.Tc1 = B / (r.g - CpRd * lT);                        // first sweep: Tc2 = T
+    r.Tc1 = fdiv(B, r.g - CpRd * lT);                     // first sweep: Tc2 = T
     return r;
 }
 

@@ -359,3 +359,37 @@ def test_time_step_stream_matches_grid_api(golden_setdata):
             assert_same(res[name], getattr(ref, name), f"step {k} {name}")
         seen.append(k)
     assert seen == list(range(5))
+
+
+def test_time_step_stream_float32_sources(golden_setdata):
+    """float32 host sources are staged as float32 (half the PCIe bytes), widened in the
+    kernel, and give exactly what the grid API gives for the same float32 arrays (wrf-python's
+    float32 rounding of the level-interpolated field included)."""
+    from meteotools_b200.grids import cylindrical_grid
+    from meteotools_b200.pipeline import TimeStepStream
+    g = golden_setdata
+    dx = float(g["s_dx"])
+    z32, hgt = g["s_z3d"].astype(np.float32), g["s_hgt"]
+    v32 = dict(T=(g["s_T"] + 280.0).astype(np.float32), p=(1e5 * np.exp(-g["s_z3d"] / 8000.0)).astype(np.float32),
+               qv=(1e-3 + 1e-4 * np.abs(g["s_u"])).astype(np.float32))
+    cyl = cylindrical_grid(dict(SD))
+    cyl.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    outs = ["Th", "Tc", "rho"]
+    ts = TimeStepStream(cyl, z32.shape, dx, dx, ["T", "p", "qv"], names2d=("f",), hgt=True, outputs=outs + ["T"],
+                        dtype=np.float32)
+    assert ts.slots[0]["pipe"].h2d_bytes() < 0.6 * (4 * z32.size * 8)
+    steps = [dict(z3d=z32, hgt=hgt, f=g["s_f"], vars3d=v32)] * 3
+    ref = cylindrical_grid(dict(SD))
+    ref.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    ref.set_data(dx, dx, z32, hgt=hgt, f=g["s_f"], **v32)
+    ref.calc_all_thermaldynamic()
+    lev = oracle.interplevel(v32["T"], z32, ref.z)
+    assert lev.dtype == np.float32
+    want_T = co.cyl_terrain_mask(oracle.interp2D_fast_layers(dx, dx, g["o_sd_xTR"], g["o_sd_yTR"], lev), ref.hgt_idx)
+    n = 0
+    for k, res in ts.process(steps):
+        assert_same(res["T"], want_T, f"step {k} T vs the CPU pipeline on float32 input")
+        for name in outs:
+            assert_same(res[name], getattr(ref, name), f"step {k} {name}")
+        n += 1
+    assert n == 3
