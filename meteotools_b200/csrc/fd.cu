@@ -1,33 +1,69 @@
 // Generic finite differences along one axis of a dense array (SURVEY 8a rows a8, a9;
 // calc/differential.py:6-180 through calc/check_arrays.py:52-63).  The array is viewed as
-// (outer, n, inner); one thread per element, neighbours come through L1/L2 (stride `inner`).
+// (outer, n, inner).  No integer division per element (the first version spent more issue slots on
+// two 64-bit div/mod pairs than on the stencil and ran at 51 % of the HBM peak):
+//   inner > 1 : blockIdx.x/threadIdx.x walk the contiguous `inner` index, blockIdx.y a chunk of the
+//               differentiated axis, blockIdx.z (+ a stride loop) the outer index; neighbours are
+//               re-read through L1/L2 (same rows, just loaded by this block);
+//   inner == 1: the differentiated axis itself is contiguous: threads walk it, blockIdx.y the rows.
 #include "fd.cuh"
 
 namespace {
+
+template <int KIND, class V>
+__device__ __forceinline__ double fd_apply(V v, int i, int n, const mt::CDiv &delta)
+{
+    if (KIND == MT_FD2) return mt::fd2(v, i, n, delta);
+    if (KIND == MT_FD4) return mt::fd4(v, i, n, delta);
+    if (KIND == MT_FD2_FRONT) return mt::fd2_front(v, i, n, delta);
+    if (KIND == MT_FD2_BACK) return mt::fd2_back(v, i, n, delta);
+    if (KIND == MT_FD2_2) return mt::fd2_2(v, i, n, delta);
+    if (KIND == MT_FD2_2_FRONT) return mt::fd2_2_front(v, i, n, delta);
+    return mt::fd2_2_back(v, i, n, delta);
+}
+
+constexpr int FD_CHUNK = 16;   // points of the differentiated axis per thread (inner > 1)
 
 template <int KIND>
 __global__ void __launch_bounds__(256)
 k_fd(const double *__restrict__ in, double *__restrict__ out, int64_t outer, int n, int64_t inner,
      double delta)
 {
-    const int64_t total = outer * n * inner;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = t % inner;
-        const int64_t oi = t / inner;
-        const int i = (int)(oi % n);
-        const int64_t o = oi / n;
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= inner) return;
+    const int i0 = blockIdx.y * FD_CHUNK, i1 = min(i0 + FD_CHUNK, n);
+    const mt::CDiv dd(delta);
+    for (int64_t o = blockIdx.z; o < outer; o += gridDim.z) {
         const double *base = in + o * n * inner + j;
+        double *ob = out + o * n * inner + j;
         auto v = [&](int k) { return __ldg(base + (int64_t)k * inner); };
-        double r;
-        if (KIND == MT_FD2) r = mt::fd2(v, i, n, delta);
-        else if (KIND == MT_FD4) r = mt::fd4(v, i, n, delta);
-        else if (KIND == MT_FD2_FRONT) r = mt::fd2_front(v, i, n, delta);
-        else if (KIND == MT_FD2_BACK) r = mt::fd2_back(v, i, n, delta);
-        else if (KIND == MT_FD2_2) r = mt::fd2_2(v, i, n, delta);
-        else if (KIND == MT_FD2_2_FRONT) r = mt::fd2_2_front(v, i, n, delta);
-        else r = mt::fd2_2_back(v, i, n, delta);
-        mt::st_stream(out + t, r);
+        if (KIND == MT_FD2) {   // the hot kind: rolling registers, one load per point
+            double prev = i0 > 0 ? v(i0 - 1) : 0.0, cur = v(i0);
+#pragma unroll 4
+            for (int i = i0; i < i1; ++i) {
+                const double nxt = i + 1 < n ? v(i + 1) : 0.0;
+                const double r = (i == 0 || i == n - 1) ? mt::fd2(v, i, n, dd) : dd((nxt - prev) / 2);
+                mt::st_stream(ob + (int64_t)i * inner, r);
+                prev = cur, cur = nxt;
+            }
+        } else {
+#pragma unroll 4
+            for (int i = i0; i < i1; ++i) mt::st_stream(ob + (int64_t)i * inner, fd_apply<KIND>(v, i, n, dd));
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_fd_row(const double *__restrict__ in, double *__restrict__ out, int64_t rows, int n, double delta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const mt::CDiv dd(delta);
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const double *base = in + r * n;
+        auto v = [&](int k) { return __ldg(base + k); };
+        mt::st_stream(out + r * n + i, fd_apply<KIND>(v, i, n, dd));
     }
 }
 
@@ -40,21 +76,42 @@ extern "C" int mt_fd(const double *in, double *out, int64_t outer, int64_t n, in
     MT_REQUIRE(outer > 0 && inner > 0 && n > 0 && n < 2147483647LL, "mt_fd: bad extents");
     const int need = (kind == MT_FD4) ? 5 : (kind == MT_FD2_2 || kind == MT_FD2_2_FRONT || kind == MT_FD2_2_BACK) ? 4 : 3;
     MT_REQUIRE(n >= need, "mt_fd: axis length %lld < %d", (long long)n, need);
-    const unsigned grid = mt::grid_for(outer * n * inner, 256, 16);
     cudaStream_t s = (cudaStream_t)stream;
     mt::ProfScope prof("k_fd", stream);
-    switch (kind) {
+    if (inner == 1) {
+        const dim3 grid((unsigned)((n + 255) / 256), (unsigned)(outer < 32768 ? outer : 32768));
+        switch (kind) {
 #define FD_CASE(K) \
-    case K: k_fd<K><<<grid, 256, 0, s>>>(in, out, outer, (int)n, inner, delta); break;
-        FD_CASE(MT_FD2)
-        FD_CASE(MT_FD4)
-        FD_CASE(MT_FD2_FRONT)
-        FD_CASE(MT_FD2_BACK)
-        FD_CASE(MT_FD2_2)
-        FD_CASE(MT_FD2_2_FRONT)
-        FD_CASE(MT_FD2_2_BACK)
+    case K: k_fd_row<K><<<grid, 256, 0, s>>>(in, out, outer, (int)n, delta); break;
+            FD_CASE(MT_FD2)
+            FD_CASE(MT_FD4)
+            FD_CASE(MT_FD2_FRONT)
+            FD_CASE(MT_FD2_BACK)
+            FD_CASE(MT_FD2_2)
+            FD_CASE(MT_FD2_2_FRONT)
+            FD_CASE(MT_FD2_2_BACK)
 #undef FD_CASE
-        default: mt::set_error("mt_fd: unknown kind %d", kind); return MT_EINVAL;
+            default: mt::set_error("mt_fd: unknown kind %d", kind); return MT_EINVAL;
+        }
+    } else {
+        const int threads = inner >= 256 ? 256 : (inner >= 128 ? 128 : (inner >= 64 ? 64 : 32));
+        const int64_t gx = (inner + threads - 1) / threads;
+        MT_REQUIRE(gx < 2147483647LL, "mt_fd: inner extent too large");
+        const dim3 grid((unsigned)gx, (unsigned)((n + FD_CHUNK - 1) / FD_CHUNK), (unsigned)(outer < 4096 ? outer : 4096));
+        MT_REQUIRE(grid.y <= 65535u, "mt_fd: axis too long for one launch (n = %lld)", (long long)n);
+        switch (kind) {
+#define FD_CASE(K) \
+    case K: k_fd<K><<<grid, threads, 0, s>>>(in, out, outer, (int)n, inner, delta); break;
+            FD_CASE(MT_FD2)
+            FD_CASE(MT_FD4)
+            FD_CASE(MT_FD2_FRONT)
+            FD_CASE(MT_FD2_BACK)
+            FD_CASE(MT_FD2_2)
+            FD_CASE(MT_FD2_2_FRONT)
+            FD_CASE(MT_FD2_2_BACK)
+#undef FD_CASE
+            default: mt::set_error("mt_fd: unknown kind %d", kind); return MT_EINVAL;
+        }
     }
     MT_LAUNCH_CHECK();
     return MT_OK;
