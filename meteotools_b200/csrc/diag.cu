@@ -165,23 +165,59 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
     const int n0 = ZTR ? nz : nt;   // march axis (slowest in memory)
     const int n2 = ZTR ? nr : nz;   // contiguous axis
     const int64_t plane = (int64_t)(ZTR ? nt : nr) * n2;
-    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= plane) return;
-    const int i1 = (int)(p / n2), i2 = (int)(p - (int64_t)i1 * n2);
-    int m_lo = 0, m_hi = n0;
+    int64_t p;
+    int i1, i2, s_lo, s_hi;
     bool first = true, last = true;
-    if (ZTR) {  // a level shard marches over its owned levels and reads the halo levels
-        m_lo = g.own_lo, m_hi = g.own_hi, first = g.bottom, last = g.top;
-    } else if (i2 < g.own_lo || i2 >= g.own_hi) {
-        return;  // TRZ: z is the contiguous axis; halo levels produce no output
-    }
-    const int s_lo = m_lo + (int)blockIdx.y * (SHELL ? 1 : seg_len);
-    const int s_hi = min(m_hi, s_lo + (SHELL ? 1 : seg_len));
-    if (s_lo >= s_hi) return;
-    if (SHELL) {  // keep only the shell: most threads leave here
-        const int iz = ZTR ? s_lo : i2, it = ZTR ? i1 : s_lo, ir = ZTR ? i2 : i1;
-        const bool z_edge = (iz == 0 && g.bottom) || (iz == nz - 1 && g.top);
-        if (!z_edge && it > 0 && it < nt - 1 && ir > 0 && ir < nr - 1) return;
+    if (ZTR) first = g.bottom, last = g.top;
+    if (!SHELL) {
+        p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        if (p >= plane) return;
+        i1 = (int)(p / n2), i2 = (int)(p - (int64_t)i1 * n2);
+        int m_lo = 0, m_hi = n0;
+        if (ZTR) {  // a level shard marches over its owned levels and reads the halo levels
+            m_lo = g.own_lo, m_hi = g.own_hi;
+        } else if (i2 < g.own_lo || i2 >= g.own_hi) {
+            return;  // TRZ: z is the contiguous axis; halo levels produce no output
+        }
+        s_lo = m_lo + (int)blockIdx.y * seg_len;
+        s_hi = min(m_hi, s_lo + seg_len);
+        if (s_lo >= s_hi) return;
+    } else {
+        // compact enumeration of the outermost shell of the owned block: the global z faces, the two
+        // theta faces of the remaining levels, the two r faces of what is left -- one thread per
+        // shell point (the first version launched a thread per GRID point and let 95 % of them
+        // leave at once: 0.26 ms of the 0.63 ms of stage B on S3)
+        const int zin_lo = g.own_lo + (g.bottom ? 1 : 0), zin_hi = g.own_hi - (g.top ? 1 : 0);
+        const int nzin = max(zin_hi - zin_lo, 0);
+        const int64_t nA = (int64_t)((g.bottom ? 1 : 0) + (g.top ? 1 : 0)) * nt * nr;
+        const int64_t nB = 2LL * nzin * nr, nC = 2LL * nzin * (nt - 2);
+        int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        int iz, it, ir;
+        if (q < nA) {
+            const int f = (int)(q / ((int64_t)nt * nr));
+            const int64_t rem = q - (int64_t)f * nt * nr;
+            it = (int)(rem / nr), ir = (int)(rem - (int64_t)it * nr);
+            iz = (f == 0 && g.bottom) ? 0 : nz - 1;
+        } else if ((q -= nA) < nB) {
+            const int f = (int)(q / ((int64_t)nzin * nr));
+            const int64_t rem = q - (int64_t)f * nzin * nr;
+            if (ZTR) {
+                iz = zin_lo + (int)(rem / nr), ir = (int)(rem % nr);
+            } else {
+                ir = (int)(rem / nzin), iz = zin_lo + (int)(rem % nzin);
+            }
+            it = f ? nt - 1 : 0;
+        } else if ((q -= nB) < nC) {
+            const int f = (int)(q / ((int64_t)nzin * (nt - 2)));
+            const int64_t rem = q - (int64_t)f * nzin * (nt - 2);
+            iz = zin_lo + (int)(rem / (nt - 2)), it = 1 + (int)(rem % (nt - 2));
+            ir = f ? nr - 1 : 0;
+        } else {
+            return;
+        }
+        s_lo = ZTR ? iz : it, s_hi = s_lo + 1;
+        i1 = ZTR ? it : ir, i2 = ZTR ? ir : iz;
+        p = (int64_t)i1 * n2 + i2;
     }
 
     const bool want_zr = o.zeta_r || o.PV;
@@ -450,7 +486,12 @@ int run_sets(const mt_grid_t *g, const mt_dyn_in_t *in, const StageAOut &a, cons
         if (nseg < 1) nseg = 1;
         const int seg_len = (int)((n_march + nseg - 1) / nseg);
         dim3 gridb((unsigned)((plane + 127) / 128), (unsigned)((n_march + seg_len - 1) / seg_len));
-        dim3 grids((unsigned)((plane + 127) / 128), (unsigned)n_march);
+        // shell launch: one thread per point of the outermost shell of the owned block
+        const int64_t own = g->nz - g->halo_lo - g->halo_hi;
+        const int64_t nzin = own - (g->is_bottom ? 1 : 0) - (g->is_top ? 1 : 0);
+        const int64_t n_shell = ((g->is_bottom ? 1 : 0) + (g->is_top ? 1 : 0)) * g->nt * g->nr +
+                                2 * (nzin > 0 ? nzin : 0) * (g->nr + g->nt - 2);
+        dim3 grids((unsigned)((n_shell + 127) / 128 > 0 ? (n_shell + 127) / 128 : 1));
         if (ztr) {
             Lay<MT_LAYOUT_ZTR> lay((int)g->nz, (int)g->nt, (int)g->nr);
             k_stage_b<MT_LAYOUT_ZTR, CYL, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);
