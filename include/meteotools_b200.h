@@ -194,10 +194,13 @@ int mt_setdata_fused(const void *const *fields, int nvar, const void *vert, int 
  *     back (a violation ends in cudaErrorIllegalInstruction).
  * `direction` must be 0 or 1 (decided by the caller from column (0,0) of the full coordinate
  * array).  mt_setdata_tma_supported() tells whether a shape can take this path (otherwise use
- * mt_setdata: same results, two kernels). */
+ * mt_setdata: same results, two kernels).
+ * The number of target levels must be even and <= 96 (the brackets of a thread's level pairs live
+ * in registers); at most MT_TMA_MAX_TARGETS targets per item. */
 #define MT_TMA_TILE_W_F64 14
 #define MT_TMA_TILE_W_F32 12
 #define MT_TMA_TILE_H 4
+#define MT_TMA_MAX_TARGETS 128
 int mt_setdata_tma_supported(int dtype, int64_t nz, int64_t nlev, int64_t row_pitch);
 int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz,
                    int64_t ny, int64_t nx, int64_t row_pitch, int64_t org_y, int64_t org_x,

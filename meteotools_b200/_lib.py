@@ -27,9 +27,14 @@ MT_NANSUM_SCRATCH = 2048
 MT_TMA_TILE_W_F64, MT_TMA_TILE_W_F32, MT_TMA_TILE_H = 14, 12, 4   # source cells per tile of mt_setdata_tma
 
 
+MT_TMA_MAX_TARGETS = 128
+
+
 def tma_tile(dtype):
-    """(tile_w, tile_h, column alignment of the tile origin) of mt_setdata_tma for MT_F64 / MT_F32."""
-    return (MT_TMA_TILE_W_F32, MT_TMA_TILE_H, 4) if dtype == MT_F32 else (MT_TMA_TILE_W_F64, MT_TMA_TILE_H, 2)
+    """(tile_w, tile_h, column alignment of the tile origin, targets per item) of mt_setdata_tma
+    for MT_F64 / MT_F32."""
+    tw, al = (MT_TMA_TILE_W_F32, 4) if dtype == MT_F32 else (MT_TMA_TILE_W_F64, 2)
+    return tw, MT_TMA_TILE_H, al, MT_TMA_MAX_TARGETS
 MT_LAYOUT_ZTR, MT_LAYOUT_TRZ = 0, 1
 MT_STAGE_A, MT_STAGE_B, MT_STAGE_ALL = 1, 2, 3
 FD_KINDS = {"FD2": 0, "FD4": 1, "FD2_front": 2, "FD2_back": 3, "FD2_2": 4, "FD2_2_front": 5,

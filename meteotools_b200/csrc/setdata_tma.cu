@@ -39,31 +39,30 @@ using mt::nan_f64;
 // The TMA unit requires the global address of a box to be 16-byte aligned: tiles start at even
 // (float64) / multiple-of-4 (float32) columns and are 14 / 12 cells wide, so that the 16-column box
 // holds the tile's width + 1 columns (measured: an odd start column -> cudaErrorIllegalInstruction).
-constexpr int BX = 16, BY = MT_TMA_TILE_H + 1, NC = BX * BY;   // columns per box: 16 x 5 = 80
-constexpr int NC_ = NC;
+constexpr int BX = 16;                                   // columns per box row (128-byte rows of float64)
 static_assert(MT_TMA_TILE_W_F64 + 1 <= BX && MT_TMA_TILE_W_F64 % 2 == 0, "float64 tile width");
 static_assert(MT_TMA_TILE_W_F32 + 1 <= BX && MT_TMA_TILE_W_F32 % 4 == 0, "float32 tile width");
-#ifndef MT_TMA_NCONS
-#define MT_TMA_NCONS 512
-#endif
-constexpr int NCONS = MT_TMA_NCONS, NTHREADS = NCONS + 32;   // consumer threads (+ one producer warp)
-constexpr int NG = NCONS / NC_;                              // level groups of the column phases
-constexpr int MAXT = 128;                               // targets per item
+constexpr int BY = MT_TMA_TILE_H + 1, NC = BX * BY;     // columns per box: 16 x 5 = 80
+constexpr int NG = 6;                                   // level groups of the column phases
+// 15 consumer warps (every consumer thread owns one (column, level group)) + one producer warp =
+// 16 warps, four per SM sub-partition: 128 registers per thread
+constexpr int NCONS = NG * NC, NTHREADS = NCONS + 32;
+static_assert(NCONS % 32 == 0, "consumer threads must be whole warps");
+constexpr int MAXT = MT_TMA_MAX_TARGETS;                // targets per item
 constexpr int NMETA = 3;                                // target-table ring
-static_assert(BX == 16 && NC == 80, "index arithmetic below assumes a 16 x 5 column tile");
+static_assert(2 * NC <= NTHREADS && MAXT % 32 == 0, "shape");
 
 struct __align__(64) TmaParams {
     CUtensorMap maps[MT_MAX_VARS + 1];   // [0]: vertical coordinate, [v+1]: variable v
     double *out[MT_MAX_VARS];
 };
 
-struct Meta {   // one staged target (three 16-byte words)
+struct Meta {   // one staged target (two 16-byte words)
     double fx, fy;
-    long long ooff;            // target * o_n: element offset of the output row
-    int terrain, pad;
-    int b00, b10, b01, b11;    // byte offsets of the four corner columns in `lev`
+    int tgt, terrain;           // target index (output row = tgt * o_n), terrain level index
+    unsigned short b[4];        // tile-local ids of the four corner columns (rows of `lev`)
 };
-static_assert(sizeof(Meta) == 48, "Meta is read as three 16-byte words");
+static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -100,21 +99,20 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
-template <typename T, bool INCLUSIVE, bool ROUND>
+// PP = level pairs per column thread (>= ceil(nlev / 2 / NG)): the brackets of a thread's own
+// (column, level pair) set live in registers for all variables of the item.
+template <typename T, bool INCLUSIVE, bool ROUND, int PP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, int LP, int stages,
               int stage_bytes, int org_x, int org_y, const double *__restrict__ levels, int decreasing,
               const int4 *__restrict__ pix, const double2 *__restrict__ pw,
               const int32_t *__restrict__ order, const int4 *__restrict__ items, int nitems,
-              int *__restrict__ counter, const int32_t *__restrict__ hgt_idx, int64_t o_n, int off_w2,
-              int off_lev, int off_kp, int off_meta, int off_misc)
+              int *__restrict__ counter, const int32_t *__restrict__ hgt_idx, int64_t o_n, int off_lev,
+              int lev_bytes, int off_meta, int off_misc)
 {
     extern __shared__ unsigned char smem_dyn[];
     // TMA destinations must be 128-byte aligned
     unsigned char *smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
-    double *w2s = reinterpret_cast<double *>(smem + off_w2);                  // [nlev][NC]
-    double *lev = reinterpret_cast<double *>(smem + off_lev);                 // [NC][LP]
-    unsigned char *kps = smem + off_kp;                                       // [nlev][NC]
     Meta *meta = reinterpret_cast<Meta *>(smem + off_meta);                   // [NMETA][MAXT]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + off_misc);           // [8]
     uint64_t *empty = full + 8;                                               // [8]
@@ -144,10 +142,11 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
         // staging pipeline of the NEXT item (registers)
         int nid = 0;
         int4 nit = make_int4(0, 0, 0, 0);
-        int tgt[4];
-        int4 six[4];
-        double2 sw[4];
-        int ster[4];
+        constexpr int TS = MAXT / 32;
+        int tgt[TS];
+        int4 six[TS];
+        double2 sw[TS];
+        int ster[TS];
         auto stage_phase = [&](int ph, int slot_meta) {
             switch (ph) {
                 case 0:
@@ -160,14 +159,14 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                     break;
                 case 2:
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < TS; ++k) {
                         const int j = lane + 32 * k;
                         tgt[k] = j < nit.w ? order[nit.z + j] : -1;
                     }
                     break;
                 case 3:
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < TS; ++k)
                         if (tgt[k] >= 0) {
                             six[k] = pix[tgt[k]];
                             sw[k] = pw[tgt[k]];
@@ -177,15 +176,16 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 case 4: {
                     Meta *mt_ = meta + slot_meta * MAXT;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < TS; ++k)
                         if (tgt[k] >= 0) {
                             Meta m;
-                            m.fx = sw[k].x, m.fy = sw[k].y, m.ooff = (long long)tgt[k] * o_n;
-                            m.terrain = ster[k], m.pad = 0;
-                            m.b00 = ((six[k].z - nit.y) * BX + (six[k].x - nit.x)) * LP * 8;
-                            m.b10 = ((six[k].z - nit.y) * BX + (six[k].y - nit.x)) * LP * 8;
-                            m.b01 = ((six[k].w - nit.y) * BX + (six[k].x - nit.x)) * LP * 8;
-                            m.b11 = ((six[k].w - nit.y) * BX + (six[k].y - nit.x)) * LP * 8;
+                            m.fx = sw[k].x, m.fy = sw[k].y, m.tgt = tgt[k], m.terrain = ster[k];
+                            // corner columns as element offsets / LP (column ids); the consumer
+                            // multiplies by the column pitch
+                            m.b[0] = (unsigned short)((six[k].z - nit.y) * BX + (six[k].x - nit.x));
+                            m.b[1] = (unsigned short)((six[k].z - nit.y) * BX + (six[k].y - nit.x));
+                            m.b[2] = (unsigned short)((six[k].w - nit.y) * BX + (six[k].x - nit.x));
+                            m.b[3] = (unsigned short)((six[k].w - nit.y) * BX + (six[k].y - nit.x));
                             mt_[lane + 32 * k] = m;
                         }
                     __syncwarp();
@@ -235,12 +235,17 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     const int klo_missing = decreasing ? 1 : 0; // any pair of valid rows: a missing bracket has w2 = NaN
     const int stage_elems = stage_bytes / (int)sizeof(T);
     const T *raw = reinterpret_cast<const T *>(smem);
-    // (column, level-group) ownership of the column phases: thread -> column tid % 80, levels
-    // tid / 80, +NG, +2 NG, ... (NG * 80 of the consumer threads; no index wrap in the loops)
+    // (column, level-group) ownership of the column phases: thread -> column tid % 80, level pairs
+    // tid / 80, +NG, +2 NG, ... (NG * 80 of the consumer threads)
     const int c_own = tid % NC, g_own = tid / NC;
     const bool col_thread = tid < NG * NC;
+    const int npair = nlev >> 1;
+    // this thread's brackets (row offsets of the "lo" samples of both levels of a pair, weights)
+    int kk[PP];
+    double wx[PP], wy[PP];
     int c_slot = 0;
     uint32_t c_par = 0;
+    int lev_sel = 0;   // `lev` is double-buffered: B of variable v + 1 may overlap C of variable v
     for (int n = 0;; ++n) {
         mbar_wait(full + c_slot, c_par);
         if (s_itemid[n & 3] < 0) break;
@@ -256,52 +261,56 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             if (!ok) mono[c_own] = 0;
         }
         cons_sync();
-        // brackets of every (level, column) pair, shared by all variables: klo = row of the "lo"
-        // sample (kp - im of DINTERP3DZ), w2 = its weight; no bracket -> w2 = NaN, so that
-        // w1*f + w2*f is NaN without a branch in the per-variable loop.  Tables are laid out
-        // [level pair][column][2]: the per-variable loop reads both levels of a pair with one load.
+        // brackets of this thread's (level pair, column) set, shared by all variables: klo = row of
+        // the "lo" sample (kp - im of DINTERP3DZ), w2 = its weight; no bracket -> w2 = NaN, so that
+        // w1*f + w2*f is NaN without a branch in the per-variable loop.
         if (col_thread) {
             const bool is_mono = mono[c_own] != 0;
-            for (int l = g_own * 2; l < nlev; l += 2 * NG) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double want = lev_s[l + h];
-                    int kp = -1;
-                    if (is_mono) {
-                        const double ww = sgn * want;  // upper bound: first K with sgn*v[K] > ww
-                        int lo = 0, hi = nz;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (sgn * (double)vt[mid * NC] > ww) hi = mid;
-                            else lo = mid + 1;
-                        }
-                        const int K = lo;
-                        if (K >= 1 && K <= nz - 1) {
-                            if (INCLUSIVE) kp = K;
-                            else if (sgn * (double)vt[(K - 1) * NC] < ww) kp = K;
-                        } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * NC] == ww) {
-                            kp = nz - 1;
-                        }
-                    } else {
-                        for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
-                            const double vlo = (double)vt[(q - im) * NC], vhi = (double)vt[(q - ip) * NC];
-                            const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
-                            if (hit) {
-                                kp = q;
-                                break;
-                            }
+            auto bracket = [&](double want, int &klo, double &w2) {
+                int kp = -1;
+                if (is_mono) {
+                    const double ww = sgn * want;  // upper bound: first K with sgn*v[K] > ww
+                    int lo = 0, hi = nz;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sgn * (double)vt[mid * NC] > ww) hi = mid;
+                        else lo = mid + 1;
+                    }
+                    const int K = lo;
+                    if (K >= 1 && K <= nz - 1) {
+                        if (INCLUSIVE) kp = K;
+                        else if (sgn * (double)vt[(K - 1) * NC] < ww) kp = K;
+                    } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * NC] == ww) {
+                        kp = nz - 1;
+                    }
+                } else {
+                    for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
+                        const double vlo = (double)vt[(q - im) * NC], vhi = (double)vt[(q - ip) * NC];
+                        const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
+                        if (hit) {
+                            kp = q;
+                            break;
                         }
                     }
-                    double w2 = nan_f64();
-                    int klo = klo_missing;
-                    if (kp >= 0) {
-                        klo = kp - im;
-                        const double vlo = (double)vt[klo * NC], vhi = (double)vt[klo * NC + dhi];
-                        w2 = (want - vlo) / (vhi - vlo);
-                    }
-                    kps[(l * NC + c_own * 2) + h] = (unsigned char)klo;   // ((l/2)*NC + c)*2 + h
-                    w2s[(l * NC + c_own * 2) + h] = w2;
                 }
+                w2 = nan_f64();
+                klo = klo_missing;
+                if (kp >= 0) {
+                    klo = kp - im;
+                    const double vlo = (double)vt[klo * NC], vhi = (double)vt[klo * NC + dhi];
+                    w2 = (want - vlo) / (vhi - vlo);
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < PP; ++i) {
+                const int lp = g_own + i * NG;
+                int k0 = klo_missing, k1 = klo_missing;
+                wx[i] = wy[i] = nan_f64();
+                if (lp < npair) {
+                    bracket(lev_s[2 * lp], k0, wx[i]);
+                    bracket(lev_s[2 * lp + 1], k1, wy[i]);
+                }
+                kk[i] = (k0 * NC) | ((k1 * NC) << 16);   // nz <= 254: k * 80 < 65536
             }
         }
         if (tid < NC) mono_s[((n + 1) & 1) * NC + tid] = 1;
@@ -311,60 +320,60 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
 
         const Meta *mt_ = meta + (n % NMETA) * MAXT;
         for (int v = 0; v < nvar; ++v) {
+            unsigned char *levb_w = smem + off_lev + lev_sel * lev_bytes;   // [NC][LP] doubles
             mbar_wait(full + c_slot, c_par);
-            // B: level-interpolated columns, one level PAIR per step (branch-free, 16-byte table
-            // load and 16-byte conflict-free store), two independent pairs per iteration
+            // B: level-interpolated columns, one level PAIR per step (branch-free, brackets from
+            // registers, conflict-free 16-byte stores)
             if (col_thread) {
                 const T *fc = raw + (size_t)c_slot * stage_elems + c_own;
-                const uchar2 *kq = reinterpret_cast<const uchar2 *>(kps) + c_own;
-                const double2 *wq = reinterpret_cast<const double2 *>(w2s) + c_own;
-                double *lv = lev + c_own * LP;
-                auto pair = [&](int lp) {   // levels 2 lp, 2 lp + 1
-                    const uchar2 k2 = kq[lp * NC];
-                    const double2 w = wq[lp * NC];
-                    const double f00 = (double)fc[k2.x * NC], f01 = (double)fc[k2.x * NC + dhi];
-                    const double f10 = (double)fc[k2.y * NC], f11 = (double)fc[k2.y * NC + dhi];
-                    double2 r;
-                    r.x = (1.0 - w.x) * f00 + w.x * f01;
-                    r.y = (1.0 - w.y) * f10 + w.y * f11;
-                    if (ROUND) r.x = (double)(float)r.x, r.y = (double)(float)r.y;
-                    return r;
-                };
-                const int npair = nlev >> 1;
-                int lp = g_own;
-                for (; lp + NG < npair; lp += 2 * NG) {
-                    const double2 ra = pair(lp), rb = pair(lp + NG);
-                    *reinterpret_cast<double2 *>(lv + 2 * lp) = ra;
-                    *reinterpret_cast<double2 *>(lv + 2 * (lp + NG)) = rb;
+                double *lv = reinterpret_cast<double *>(levb_w) + c_own * LP;
+#pragma unroll
+                for (int i = 0; i < PP; ++i) {
+                    const int lp = g_own + i * NG;
+                    if (lp < npair) {
+                        const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;
+                        const double f00 = (double)fc[ka], f01 = (double)fc[ka + dhi];
+                        const double f10 = (double)fc[kb], f11 = (double)fc[kb + dhi];
+                        double2 r;
+                        r.x = (1.0 - wx[i]) * f00 + wx[i] * f01;
+                        r.y = (1.0 - wy[i]) * f10 + wy[i] * f11;
+                        if (ROUND) r.x = (double)(float)r.x, r.y = (double)(float)r.y;
+                        *reinterpret_cast<double2 *>(lv + 2 * lp) = r;
+                    }
                 }
-                if (lp < npair) *reinterpret_cast<double2 *>(lv + 2 * lp) = pair(lp);
             }
-            cons_sync();
+            cons_sync();   // the only block barrier per variable: `lev` complete, tile consumed
             if (tid == 0) mbar_arrive(empty + c_slot);  // the ring slot may be refilled
             if (++c_slot == stages) c_slot = 0, c_par ^= 1u;
             // C: bilinear, one warp per target, two consecutive targets per step; the item's targets
             // are sorted by source cell, so a pair usually shares its four corner columns: one set
             // of shared-memory loads then serves both
             double *__restrict__ out = P.out[v];
-            const char *levb = reinterpret_cast<const char *>(lev);
+            const char *levb = reinterpret_cast<const char *>(levb_w);
+            const int cpitch = LP * 8;
             for (int j = 2 * warp; j < cnt; j += 2 * (NCONS / 32)) {
                 const bool two = j + 1 < cnt;
                 const Meta m0 = mt_[j];
                 const Meta m1 = mt_[two ? j + 1 : j];
-                double *o0 = out + m0.ooff, *o1 = out + m1.ooff;
+                double *o0 = out + (int64_t)m0.tgt * o_n, *o1 = out + (int64_t)m1.tgt * o_n;
                 const bool masked = (m0.terrain | m1.terrain) > 0;                       // warp-uniform
-                const bool same = m0.b00 == m1.b00 && m0.b10 == m1.b10 && m0.b01 == m1.b01 && m0.b11 == m1.b11;
+                const bool same = m0.b[0] == m1.b[0] && m0.b[1] == m1.b[1] && m0.b[2] == m1.b[2] &&
+                                  m0.b[3] == m1.b[3];
+                const char *pa0 = levb + m0.b[0] * cpitch, *pb0 = levb + m0.b[1] * cpitch;
+                const char *pc0 = levb + m0.b[2] * cpitch, *pd0 = levb + m0.b[3] * cpitch;
+                const char *pa1 = levb + m1.b[0] * cpitch, *pb1 = levb + m1.b[1] * cpitch;
+                const char *pc1 = levb + m1.b[2] * cpitch, *pd1 = levb + m1.b[3] * cpitch;
                 for (int l = lane * 2; l < nlev; l += 64) {
-                    const double2 a0 = *reinterpret_cast<const double2 *>(levb + m0.b00 + l * 8);
-                    const double2 b0 = *reinterpret_cast<const double2 *>(levb + m0.b10 + l * 8);
-                    const double2 c0 = *reinterpret_cast<const double2 *>(levb + m0.b01 + l * 8);
-                    const double2 d0 = *reinterpret_cast<const double2 *>(levb + m0.b11 + l * 8);
+                    const double2 a0 = *reinterpret_cast<const double2 *>(pa0 + l * 8);
+                    const double2 b0 = *reinterpret_cast<const double2 *>(pb0 + l * 8);
+                    const double2 c0 = *reinterpret_cast<const double2 *>(pc0 + l * 8);
+                    const double2 d0 = *reinterpret_cast<const double2 *>(pd0 + l * 8);
                     double2 a1 = a0, b1 = b0, c1 = c0, d1 = d0;
                     if (!same) {
-                        a1 = *reinterpret_cast<const double2 *>(levb + m1.b00 + l * 8);
-                        b1 = *reinterpret_cast<const double2 *>(levb + m1.b10 + l * 8);
-                        c1 = *reinterpret_cast<const double2 *>(levb + m1.b01 + l * 8);
-                        d1 = *reinterpret_cast<const double2 *>(levb + m1.b11 + l * 8);
+                        a1 = *reinterpret_cast<const double2 *>(pa1 + l * 8);
+                        b1 = *reinterpret_cast<const double2 *>(pb1 + l * 8);
+                        c1 = *reinterpret_cast<const double2 *>(pc1 + l * 8);
+                        d1 = *reinterpret_cast<const double2 *>(pd1 + l * 8);
                     }
                     double2 r0, r1;
                     {   // fastcompute.f90:100-102
@@ -389,7 +398,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                     if (two) __stcs(reinterpret_cast<double2 *>(o1 + l), r1);
                 }
             }
-            if (v + 1 < nvar) cons_sync();  // `lev` is rewritten by the next variable
+            lev_sel ^= 1;   // no barrier here: the next variable's B writes the other `lev` buffer
         }
     }
 }
@@ -428,26 +437,28 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
 struct MapKey {
     const void *ptr;
     int64_t nz, ny, nx, pitch;
-    int dtype;
+    int dtype, by;
     bool operator==(const MapKey &o) const
     {
-        return ptr == o.ptr && nz == o.nz && ny == o.ny && nx == o.nx && pitch == o.pitch && dtype == o.dtype;
+        return ptr == o.ptr && nz == o.nz && ny == o.ny && nx == o.nx && pitch == o.pitch && dtype == o.dtype &&
+               by == o.by;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey &k) const
     {
         size_t h = std::hash<const void *>()(k.ptr);
-        for (int64_t v : {k.nz, k.ny, k.nx, k.pitch, (int64_t)k.dtype}) h = h * 1000003u ^ std::hash<int64_t>()(v);
+        for (int64_t v : {k.nz, k.ny, k.nx, k.pitch, (int64_t)k.dtype, (int64_t)k.by}) h = h * 1000003u ^ std::hash<int64_t>()(v);
         return h;
     }
 };
 
-int tensor_map_for(const void *ptr, int dtype, int64_t nz, int64_t ny, int64_t nx, int64_t pitch, CUtensorMap *out)
+int tensor_map_for(const void *ptr, int dtype, int64_t nz, int64_t ny, int64_t nx, int64_t pitch, int by,
+                   CUtensorMap *out)
 {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ptr, nz, ny, nx, pitch, dtype};
+    const MapKey key{ptr, nz, ny, nx, pitch, dtype, by};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) {
@@ -462,7 +473,7 @@ int tensor_map_for(const void *ptr, int dtype, int64_t nz, int64_t ny, int64_t n
     const cuuint64_t eb = dtype == MT_F64 ? 8 : 4;
     cuuint64_t gdim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
     cuuint64_t gstr[2] = {(cuuint64_t)pitch * eb, (cuuint64_t)pitch * (cuuint64_t)ny * eb};
-    cuuint32_t box[3] = {(cuuint32_t)BX, (cuuint32_t)BY, (cuuint32_t)nz};
+    cuuint32_t box[3] = {(cuuint32_t)BX, (cuuint32_t)by, (cuuint32_t)nz};
     cuuint32_t es[3] = {1, 1, 1};
     CUtensorMap m;
     const CUresult r = enc(&m, dtype == MT_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
@@ -481,29 +492,25 @@ int tensor_map_for(const void *ptr, int dtype, int64_t nz, int64_t ny, int64_t n
 }
 
 struct Layout {
-    int stages, stage_bytes, LP, off_w2, off_lev, off_kp, off_meta, off_misc;
+    int stages, stage_bytes, LP, off_lev, lev_bytes, off_meta, off_misc;
     size_t total;
 };
 
 bool make_layout(int dtype, int64_t nz, int64_t nlev, Layout *L)
 {
-    static const int want = [] {   // MT_TMA_STAGES=2..4: ring depth (experiments); default 3
+    static const int want = [] {   // MT_TMA_STAGES=2..4: ring depth (experiments); default: what fits
         const char *e = getenv("MT_TMA_STAGES");
-        const int v = e ? atoi(e) : 3;
+        const int v = e ? atoi(e) : 4;
         return v < 2 ? 2 : (v > 4 ? 4 : v);
     }();
     const size_t eb = dtype == MT_F64 ? 8 : 4;
     const size_t stage = ((size_t)NC * nz * eb + 127) & ~size_t(127);
     const int LP = (int)((nlev % 4 == 2) ? nlev : nlev + 2);  // even; LP = 2 (mod 4): 2-way conflicts at worst
+    const size_t lev_bytes = ((size_t)NC * LP * 8 + 127) & ~size_t(127);
     for (int stages = want; stages >= 2; --stages) {
         size_t off = stage * stages;
-        const size_t off_w2 = off;
-        off += (size_t)nlev * NC * 8;
         const size_t off_lev = off;
-        off += (size_t)NC * LP * 8;
-        const size_t off_kp = off;
-        off += (size_t)nlev * NC;
-        off = (off + 15) & ~size_t(15);
+        off += 2 * lev_bytes;   // double-buffered level-interpolated columns
         const size_t off_meta = off;
         off += (size_t)NMETA * MAXT * sizeof(Meta);
         const size_t off_misc = off;
@@ -511,7 +518,7 @@ bool make_layout(int dtype, int64_t nz, int64_t nlev, Layout *L)
         const size_t total = off + 128;  // slack for the 128-byte alignment of the base
         if (total <= 227 * 1024) {
             L->stages = stages, L->stage_bytes = (int)stage, L->LP = LP;
-            L->off_w2 = (int)off_w2, L->off_lev = (int)off_lev, L->off_kp = (int)off_kp;
+            L->off_lev = (int)off_lev, L->lev_bytes = (int)lev_bytes;
             L->off_meta = (int)off_meta, L->off_misc = (int)off_misc;
             L->total = total;
             return true;
@@ -520,26 +527,25 @@ bool make_layout(int dtype, int64_t nz, int64_t nlev, Layout *L)
     return false;
 }
 
-}  // namespace
+constexpr int PP_SMALL = 5, PP_LARGE = 8;   // level pairs per column thread: nlev <= 60 / <= 96
 
-extern "C" {
-
-int mt_setdata_tma_supported(int dtype, int64_t nz, int64_t nlev, int64_t row_pitch)
+int supported_impl(int dtype, int64_t nz, int64_t nlev, int64_t row_pitch)
 {
     if (dtype != MT_F64 && dtype != MT_F32) return 0;
     const int64_t eb = dtype == MT_F64 ? 8 : 4;
-    if (nz < 2 || nz > 254 || nlev < 2 || nlev % 2 != 0 || (row_pitch * eb) % 16 != 0) return 0;
+    if (nz < 2 || nz > 254 || nlev < 2 || nlev % 2 != 0 || nlev > 2 * NG * PP_LARGE || (row_pitch * eb) % 16 != 0)
+        return 0;
     Layout L;
     if (!make_layout(dtype, nz, nlev, &L)) return 0;
     return encode_fn() != nullptr ? 1 : 0;
 }
 
-int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz, int64_t ny,
-                   int64_t nx, int64_t row_pitch, int64_t org_y, int64_t org_x, const double *levels,
-                   int64_t nlev, int direction, const int32_t *plan_ix, const double *plan_w, int64_t n,
-                   const int32_t *order, const int32_t *items, int64_t nitems, int64_t nflagged,
-                   const int32_t *hgt_idx, double *const *out, int64_t o_n, int flags, int32_t *counter,
-                   mt_stream_t stream)
+int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz, int64_t ny,
+                     int64_t nx, int64_t row_pitch, int64_t org_y, int64_t org_x, const double *levels,
+                     int64_t nlev, int direction, const int32_t *plan_ix, const double *plan_w, int64_t n,
+                     const int32_t *order, const int32_t *items, int64_t nitems, int64_t nflagged,
+                     const int32_t *hgt_idx, double *const *out, int64_t o_n, int flags, int32_t *counter,
+                     mt_stream_t stream)
 {
     MT_REQUIRE(fields && vert && levels && plan_ix && plan_w && order && items && out && counter,
                "mt_setdata_tma: null pointer");
@@ -548,22 +554,24 @@ int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dt
     MT_REQUIRE(direction == 0 || direction == 1, "mt_setdata_tma: direction must be 0 or 1 (decided by the caller "
                                                  "from column (0,0) of the full coordinate array)");
     const int64_t eb = dtype == MT_F64 ? 8 : 4;
-    MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 2 && nlev % 2 == 0 && nlev < 2147483647LL && o_n >= nlev &&
-                   o_n % 2 == 0,
-               "mt_setdata_tma: need 2 <= nz <= 254, an even number of levels and an even output pitch");
+    MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 2 && nlev % 2 == 0 && nlev <= 2 * NG * PP_LARGE && o_n >= nlev &&
+                   o_n % 2 == 0 && n < 2147483647LL,
+               "mt_setdata_tma: need 2 <= nz <= 254, an even number of levels <= %d and an even output pitch",
+               2 * NG * PP_LARGE);
     MT_REQUIRE(row_pitch >= nx && (row_pitch * eb) % 16 == 0 && ((uintptr_t)vert % 16) == 0,
                "mt_setdata_tma: source rows must be 16-byte aligned (row pitch %lld elements)", (long long)row_pitch);
     Layout L;
-    MT_REQUIRE(make_layout(dtype, nz, nlev, &L), "mt_setdata_tma: tile does not fit in shared memory (nz=%lld, nlev=%lld)",
-               (long long)nz, (long long)nlev);
+    MT_REQUIRE(make_layout(dtype, nz, nlev, &L),
+               "mt_setdata_tma: tile does not fit in shared memory (nz=%lld, nlev=%lld)", (long long)nz,
+               (long long)nlev);
     TmaParams P;
-    int rc = tensor_map_for(vert, dtype, nz, ny, nx, row_pitch, &P.maps[0]);
+    int rc = tensor_map_for(vert, dtype, nz, ny, nx, row_pitch, BY, &P.maps[0]);
     if (rc != MT_OK) return rc;
     OutPtrs op;
     for (int v = 0; v < nvar; ++v) {
         MT_REQUIRE(fields[v] && out[v] && ((uintptr_t)out[v] % 16 == 0) && ((uintptr_t)fields[v] % 16 == 0),
                    "mt_setdata_tma: field %d is null or not 16-byte aligned", v);
-        rc = tensor_map_for(fields[v], dtype, nz, ny, nx, row_pitch, &P.maps[v + 1]);
+        rc = tensor_map_for(fields[v], dtype, nz, ny, nx, row_pitch, BY, &P.maps[v + 1]);
         if (rc != MT_OK) return rc;
         P.out[v] = out[v];
         op.out[v] = out[v];
@@ -578,33 +586,61 @@ int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dt
     }
     if (nitems == 0) return MT_OK;
     MT_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), s));
-    int64_t grid64 = mt::sm_count();
+    int64_t grid64 = mt::sm_count();   // persistent: one CTA per SM
     if (grid64 > nitems) grid64 = nitems;
     const unsigned grid = (unsigned)grid64;
     const bool rf = (flags & MT_IL_ROUND_F32) != 0, inc = (flags & MT_IL_INCLUSIVE) != 0;
     mt::ProfScope prof("k_setdata_tma", stream);
-#define ST_LAUNCH(T, INC, RND)                                                                                     \
+    const bool small = nlev <= 2 * NG * PP_SMALL;
+#define ST_LAUNCH(T, INC, RND, PPV)                                                                                \
     do {                                                                                                           \
-        MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+        MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC, RND, PPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)L.total));                                                               \
-        k_setdata_tma<T, INC, RND><<<grid, NTHREADS, L.total, s>>>(                                                \
+        k_setdata_tma<T, INC, RND, PPV><<<grid, NTHREADS, L.total, s>>>(                                           \
             P, nvar, (int)nz, (int)nlev, L.LP, L.stages, L.stage_bytes, (int)org_x, (int)org_y, levels, direction, \
-            pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n, L.off_w2,   \
-            L.off_lev, L.off_kp, L.off_meta, L.off_misc);                                                          \
+            pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n, L.off_lev,  \
+            L.lev_bytes, L.off_meta, L.off_misc);                                                                  \
     } while (0)
-#define ST_DISPATCH(T)                           \
-    do {                                         \
-        if (inc && rf) ST_LAUNCH(T, true, true); \
-        else if (inc) ST_LAUNCH(T, true, false); \
-        else if (rf) ST_LAUNCH(T, false, true);  \
-        else ST_LAUNCH(T, false, false);         \
+#define ST_DISPATCH2(T, INC, RND)                      \
+    do {                                               \
+        if (small) ST_LAUNCH(T, INC, RND, PP_SMALL);   \
+        else ST_LAUNCH(T, INC, RND, PP_LARGE);         \
+    } while (0)
+#define ST_DISPATCH(T)                              \
+    do {                                            \
+        if (inc && rf) ST_DISPATCH2(T, true, true); \
+        else if (inc) ST_DISPATCH2(T, true, false); \
+        else if (rf) ST_DISPATCH2(T, false, true);  \
+        else ST_DISPATCH2(T, false, false);         \
     } while (0)
     if (dtype == MT_F64) ST_DISPATCH(double);
     else ST_DISPATCH(float);
 #undef ST_DISPATCH
+#undef ST_DISPATCH2
 #undef ST_LAUNCH
     MT_LAUNCH_CHECK();
     return MT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mt_setdata_tma_supported(int dtype, int64_t nz, int64_t nlev, int64_t row_pitch)
+{
+    return supported_impl(dtype, nz, nlev, row_pitch);
+}
+
+int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz, int64_t ny,
+                   int64_t nx, int64_t row_pitch, int64_t org_y, int64_t org_x, const double *levels,
+                   int64_t nlev, int direction, const int32_t *plan_ix, const double *plan_w, int64_t n,
+                   const int32_t *order, const int32_t *items, int64_t nitems, int64_t nflagged,
+                   const int32_t *hgt_idx, double *const *out, int64_t o_n, int flags, int32_t *counter,
+                   mt_stream_t stream)
+{
+    return setdata_tma_impl(fields, nvar, vert, dtype, nz, ny, nx, row_pitch, org_y, org_x, levels, nlev, direction,
+                            plan_ix, plan_w, n, order, items, nitems, nflagged, hgt_idx, out, o_n, flags, counter,
+                            stream);
 }
 
 }  // extern "C"

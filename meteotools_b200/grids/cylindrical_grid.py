@@ -183,9 +183,9 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 fits = trz and nz <= 254 and self.Nz % 2 == 0
                 if fits and mode == "tma" and lib.mt_setdata_tma_supported(dtype, nz, self.Nz, snx):
                     # one warp-specialised TMA kernel, no intermediate in HBM (csrc/setdata_tma.cu)
-                    tw_, th_, al_ = _lib.tma_tile(dtype)
+                    tw_, th_, al_, mt_ = _lib.tma_tile(dtype)
                     order_t, items_t, nitems, nflag, counter = self._fused_items_for(
-                        plan, tw_, th_, spatial=True, align=al_, org_x=ox)
+                        plan, tw_, th_, max_targets=mt_, spatial=True, align=al_, org_x=ox)
                     _lib.check(lib.mt_setdata_tma(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, sny,
                                                   snx, snx, oy, ox, D.ptr(levels), self.Nz, direction,
                                                   D.ptr(plan[0]), D.ptr(plan[1]), n, D.ptr(order_t),
