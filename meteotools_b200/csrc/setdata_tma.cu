@@ -60,7 +60,7 @@ struct __align__(64) TmaParams {
 struct Meta {   // one staged target (two 16-byte words)
     double fx, fy;
     int tgt, terrain;           // target index (output row = tgt * o_n), terrain level index
-    unsigned short b[4];        // tile-local ids of the four corner columns (rows of `lev`)
+    uint32_t b01, b23;          // tile-local ids of the four corner columns (rows of `lev`), 16 bits each
 };
 static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
 
@@ -182,10 +182,10 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                             m.fx = sw[k].x, m.fy = sw[k].y, m.tgt = tgt[k], m.terrain = ster[k];
                             // corner columns as element offsets / LP (column ids); the consumer
                             // multiplies by the column pitch
-                            m.b[0] = (unsigned short)((six[k].z - nit.y) * BX + (six[k].x - nit.x));
-                            m.b[1] = (unsigned short)((six[k].z - nit.y) * BX + (six[k].y - nit.x));
-                            m.b[2] = (unsigned short)((six[k].w - nit.y) * BX + (six[k].x - nit.x));
-                            m.b[3] = (unsigned short)((six[k].w - nit.y) * BX + (six[k].y - nit.x));
+                            const uint32_t r0 = (uint32_t)(six[k].z - nit.y) * BX, r1 = (uint32_t)(six[k].w - nit.y) * BX;
+                            const uint32_t c0 = (uint32_t)(six[k].x - nit.x), c1 = (uint32_t)(six[k].y - nit.x);
+                            m.b01 = (r0 + c0) | ((r0 + c1) << 16);
+                            m.b23 = (r1 + c0) | ((r1 + c1) << 16);
                             mt_[lane + 32 * k] = m;
                         }
                     __syncwarp();
@@ -235,11 +235,11 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     const int klo_missing = decreasing ? 1 : 0; // any pair of valid rows: a missing bracket has w2 = NaN
     const int stage_elems = stage_bytes / (int)sizeof(T);
     const T *raw = reinterpret_cast<const T *>(smem);
-    // (column, level-group) ownership of the column phases: thread -> column tid % 80, level pairs
-    // tid / 80, +NG, +2 NG, ... (NG * 80 of the consumer threads)
+    // (column, level-group) ownership of the column phases: thread -> column tid % 80 and the ppn
+    // consecutive level pairs from (tid / 80) * ppn
     const int c_own = tid % NC, g_own = tid / NC;
     const bool col_thread = tid < NG * NC;
-    const int npair = nlev >> 1;
+    const int npair = nlev >> 1, ppn = (npair + NG - 1) / NG, lp_own = g_own * ppn;
     // this thread's brackets (row offsets of the "lo" samples of both levels of a pair, weights)
     int kk[PP];
     double wx[PP], wy[PP];
@@ -266,17 +266,28 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
         // w1*f + w2*f is NaN without a branch in the per-variable loop.
         if (col_thread) {
             const bool is_mono = mono[c_own] != 0;
+            // K = first row with sgn * v[K] > sgn * want (upper bound).  The thread's levels are
+            // consecutive: when they ascend (in the direction of the coordinate) K only moves
+            // forward, so after the first binary search the rows are walked, not searched.
+            int K = 0;
+            double ww_prev = 0.0;
+            bool have_prev = false;
             auto bracket = [&](double want, int &klo, double &w2) {
                 int kp = -1;
                 if (is_mono) {
-                    const double ww = sgn * want;  // upper bound: first K with sgn*v[K] > ww
-                    int lo = 0, hi = nz;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (sgn * (double)vt[mid * NC] > ww) hi = mid;
-                        else lo = mid + 1;
+                    const double ww = sgn * want;
+                    if (have_prev && ww >= ww_prev) {
+                        while (K < nz && sgn * (double)vt[K * NC] <= ww) ++K;
+                    } else {
+                        int lo = 0, hi = nz;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sgn * (double)vt[mid * NC] > ww) hi = mid;
+                            else lo = mid + 1;
+                        }
+                        K = lo;
                     }
-                    const int K = lo;
+                    ww_prev = ww, have_prev = true;
                     if (K >= 1 && K <= nz - 1) {
                         if (INCLUSIVE) kp = K;
                         else if (sgn * (double)vt[(K - 1) * NC] < ww) kp = K;
@@ -303,10 +314,10 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             };
 #pragma unroll
             for (int i = 0; i < PP; ++i) {
-                const int lp = g_own + i * NG;
+                const int lp = lp_own + i;
                 int k0 = klo_missing, k1 = klo_missing;
                 wx[i] = wy[i] = nan_f64();
-                if (lp < npair) {
+                if (i < ppn && lp < npair) {
                     bracket(lev_s[2 * lp], k0, wx[i]);
                     bracket(lev_s[2 * lp + 1], k1, wy[i]);
                 }
@@ -329,8 +340,8 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 double *lv = reinterpret_cast<double *>(levb_w) + c_own * LP;
 #pragma unroll
                 for (int i = 0; i < PP; ++i) {
-                    const int lp = g_own + i * NG;
-                    if (lp < npair) {
+                    const int lp = lp_own + i;
+                    if (i < ppn && lp < npair) {
                         const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;
                         const double f00 = (double)fc[ka], f01 = (double)fc[ka + dhi];
                         const double f10 = (double)fc[kb], f11 = (double)fc[kb + dhi];
@@ -349,7 +360,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             // are sorted by source cell, so a pair usually shares its four corner columns: one set
             // of shared-memory loads then serves both
             double *__restrict__ out = P.out[v];
-            const char *levb = reinterpret_cast<const char *>(levb_w);
+            const char *lane_b = reinterpret_cast<const char *>(levb_w) + lane * 16;   // this lane's level pair
             const int cpitch = LP * 8;
             for (int j = 2 * warp; j < cnt; j += 2 * (NCONS / 32)) {
                 const bool two = j + 1 < cnt;
@@ -357,23 +368,22 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 const Meta m1 = mt_[two ? j + 1 : j];
                 double *o0 = out + (int64_t)m0.tgt * o_n, *o1 = out + (int64_t)m1.tgt * o_n;
                 const bool masked = (m0.terrain | m1.terrain) > 0;                       // warp-uniform
-                const bool same = m0.b[0] == m1.b[0] && m0.b[1] == m1.b[1] && m0.b[2] == m1.b[2] &&
-                                  m0.b[3] == m1.b[3];
-                const char *pa0 = levb + m0.b[0] * cpitch, *pb0 = levb + m0.b[1] * cpitch;
-                const char *pc0 = levb + m0.b[2] * cpitch, *pd0 = levb + m0.b[3] * cpitch;
-                const char *pa1 = levb + m1.b[0] * cpitch, *pb1 = levb + m1.b[1] * cpitch;
-                const char *pc1 = levb + m1.b[2] * cpitch, *pd1 = levb + m1.b[3] * cpitch;
-                for (int l = lane * 2; l < nlev; l += 64) {
-                    const double2 a0 = *reinterpret_cast<const double2 *>(pa0 + l * 8);
-                    const double2 b0 = *reinterpret_cast<const double2 *>(pb0 + l * 8);
-                    const double2 c0 = *reinterpret_cast<const double2 *>(pc0 + l * 8);
-                    const double2 d0 = *reinterpret_cast<const double2 *>(pd0 + l * 8);
+                const bool same = m0.b01 == m1.b01 && m0.b23 == m1.b23;
+                const char *pa0 = lane_b + (m0.b01 & 0xffffu) * cpitch, *pb0 = lane_b + (m0.b01 >> 16) * cpitch;
+                const char *pc0 = lane_b + (m0.b23 & 0xffffu) * cpitch, *pd0 = lane_b + (m0.b23 >> 16) * cpitch;
+                const char *pa1 = lane_b + (m1.b01 & 0xffffu) * cpitch, *pb1 = lane_b + (m1.b01 >> 16) * cpitch;
+                const char *pc1 = lane_b + (m1.b23 & 0xffffu) * cpitch, *pd1 = lane_b + (m1.b23 >> 16) * cpitch;
+                for (int l = lane * 2, lo8 = 0; l < nlev; l += 64, lo8 += 512) {
+                    const double2 a0 = *reinterpret_cast<const double2 *>(pa0 + lo8);
+                    const double2 b0 = *reinterpret_cast<const double2 *>(pb0 + lo8);
+                    const double2 c0 = *reinterpret_cast<const double2 *>(pc0 + lo8);
+                    const double2 d0 = *reinterpret_cast<const double2 *>(pd0 + lo8);
                     double2 a1 = a0, b1 = b0, c1 = c0, d1 = d0;
                     if (!same) {
-                        a1 = *reinterpret_cast<const double2 *>(pa1 + l * 8);
-                        b1 = *reinterpret_cast<const double2 *>(pb1 + l * 8);
-                        c1 = *reinterpret_cast<const double2 *>(pc1 + l * 8);
-                        d1 = *reinterpret_cast<const double2 *>(pd1 + l * 8);
+                        a1 = *reinterpret_cast<const double2 *>(pa1 + lo8);
+                        b1 = *reinterpret_cast<const double2 *>(pb1 + lo8);
+                        c1 = *reinterpret_cast<const double2 *>(pc1 + lo8);
+                        d1 = *reinterpret_cast<const double2 *>(pd1 + lo8);
                     }
                     double2 r0, r1;
                     {   // fastcompute.f90:100-102
