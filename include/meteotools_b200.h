@@ -146,6 +146,24 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
                    double *const *out, int64_t o_lev, int64_t o_y, int64_t o_x, int flags,
                    mt_stream_t stream);
 
+/* ---- spline vertical interpolation (`ver_interp_order = 2 / 3`:
+ *      grids/cylindrical_grid.py:83-93,123-127, grids/cartesian_grid.py:61-74,108-112) -----------
+ * Per column: scipy.interpolate.splrep(vert[:,j,i], field[:,j,i], k=order) followed by
+ * splev(levels) -- FITPACK's interpolating spline (s = 0), end polynomials extrapolate; same
+ * array / box / output conventions as mt_interplevel, float32 input is widened, the result is
+ * float64 (no rounding: the reference writes into a float64 array).  A column whose coordinate
+ * decreases (scipy raises ValueError "Error on input data") sets a status bit that
+ * mt_spline_status() returns and clears (it synchronises the stream); the values written for such
+ * a column are unspecified.  mt_setdata takes MT_IL_SPLINE2 / MT_IL_SPLINE3 in `flags` to use this
+ * routine as its vertical stage. */
+#define MT_IL_SPLINE2 4
+#define MT_IL_SPLINE3 8
+int mt_spline_levels(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz,
+                     int64_t ny, int64_t nx, int64_t y0, int64_t y1, int64_t x0, int64_t x1,
+                     const double *levels, int64_t nlev, int order, double *const *out,
+                     int64_t o_lev, int64_t o_y, int64_t o_x, mt_stream_t stream);
+int mt_spline_status(mt_stream_t stream);
+
 /* ---- fused set_data (F1): vertical interpolation of the bounding box of the targets, then the
  *      bilinear gather, then the optional terrain mask -- the pipeline of
  *      cylindrical_grid.set_data (:95-137) / cartesian_grid.set_data (:76-125).

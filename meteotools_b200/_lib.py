@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(path_of_meteotools, "lib",
 
 # constants of the header
 MT_F64, MT_F32 = 0, 1
-MT_IL_INCLUSIVE, MT_IL_ROUND_F32 = 1, 2
+MT_IL_INCLUSIVE, MT_IL_ROUND_F32, MT_IL_SPLINE2, MT_IL_SPLINE3 = 1, 2, 4, 8
 MT_MAX_VARS = 16
 MT_NANSUM_SCRATCH = 2048
 MT_TMA_TILE_W_F64, MT_TMA_TILE_W_F32, MT_TMA_TILE_H = 14, 12, 4   # source cells per tile of mt_setdata_tma
@@ -111,6 +111,9 @@ _SIGS = {
                                             c_i64, c_i64, c_vp]),
     "mt_interplevel": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_int, c_vp]),
+    "mt_spline_levels": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                 c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "mt_spline_status": (c_int, [c_vp]),
     "mt_setdata_workspace_bytes": (c_i64, [c_int, c_i64, c_i64, c_i64, c_i64, c_i64]),
     "mt_setdata": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                            c_dbl, c_dbl, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_vp,

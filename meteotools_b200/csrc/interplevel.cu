@@ -525,7 +525,13 @@ int mt_setdata(const void *const *fields, int nvar, const void *vert, int dtype,
         virt[v] = ws[v] - (y0 * bx + x0) * nlev;
     }
     // stage 1: vertical interpolation of the box, level-fastest [by][bx][nlev]
-    int rc = mt_interplevel(fields, nvar, vert, dtype, nz, ny, nx, y0 - org_y, y1 - org_y, x0 - org_x,
+    int rc;
+    if (flags & (MT_IL_SPLINE2 | MT_IL_SPLINE3))   // ver_interp_order = 2 / 3 (csrc/spline.cu)
+        rc = mt_spline_levels(fields, nvar, vert, dtype, nz, ny, nx, y0 - org_y, y1 - org_y, x0 - org_x,
+                              x1 - org_x, levels, nlev, (flags & MT_IL_SPLINE3) ? 3 : 2, ws, 1, bx * nlev, nlev,
+                              stream);
+    else
+        rc = mt_interplevel(fields, nvar, vert, dtype, nz, ny, nx, y0 - org_y, y1 - org_y, x0 - org_x,
                             x1 - org_x, levels, nlev, levels_order, direction, ws, 1, bx * nlev, nlev,
                             flags, stream);
     if (rc != MT_OK) return rc;

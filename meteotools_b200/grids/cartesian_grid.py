@@ -74,8 +74,8 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
     @timer
     def set_data(self, src_dx, src_dy, src_vertical, vertical_interp_order=1, inclusive=False, **vardict):
         """Interpolate source fields onto this grid (:76-125); terrain: z <= hgt -> NaN (:127-136)."""
-        if vertical_interp_order != 1:
-            raise NotImplementedError("spline vertical interpolation is a later row (SURVEY 8f-3)")
+        if vertical_interp_order not in (1, 2, 3):   # the reference leaves `tmp` undefined (:100-112)
+            raise NameError(f"vertical_interp_order must be 1, 2 or 3, got {vertical_interp_order}")
         cur3d = []
         for varname, var in vardict.items():
             if len(var.shape) == 3:
@@ -85,7 +85,8 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
                 self._put(varname, self._interp2d_var(src_dx, src_dy, var), ndim=2)
                 self.varlist2D.append(varname)
         if cur3d:
-            self._setdata3d(src_dx, src_dy, src_vertical, [vardict[n] for n in cur3d], cur3d, None, inclusive)
+            self._setdata3d(src_dx, src_dy, src_vertical, [vardict[n] for n in cur3d], cur3d, None, inclusive,
+                            spline_order=vertical_interp_order)
         if 'hgt' in self.varlist2D:
             self.set_terrain()
             self.terrain_mask_vars()

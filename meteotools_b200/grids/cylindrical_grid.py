@@ -12,7 +12,8 @@ CUDA library:
 Fields live on the device in (theta, r, z) memory order ("TRZ": z contiguous), which is what the
 gather produces and what the reference's own interpolation returns (a layer-fastest strided
 array); through the attribute protocol they appear as (Nz, Ntheta, Nr) arrays.
-Spline vertical interpolation (ver_interp_order=2) is a SURVEY 8(f) "next" row.
+Spline vertical interpolation (``ver_interp_order=2``, :83-93, :123-127) runs FITPACK's
+interpolating spline per column on the device (``mt_spline_levels``, csrc/spline.cu).
 """
 import numpy as np
 
@@ -107,8 +108,8 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
 
         ``inclusive``: bracket test of the vertical interpolation, see include/meteotools_b200.h
         (MT_IL_INCLUSIVE); default = the strict test of wrf-python's DINTERP3DZ."""
-        if ver_interp_order != 1:
-            raise NotImplementedError("spline vertical interpolation is a later row (SURVEY 8f-3)")
+        if ver_interp_order not in (1, 2):   # the reference leaves `tmp` undefined -> NameError (:110-127)
+            raise NameError(f"ver_interp_order must be 1 (linear) or 2 (quadratic spline), got {ver_interp_order}")
         self.varlist3D, self.varlist2D = [], []
         for varname, var in vardict.items():
             if len(var.shape) == 3:
@@ -122,12 +123,14 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             hgt_idx = self._hgt_idx_dev
         if self.varlist3D:
             self._setdata3d(wrf_dx, wrf_dy, wrf_vertical, [vardict[n] for n in self.varlist3D],
-                            self.varlist3D, hgt_idx, inclusive)
+                            self.varlist3D, hgt_idx, inclusive, spline_order=ver_interp_order)
 
-    def _setdata3d(self, dx, dy, vert, sources, names, hgt_idx, inclusive):
+    def _setdata3d(self, dx, dy, vert, sources, names, hgt_idx, inclusive, spline_order=1):
         """3-D variables: one ``mt_setdata`` per batch of <= 16 variables.  Host arrays are
         uploaded box-only with one strided DMA each (``mt_upload_box``); CUDA tensors are used in
-        place (full array, no copy)."""
+        place (full array, no copy).  ``spline_order`` 2 / 3: the vertical stage is the per-column
+        interpolating spline of the reference's ``spline`` method (splrep + splev) instead of
+        wrf.interplevel; the result is float64 whatever the input dtype, as in the reference."""
         lib = _lib.load()
         t = D.torch()
         nz, ny, nx = vert.shape
@@ -174,13 +177,15 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 vert_cache[dtype] = stage(vert, use32)
             vert_d = vert_cache[dtype]
             flags = (_lib.MT_IL_INCLUSIVE if inclusive else 0) | (_lib.MT_IL_ROUND_F32 if want32 else 0)
+            if spline_order != 1:
+                flags = _lib.MT_IL_SPLINE2 if spline_order == 2 else _lib.MT_IL_SPLINE3
             for b0 in range(0, len(group), _lib.MT_MAX_VARS):
                 batch = group[b0:b0 + _lib.MT_MAX_VARS]
                 srcs = [stage(s, use32) for _, s in batch]
                 outs = [self._new() for _ in batch]
                 import os
                 mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
-                fits = trz and nz <= 254 and self.Nz % 2 == 0
+                fits = trz and nz <= 254 and self.Nz % 2 == 0 and spline_order == 1
                 if fits and mode == "tma" and lib.mt_setdata_tma_supported(dtype, nz, self.Nz, snx):
                     # one warp-specialised TMA kernel, no intermediate in HBM (csrc/setdata_tma.cu)
                     tw_, th_, al_, mt_ = _lib.tma_tile(dtype)
@@ -215,6 +220,9 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                                           D.ptr(plan[0]), D.ptr(plan[1]), n, D.ptr(hgt_idx),
                                           D.ptr_array(outs), 1 if trz else n, self.Nz if trz else 1, flags,
                                           D.ptr(ws), wsb, D.stream()), 'mt_setdata')
+                if spline_order != 1 and lib.mt_spline_status(D.stream()) != 0:
+                    # scipy.interpolate.splrep: ier = 10 -> ValueError (cylindrical_grid.py:90)
+                    raise ValueError("Error on input data")
                 for (name, _), o in zip(batch, outs):
                     self._put(name, o)
 

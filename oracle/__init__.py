@@ -14,6 +14,10 @@ Contents
 * ``calc_oracle.py``        numpy restatement of ``meteotools/calc`` and of the
   diagnostic methods of ``meteotools/grids``.
 
+* ``spline_levels``         the reference's ``spline`` method (per-column
+  ``scipy.interpolate.splrep`` + ``splev``): scipy IS the third-party dependency the
+  reference calls and it is installed, so this row's oracle is the real thing.
+
 gfortran is absent from this image, so ``oracle/_ref`` (the real reference
 library) cannot be built; every number labelled "cpu_baseline" is therefore
 ``kind="port"``.
@@ -275,3 +279,19 @@ def interplevel(field3d, vert, levels, inclusive: bool = False):
     out = np.empty((lv.shape[0], ny, nx))
     lib().oi_interplevel(_p(f), _p(v), nz, ny, nx, _p(lv), lv.shape[0], int(inclusive), _p(out))
     return out.astype(in_dtype, copy=False)
+
+
+def spline_levels(var, vert, obj_vert, order=2):
+    """``cylindrical_grid.spline`` (grids/cylindrical_grid.py:83-93, k = 2) /
+    ``cartesian_grid.spline`` (grids/cartesian_grid.py:61-74, k = order): per column the
+    interpolating spline of scipy (FITPACK ``curfit`` with s = 0) evaluated at ``obj_vert``
+    (``splev``, ext = 0: extrapolates).  Result float64 (the reference fills ``np.zeros``)."""
+    from scipy.interpolate import splev, splrep
+    var, vert = np.asarray(var), np.asarray(vert)
+    ny, nx = var.shape[1], var.shape[2]
+    out = np.zeros([len(obj_vert), ny, nx])
+    for j in range(ny):
+        for i in range(nx):
+            cs = splrep(vert[:, j, i], var[:, j, i], k=order)
+            out[:, j, i] = splev(obj_vert, cs)
+    return out

@@ -370,10 +370,43 @@ def gen_reductions(mt, out):
         out["o_rcar_smooth3d_u_cw"] = np.asarray(car.smooth3d_u)
 
 
+def gen_spline(mt, out):
+    """``ver_interp_order = 2`` (cylindrical) / ``vertical_interp_order = 2, 3``
+    (Cartesian) through the reference's own set_data (multiprocessing pool + scipy splrep/splev)."""
+    from meteotools.grids import cartesian_grid, cylindrical_grid
+    rng = np.random.default_rng(7)
+    nz, ny, nx, dx = 14, 40, 44, 2000.0
+    hgt, z3d, fields = synth_wrf(rng, nz, ny, nx, dx)
+    cxl, cyl_ = ((nx + 1) / 2 - 1) * dx, ((ny + 1) / 2 - 1) * dx
+    out.update(s_hgt=hgt, s_z3d=z3d, s_u=fields["u"], s_T=fields["T"], s_dx=dx, s_cx=cxl, s_cy=cyl_)
+    cyl = cylindrical_grid(dict(SD))
+    cyl.set_horizontal_location(cxl, cyl_)
+    cyl.set_data(dx, dx, z3d, ver_interp_order=2, u=fields["u"], T=fields["T"], hgt=hgt)
+    out.update(o_cyl_u_k2=cyl.u, o_cyl_T_k2=cyl.T, o_cyl_hgt_idx=cyl.hgt_idx)
+    for order in (2, 3):
+        car = cartesian_grid(dict(Nx=10, Ny=9, Nz=10, dx=3000, dy=3000, dz=600, z_start=100,
+                                  vertical_coord_type="z", SOR_parameter=1.9, max_iteration_times=10,
+                                  iteration_tolerance=0.05))
+        car.set_horizontal_location(cxl, cyl_)
+        car.set_data(dx, dx, z3d, vertical_interp_order=order, u=fields["u"], hgt=hgt)
+        out[f"o_car_u_k{order}"] = car.u
+    # the method itself on a few columns, float32 input included
+    sub = (slice(None), slice(3, 6), slice(4, 9))
+    lev = np.arange(-200.0, 21000.0, 700.0)      # extrapolates below and above the column
+    out["s_lev"] = lev
+    out["o_spline_k2"] = cylindrical_grid.spline(None, fields["u"][sub], z3d[sub], lev)
+    out["o_spline_k3"] = cartesian_grid.spline(None, fields["u"][sub], z3d[sub], lev, 3)
+    out["o_spline_k3_f32"] = cartesian_grid.spline(None, fields["u"][sub].astype(np.float32),
+                                                   z3d[sub].astype(np.float32), lev, 3)
+
+
 def main():
     mt = import_reference()
+    only = set(sys.argv[1:])
     for name, fn in (("interp", gen_interp), ("calc", gen_calc), ("grids", gen_grids),
-                     ("setdata", gen_setdata), ("reductions", gen_reductions)):
+                     ("setdata", gen_setdata), ("reductions", gen_reductions), ("spline", gen_spline)):
+        if only and name not in only:
+            continue
         out = {}
         fn(mt, out)
         path = os.path.join(HERE, f"{name}.npz")
