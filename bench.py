@@ -485,11 +485,12 @@ def roofline(kern, pipe, cyl, tc_iters, steps):
         # outputs, plan
         "k_setdata_fused": 8.0 * nz * U * (V + 1) + 8.0 * nlev * n * V + 32.0 * n,
         "k_setdata_tma": 8.0 * nz * U * (V + 1) + 8.0 * nlev * n * V + 32.0 * n,
-        # remaining Tc sweeps (in registers when NaN is present) + theta_e: reads g, Tc, Th, qv;
-        # writes Tc, Th_e
-        "k_tc_finish": 8.0 * NPTS * 6,
-        # reads T,p,qv,qc,qr; writes 12 outputs (incl. the first Tc sweep) + the sweep-invariant g
-        "k_td_main": 8.0 * NPTS * (5 + 13),
+        # the stop-test kernel: with NaN in the data (terrain) the ten certain sweeps were already
+        # produced speculatively by k_td_main and this launch only reads the flag
+        "k_tc_finish": None,
+        # reads T,p,qv,qc,qr; writes the 13 outputs of the cyl_td set (Tc after the ten certain
+        # sweeps and theta_e included) + the sweep-invariant g
+        "k_td_main": 8.0 * NPTS * (5 + 14),
         # reads g, Tc; writes Tc
         "k_tc_iter": 8.0 * NPTS * 3,
     }

@@ -128,6 +128,60 @@ k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__
     block_max_to(m, maxbits + iter);
 }
 
+// The remaining `nrest` CERTAIN sweeps of calc_Tc for one point (t = the iterate after sweep
+// `10 - nrest`, gg = the sweep-invariant g), used when the reference is known to run all ten sweeps
+// (some point is NaN, see k_tc_finish).
+// The sweeps are the fixed-point iteration L <- F(L) = log B - log(g - a L) on L = log Tc
+// (a = Cp/Rd, contraction F' = a/D = a Tc/B ~ 0.18).  With L* the fixed point, D* = g - a L*
+// and c = a/D*, the iterates obey EXACTLY  delta' = -log1p(-c delta)  for delta = L - L*.
+// After the remaining sweeps delta is ~1e-9, so float32 carries it to ~1e-15 of Tc; what needs
+// double precision is L* alone: two float32 Newton steps on h(L) = L - F(L) from log Tc_first
+// and ONE double step (quadratic: error ~0.02 e^2) -- one double log and two double divisions
+// per point instead of nine logs.  Measured against the literal ten sweeps: <= 3e-13 relative
+// over T 180..330 K, P 10..1080 hPa, qv 1e-8..0.05 (tests/test_gpu_calc.py); points outside the
+// series' range (|c delta|, |Tc_first/Tc* - 1| >= 0.1, no convergence, non-finite) take the
+// literal sweeps, NaN points (terrain) stay NaN.
+__device__ __forceinline__ double tc_finish_point(double t, double gg, int nrest, int exact,
+                                                  const mt::fm::Tables *tb)
+{
+    constexpr double logB = 8.597851094433691;  // log(5420)
+    if (t != t || gg != gg) return mt::nan_f64();
+    const float gf = (float)gg, af = (float)CpRd, lbf = (float)logB;
+    // MUFU-based float32 log / divide (abs. error ~1e-6 on L): the double step squares it
+    float Lf = __logf((float)t);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float Df = gf - af * Lf;
+        const float hf = Lf - lbf + __logf(Df);
+        Lf = Lf - __fdividef(hf * Df, Df - af);
+    }
+    double L = (double)Lf;
+    double D = gg - CpRd * L;
+    const double h = L - logB + mt::fm::flog(D, tb);
+    L = L - mt::fm::fdiv(h * D, D - CpRd);
+    D = gg - CpRd * L;
+    const double Tcs = mt::fm::fdiv(B, D);
+    const float c = __fdividef(af, (float)D);
+    const float d = __fdividef((float)(t - Tcs), (float)Tcs);
+    // delta_first = log1p(d)
+    float dl = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
+    const bool ok = fabs(h) < 1e-4 && fabsf(d) < 0.1f && fabsf(c * dl) < 0.1f && D > 0.0;
+    if (!ok || exact) {   // the literal sweeps
+        double Lx = log(t), Dx = gg - CpRd * Lx;
+        for (int it = 1; it < nrest; ++it) {
+            Lx = logB - log(Dx);
+            Dx = gg - CpRd * Lx;
+        }
+        return B / Dx;
+    }
+    for (int k = 0; k < nrest; ++k) {
+        const float u = c * dl;  // -log1p(-u) = u + u^2/2 + u^3/3 + ...
+        dl = u * fmaf(u, fmaf(u, fmaf(u, fmaf(u, 0.2f, 0.25f), 0.33333334f), 0.5f), 1.0f);
+    }
+    const float e = fmaf(dl * dl, fmaf(dl, 0.16666667f, 0.5f), dl);  // expm1(delta)
+    return Tcs + Tcs * (double)e;
+}
+
 // Everything after the first sweep in ONE cooperative launch (replaces nine per-sweep launches,
 // the iteration counter and the theta_e kernel):
 //  * NaN fast path.  If the max |diff| of sweep `first-1` is NaN, some point is NaN for good (a NaN
@@ -141,10 +195,10 @@ k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__
 __global__ void __launch_bounds__(256)
 k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, int first,
             unsigned long long *__restrict__ maxbits, int vec_ok, const double *__restrict__ Th,
-            const double *__restrict__ qv, double *__restrict__ Th_e, int exact)
+            const double *__restrict__ qv, double *__restrict__ Th_e, int exact, int speculated,
+            const double *__restrict__ T)
 {
     namespace cg = cooperative_groups;
-    constexpr double logB = 8.597851094433691;  // log(5420)
     __shared__ mt::fm::Tables tb;
     mt::fm::load_tables(&tb);
     __syncthreads();
@@ -156,55 +210,9 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
             for (int it = first; it < 10; ++it) maxbits[it] = maxbits[first - 1];
             reinterpret_cast<double *>(maxbits)[15] = 10.0;
         }
+        if (speculated) return;   // k_td_main already wrote the results of this branch
         const int nrest = 10 - first;  // sweeps still to run (>= 1); t below is the iterate Tc_first
-        auto finish_exact = [&](double t, double gg) {
-            double L = log(t), D = gg - CpRd * L;
-            for (int it = first + 1; it < 10; ++it) {
-                L = logB - log(D);
-                D = gg - CpRd * L;
-            }
-            return B / D;
-        };
-        // The sweeps are the fixed-point iteration L <- F(L) = log B - log(g - a L) on L = log Tc
-        // (a = Cp/Rd, contraction F' = a/D = a Tc/B ~ 0.18).  With L* the fixed point, D* = g - a L*
-        // and c = a/D*, the iterates obey EXACTLY  delta' = -log1p(-c delta)  for delta = L - L*.
-        // After the remaining sweeps delta is ~1e-9, so float32 carries it to ~1e-15 of Tc; what needs
-        // double precision is L* alone: two float32 Newton steps on h(L) = L - F(L) from log Tc_first
-        // and ONE double step (quadratic: error ~0.02 e^2) -- one double log and two double divisions
-        // per point instead of nine logs.  Measured against the literal ten sweeps: <= 3e-13 relative
-        // over T 180..330 K, P 10..1080 hPa, qv 1e-8..0.05 (tests/test_thermo_gpu.py); points outside the
-        // series' range (|c delta|, |Tc_first/Tc* - 1| >= 0.1, no convergence, non-finite) take the
-        // literal sweeps, NaN points (terrain) stay NaN.
-        auto finish = [&](double t, double gg) {
-            if (t != t || gg != gg) return mt::nan_f64();
-            const float gf = (float)gg, af = (float)CpRd, lbf = (float)logB;
-            // MUFU-based float32 log / divide (abs. error ~1e-6 on L): the double step squares it
-            float Lf = __logf((float)t);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const float Df = gf - af * Lf;
-                const float hf = Lf - lbf + __logf(Df);
-                Lf = Lf - __fdividef(hf * Df, Df - af);
-            }
-            double L = (double)Lf;
-            double D = gg - CpRd * L;
-            const double h = L - logB + mt::fm::flog(D, &tb);
-            L = L - mt::fm::fdiv(h * D, D - CpRd);
-            D = gg - CpRd * L;
-            const double Tcs = mt::fm::fdiv(B, D);
-            const float c = __fdividef(af, (float)D);
-            const float d = __fdividef((float)(t - Tcs), (float)Tcs);
-            // delta_first = log1p(d)
-            float dl = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
-            const bool ok = fabs(h) < 1e-4 && fabsf(d) < 0.1f && fabsf(c * dl) < 0.1f && D > 0.0;
-            if (!ok || exact) return finish_exact(t, gg);
-            for (int k = 0; k < nrest; ++k) {
-                const float u = c * dl;  // -log1p(-u) = u + u^2/2 + u^3/3 + ...
-                dl = u * fmaf(u, fmaf(u, fmaf(u, fmaf(u, 0.2f, 0.25f), 0.33333334f), 0.5f), 1.0f);
-            }
-            const float e = fmaf(dl * dl, fmaf(dl, 0.16666667f, 0.5f), dl);  // expm1(delta)
-            return Tcs + Tcs * (double)e;
-        };
+        auto finish = [&](double t, double gg) { return tc_finish_point(t, gg, nrest, exact, &tb); };
         const int64_t npair = vec_ok ? (n >> 1) : 0;
         const double2 *__restrict__ g2 = reinterpret_cast<const double2 *>(g);
         double2 *__restrict__ Tc2 = reinterpret_cast<double2 *>(Tc);
@@ -230,6 +238,11 @@ k_tc_finish(const double *__restrict__ g, double *__restrict__ Tc, int64_t n, in
         return;
     }
     cg::grid_group grid = cg::this_grid();
+    if (speculated)   // Tc holds k_td_main's speculative result: put the first iterate back (same
+                      // expression and operands as td_point -> same bits); every thread rewrites
+                      // exactly the elements it sweeps below, so no grid barrier is needed
+        for (int64_t i = tid; i < n; i += nthr)
+            Tc[i] = mt::fm::fdiv(B, g[i] - CpRd * mt::fm::flog(__ldg(T + i), &tb));
     int count = first;  // sweeps executed so far
     if (!(prev_max < 0.1)) {
         for (int it = first; it < 10; ++it) {
@@ -297,7 +310,7 @@ __device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const
 
 __global__ void __launch_bounds__(256)
 k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restrict__ maxbits,
-          double *__restrict__ gbuf)
+          double *__restrict__ gbuf, int exact)
 {
     // one point per thread and iteration: 60 registers / 4 CTAs per SM measured 25 % faster than
     // two points per thread (117 registers) -- profiles/experiments_r01.md
@@ -327,18 +340,31 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
         if (out.rho) __stcs(out.rho + i, r.rho);
         if (out.moist_dTdz) __stcs(out.moist_dTdz + i, r.dTdz);
         if (out.Tc) {
+            // SPECULATION: data on a terrain-masked grid hold NaN, and then the reference is
+            // certain to run all ten calc_Tc sweeps (k_tc_finish).  The result of that branch --
+            // Tc after the nine remaining sweeps and theta_e -- is produced here, while T, p, qv
+            // and Th are in registers; k_tc_finish then has nothing left to do.  Without NaN it
+            // restores the first iterate from g and T and runs the reference's sweeps.
             gbuf[i] = r.g;
-            out.Tc[i] = r.Tc1;
             const unsigned long long b = absbits(r.Tc1 - T);
             m = b > m ? b : m;
+            const double tc = tc_finish_point(r.Tc1, r.g, 9, exact, &tb);
+            out.Tc[i] = tc;
+            if (out.Th_e) __stcs(out.Th_e + i, r.Th * mt::fm::fexp(mt::fm::fdiv((Lv / Cp) * qv, tc), &tb));
         }
     }
     if (out.Tc) block_max_to(m, maxbits);
 }
 
 // sweeps first..9 (+ theta_e): one cooperative launch sized to what is co-resident
+bool tc_exact_mode()   // MT_TC_EXACT=1: the literal sweeps for every point (A/B measurements)
+{
+    static const bool e = getenv("MT_TC_EXACT") && getenv("MT_TC_EXACT")[0] == '1';
+    return e;
+}
+
 int tc_tail(const double *T, const double *g, double *Tc, int64_t n, unsigned long long *bits, int first_iter,
-            const double *Th, const double *qv, double *Th_e, cudaStream_t s)
+            const double *Th, const double *qv, double *Th_e, int speculated, cudaStream_t s)
 {
     const int vec_ok = (((uintptr_t)T | (uintptr_t)g | (uintptr_t)Tc | (uintptr_t)Th | (uintptr_t)qv |
                          (uintptr_t)Th_e) % 16 == 0) ? 1 : 0;
@@ -356,10 +382,9 @@ int tc_tail(const double *T, const double *g, double *Tc, int64_t n, unsigned lo
     int64_t want = ((n + 1) / 2 + 255) / 256;
     int64_t cap = (int64_t)mt::sm_count() * blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
-    static const int exact_env = (getenv("MT_TC_EXACT") && getenv("MT_TC_EXACT")[0] == '1') ? 1 : 0;
-    int exact = exact_env;  // MT_TC_EXACT=1: the literal sweeps for every point (A/B measurements)
+    int exact = tc_exact_mode() ? 1 : 0;
     void *args[] = {(void *)&g, (void *)&Tc, (void *)&n, (void *)&first_iter, (void *)&bits, (void *)&vec_ok,
-                    (void *)&Th, (void *)&qv, (void *)&Th_e, (void *)&exact};
+                    (void *)&Th, (void *)&qv, (void *)&Th_e, (void *)&exact, (void *)&speculated, (void *)&T};
     mt::ProfScope prof("k_tc_finish", (mt_stream_t)s);
     MT_CUDA(cudaLaunchCooperativeKernel((const void *)k_tc_finish, dim3(grid), dim3(256), args, 0, s));
     MT_LAUNCH_CHECK();
@@ -404,7 +429,7 @@ int mt_calc_tc(const double *T, const double *P, const double *qv, double *Tc, i
         k_tc_prepare<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(T, P, qv, g, n);
         MT_LAUNCH_CHECK();
     }
-    return tc_tail(T, g, Tc, n, reinterpret_cast<unsigned long long *>(scratch), 0, nullptr, nullptr, nullptr, s);
+    return tc_tail(T, g, Tc, n, reinterpret_cast<unsigned long long *>(scratch), 0, nullptr, nullptr, nullptr, 0, s);
 }
 
 int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *scratch,
@@ -418,13 +443,14 @@ int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *s
     if (out->Tc) MT_CUDA(cudaMemsetAsync(scratch, 0, 16 * sizeof(double), s));
     {
         mt::ProfScope prof("k_td_main", stream);
-        k_td_main<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits, scratch ? scratch + 16 : nullptr);
+        k_td_main<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits, scratch ? scratch + 16 : nullptr,
+                                                          tc_exact_mode() ? 1 : 0);
         MT_LAUNCH_CHECK();
     }
     if (out->Tc) {
         // Th_e needs Th: taken from the output buffer when requested, else recomputed is not
         // possible here -> Th is required as an output whenever Th_e is
-        int rc = tc_tail(in->T, scratch + 16, out->Tc, n, bits, 1, out->Th, in->qv, out->Th_e, s);
+        int rc = tc_tail(in->T, scratch + 16, out->Tc, n, bits, 1, out->Th, in->qv, out->Th_e, 1, s);
         if (rc != MT_OK) return rc;
     }
     return MT_OK;
