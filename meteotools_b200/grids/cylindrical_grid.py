@@ -15,6 +15,8 @@ array); through the attribute protocol they appear as (Nz, Ntheta, N
 Spline vertical interpolation (``ver_interp_order=2``, :83-93, :123-127) runs FITPACK's
 interpolating spline per column on the device (``mt_spline_levels``, csrc/spline.cu).
 """
+import os
+
 import numpy as np
 
 from .. import _device as D
@@ -183,7 +185,6 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 batch = group[b0:b0 + _lib.MT_MAX_VARS]
                 srcs = [stage(s, use32) for _, s in batch]
                 outs = [self._new() for _ in batch]
-                import os
                 mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
                 fits = trz and nz <= 254 and self.Nz % 2 == 0 and spline_order == 1
                 if fits and mode == "tma" and lib.mt_setdata_tma_supported(dtype, nz, self.Nz, snx):
@@ -282,6 +283,17 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             items = np.array(rows, dtype=np.int32)
             if not spatial:
                 items = items[np.argsort(-items[:, 3], kind='stable')]   # big items first: short tail
+            else:
+                # spatial order, except that the smallest items go last (largest of them first):
+                # the persistent CTAs draw items from a counter, and a tail of small items ends
+                # the kernel evenly on all SMs
+                ntail = min(len(items) // 4, int(os.environ.get("MT_TMA_TAIL", 148)))
+                if ntail > 0:
+                    by_size = np.argsort(items[:, 3], kind='stable')
+                    tail = by_size[:ntail][::-1]
+                    keep = np.ones(len(items), bool)
+                    keep[tail] = False
+                    items = np.concatenate([items[keep], items[tail]])
             order = idx[srt].astype(np.int32)
         else:
             items, order = np.zeros((0, 4), np.int32), np.zeros((1,), np.int32)
