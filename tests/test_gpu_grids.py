@@ -228,15 +228,21 @@ def lib_profile_names(lib, fn):
     return out
 
 
-@pytest.mark.parametrize("case", ["pressure", "nonmonotone_inclusive", "resident_odd", "many_vars"])
+@pytest.mark.parametrize("case", ["pressure", "nonmonotone_inclusive", "resident_odd", "many_vars", "levels72",
+                                  "levels100", "levels_dense", "levels_descending"])
 def test_set_data_tma_against_oracle(case, monkeypatch):
     """mt_setdata_tma on shapes the golden file does not hold: decreasing (pressure) coordinate,
     non-monotone columns + the inclusive bracket test, resident device sources with the cylinder
-    at an odd offset (tiles hanging over the array edge: TMA out-of-bounds fill), 16 variables."""
+    at an odd offset (tiles hanging over the array edge: TMA out-of-bounds fill), 16 variables,
+    72 target levels (the kernel instantiation with 8 level pairs per thread), 100 target levels
+    (more than the TMA kernel takes: the two-kernel path must be chosen), closely spaced levels
+    (several target levels between two model levels: the bracket walk does not move), descending
+    levels on an increasing coordinate (no walk: every bracket takes the binary search)."""
     import torch
     from meteotools_b200.grids import cylindrical_grid
     monkeypatch.setenv("MT_SETDATA", "tma")
-    rng = np.random.default_rng({"pressure": 1, "nonmonotone_inclusive": 2, "resident_odd": 3, "many_vars": 4}[case])
+    rng = np.random.default_rng({"pressure": 1, "nonmonotone_inclusive": 2, "resident_odd": 3, "many_vars": 4,
+                                 "levels72": 5, "levels100": 6, "levels_dense": 7, "levels_descending": 8}[case])
     nz, ny, nx, dx = 14, 70, 84, 2000.0
     settings = dict(Nr=30, Ntheta=40, Nz=12, dr=1100, dtheta=2 * np.pi / 40, dz=450, z_start=150,
                     r_start=0, theta_start=0, vertical_coord_type="z", dt=300)
@@ -249,6 +255,14 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
     if case == "pressure":
         settings.update(vertical_coord_type="p", dz=-5000, z_start=95000)   # 95000, 90000, ... Pa
         vert = 1e5 * np.exp(-z3d / 8000.0)
+    if case == "levels72":
+        settings.update(Nz=72, dz=95, z_start=40)
+    if case == "levels100":
+        settings.update(Nz=100, dz=70, z_start=40)
+    if case == "levels_dense":
+        settings.update(Nz=40, dz=11, z_start=3000)
+    if case == "levels_descending":   # height coordinate, levels from the top down: every bracket is searched
+        settings.update(Nz=12, dz=-450, z_start=5500)
     if case == "nonmonotone_inclusive":
         vert = z3d.copy()
         vert[5, ::3, ::4] -= 900.0
@@ -261,14 +275,26 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
     if case == "resident_odd":
         cyl.set_data(dx, dx, torch.from_numpy(vert).cuda(), inclusive=inclusive,
                      **{k_: torch.from_numpy(v).cuda() for k_, v in kw.items()})
-    elif case == "pressure":
+    elif case in ("pressure", "levels_descending"):
         cyl.set_data(dx, dx, vert, inclusive=inclusive, **kw)
     else:
         cyl.set_data(dx, dx, vert, inclusive=inclusive, hgt=hgt, **kw)
     hidx = None
-    if case not in ("resident_odd", "pressure"):
+    if case not in ("resident_odd", "pressure", "levels_descending"):
         hgt_c = oracle.interp2D_fast(dx, dx, cyl.xTR, cyl.yTR, hgt)
         hidx = co.cyl_terrain_index(hgt_c, cyl.z_start, cyl.dz)
+    if case in ("levels72", "levels100"):
+        import ctypes as ct
+        from meteotools_b200 import _lib
+        lib = _lib.load()
+        lib.mt_profile_enable(1)
+        cyl.set_data(dx, dx, vert, inclusive=inclusive, hgt=hgt, **kw)
+        torch.cuda.synchronize()
+        buf = ct.create_string_buffer(1 << 16)
+        lib.mt_profile_fetch(buf, len(buf))
+        lib.mt_profile_enable(0)
+        names = buf.value.decode()
+        assert ("k_setdata_tma" in names) == (case == "levels72"), names
     for name, a in fields.items():
         levf = oracle.interplevel(a, vert, cyl.z, inclusive=inclusive)
         ref = oracle.interp2D_fast_layers(dx, dx, cyl.xTR, cyl.yTR, levf)
