@@ -156,7 +156,11 @@ __device__ __forceinline__ double dmarch(const Roll &r, int i, int n, bool first
 //                 branches, modest register count);
 // SHELL = true:  one thread per point of the outermost shell (global first / last index of any
 //                 axis), general body with the one-sided formulas; planes are loaded directly.
-template <int LAYOUT, bool CYL, bool SHELL>
+// FULL = true: every stencil output of the set is requested (calc_diagnostics): the output tests are
+//                compile-time true, the body is straight-line code and the compiler can issue all
+//                neighbour loads of a point together (the generic body issues them in small groups
+//                between run-time branches and pays the L2 latency once per group).
+template <int LAYOUT, bool CYL, bool SHELL, bool FULL>
 __global__ void __launch_bounds__(128, SHELL ? 4 : 6)
 k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
 {
@@ -220,14 +224,14 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
         p = (int64_t)i1 * n2 + i2;
     }
 
-    const bool want_zr = o.zeta_r || o.PV;
-    const bool want_zt = o.zeta_t || o.PV;
-    const bool want_zz = o.zeta_z || o.abs_zeta_z || o.PV || o.filamentation_time || o.strain_region;
-    const bool want_def = o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
-    const bool want_div = o.div_hori || o.div;
-    const bool use_ab = want_zr || want_zt || want_zz || want_def || want_div || o.agradient_force;
-    const bool use_w = in.w && (want_zr || want_zt || o.div);
-    const bool use_t = o.PV != nullptr;
+    const bool want_zr = FULL || o.zeta_r || o.PV;
+    const bool want_zt = FULL || o.zeta_t || o.PV;
+    const bool want_zz = FULL || o.zeta_z || o.abs_zeta_z || o.PV || o.filamentation_time || o.strain_region;
+    const bool want_def = FULL || o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
+    const bool want_div = FULL || o.div_hori || o.div;
+    const bool use_ab = FULL || want_zr || want_zt || want_zz || want_def || want_div || o.agradient_force;
+    const bool use_w = FULL || (in.w && (want_zr || want_zt || o.div));
+    const bool use_t = FULL || o.PV != nullptr;
 
     int64_t m = (int64_t)s_lo * plane + p;
     Roll ra = {0, 0, 0}, rb = {0, 0, 0}, rw = {0, 0, 0}, rt = {0, 0, 0};
@@ -297,13 +301,13 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
                 const double dw_dt = dt(in.w, rw);
                 // cyl :387-388  FD2(w,dtheta,1)/r - FD2(vt,dz,0) ; car :250  FD2(w,dy,1) - FD2(v,dz,0)
                 zeta_r = CYL ? dw_dt / rr - db_dz : dw_dt - db_dz;
-                if (o.zeta_r) __stcs(o.zeta_r + m, zeta_r);
+                if (FULL || o.zeta_r) __stcs(o.zeta_r + m, zeta_r);
             }
             if (want_zt) {
                 const double dw_dr = dr(in.w);
                 if (CYL) zeta_t = dz(in.a, ra) - dw_dr;  // :389-390
                 else zeta_t = db_dz - dw_dr;             // cartesian_grid.py:251 (sic: v, not u)
-                if (o.zeta_t) __stcs(o.zeta_t + m, zeta_t);
+                if (FULL || o.zeta_t) __stcs(o.zeta_t + m, zeta_t);
             }
             double da_dr = 0, db_dr = 0;
             if (!CYL && (want_zz || want_def || want_div)) {
@@ -313,20 +317,20 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
             if (want_zz) {
                 if (CYL) zeta_z = dr_times_r(in.b, false) / rr - da_dt / rr;  // :391-392
                 else zeta_z = db_dr - da_dt;                                   // :252 FD2(v,dx,2) - FD2(u,dy,1)
-                if (o.zeta_z) __stcs(o.zeta_z + m, zeta_z);
-                if (o.abs_zeta_z || o.PV) {
+                if (FULL || o.zeta_z) __stcs(o.zeta_z + m, zeta_z);
+                if (FULL || o.abs_zeta_z || o.PV) {
                     abs_zz = zeta_z + __ldg(in.f + (int64_t)it * nr + ir);  // :400
-                    if (o.abs_zeta_z) __stcs(o.abs_zeta_z + m, abs_zz);
+                    if (FULL || o.abs_zeta_z) __stcs(o.abs_zeta_z + m, abs_zz);
                 }
             }
             if (want_div) {
                 double dh;
                 if (CYL) dh = dr_times_r(in.a, true) / rr + db_dt / rr;  // :408-409
                 else dh = da_dr + db_dt;                                  // :266-267
-                if (o.div_hori) __stcs(o.div_hori + m, dh);
-                if (o.div) __stcs(o.div + m, dh + dz(in.w, rw));
+                if (FULL || o.div_hori) __stcs(o.div_hori + m, dh);
+                if (FULL || o.div) __stcs(o.div + m, dh + dz(in.w, rw));
             }
-            if (o.PV) {
+            if (FULL || o.PV) {
                 const double dthr_dr = dr(in.thr);
                 const double dthr_dt = dt(in.thr, rt);
                 const double dthr_dz = dz(in.thr, rt);
@@ -344,20 +348,20 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
                     sh = da_dr - db_dt;   // :344-345 FD2(u,dx) - FD2(v,dy)
                     stc = db_dr + da_dt;  // :346-347 FD2(v,dx) + FD2(u,dy)
                 }
-                if (o.shear_deform) __stcs(o.shear_deform + m, sh);
-                if (o.stretch_deform) __stcs(o.stretch_deform + m, stc);
-                if (o.filamentation_time || o.strain_region) {
+                if (FULL || o.shear_deform) __stcs(o.shear_deform + m, sh);
+                if (FULL || o.stretch_deform) __stcs(o.stretch_deform + m, stc);
+                if (FULL || o.filamentation_time || o.strain_region) {
                     const double s2 = sh * sh + stc * stc, z2 = zeta_z * zeta_z;
                     const bool strain = s2 > z2;  // :504-505
-                    if (o.strain_region) o.strain_region[m] = strain ? 1 : 0;
-                    if (o.filamentation_time)  // :501-508, x**-0.5 as 1/sqrt(x): <= 1 ulp
+                    if ((FULL && CYL) || o.strain_region) o.strain_region[m] = strain ? 1 : 0;
+                    if (FULL || o.filamentation_time)  // :501-508, x**-0.5 as 1/sqrt(x): <= 1 ulp
                         __stcs(o.filamentation_time + m, strain ? 2 * (1.0 / sqrt(s2 - z2)) : inf_f64());
                 }
             }
-            if (CYL && (o.radial_PG_force || o.agradient_force)) {
+            if (CYL && (FULL || o.radial_PG_force || o.agradient_force)) {
                 const double pg = -dr(in.p) / __ldg(in.rho + m);  // :343
-                if (o.radial_PG_force) __stcs(o.radial_PG_force + m, pg);
-                if (o.agradient_force) {
+                if (FULL || o.radial_PG_force) __stcs(o.radial_PG_force + m, pg);
+                if (FULL || o.agradient_force) {
                     const double vt = rb.c;
                     const double cor = __ldg(in.f + (int64_t)it * nr + ir) * vt;  // :341
                     const double cen = vt * vt / rr;                             // :342
@@ -492,17 +496,23 @@ int run_sets(const mt_grid_t *g, const mt_dyn_in_t *in, const StageAOut &a, cons
         const int64_t n_shell = ((g->is_bottom ? 1 : 0) + (g->is_top ? 1 : 0)) * g->nt * g->nr +
                                 2 * (nzin > 0 ? nzin : 0) * (g->nr + g->nt - 2);
         dim3 grids((unsigned)((n_shell + 127) / 128 > 0 ? (n_shell + 127) / 128 : 1));
-        if (ztr) {
-            Lay<MT_LAYOUT_ZTR> lay((int)g->nz, (int)g->nt, (int)g->nr);
-            k_stage_b<MT_LAYOUT_ZTR, CYL, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);
-            MT_LAUNCH_CHECK();
-            k_stage_b<MT_LAYOUT_ZTR, CYL, true><<<grids, 128, 0, s>>>(lay, p, bi, bo, 1);
-        } else {
-            Lay<MT_LAYOUT_TRZ> lay((int)g->nz, (int)g->nt, (int)g->nr);
-            k_stage_b<MT_LAYOUT_TRZ, CYL, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);
-            MT_LAUNCH_CHECK();
-            k_stage_b<MT_LAYOUT_TRZ, CYL, true><<<grids, 128, 0, s>>>(lay, p, bi, bo, 1);
-        }
+        // the whole set requested -> the straight-line instantiation (MT_STAGEB_GENERIC=1: A/B runs)
+        static const bool force_generic = getenv("MT_STAGEB_GENERIC") && getenv("MT_STAGEB_GENERIC")[0] == '1';
+        const bool full = !force_generic && bi.a && bi.b && bi.w && bi.thr && bi.rho && bi.f && bo.zeta_r &&
+                          bo.zeta_t && bo.zeta_z && bo.abs_zeta_z && bo.div_hori && bo.div && bo.PV &&
+                          bo.shear_deform && bo.stretch_deform && bo.filamentation_time &&
+                          (!CYL || (bi.p && bo.radial_PG_force && bo.agradient_force && bo.strain_region));
+#define SB_LAUNCH(LAYOUT_)                                                                         \
+    do {                                                                                           \
+        Lay<LAYOUT_> lay((int)g->nz, (int)g->nt, (int)g->nr);                                      \
+        if (full) k_stage_b<LAYOUT_, CYL, false, true><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len); \
+        else k_stage_b<LAYOUT_, CYL, false, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);  \
+        MT_LAUNCH_CHECK();                                                                         \
+        k_stage_b<LAYOUT_, CYL, true, false><<<grids, 128, 0, s>>>(lay, p, bi, bo, 1);             \
+    } while (0)
+        if (ztr) SB_LAUNCH(MT_LAYOUT_ZTR);
+        else SB_LAUNCH(MT_LAYOUT_TRZ);
+#undef SB_LAUNCH
         MT_LAUNCH_CHECK();
     }
     return MT_OK;
