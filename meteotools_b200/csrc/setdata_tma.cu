@@ -57,7 +57,7 @@ struct __align__(64) TmaParams {
     double *out[MT_MAX_VARS];
 };
 
-struct Meta {   // one staged target (two 16-byte words)
+struct __align__(16) Meta {   // one staged target (two 16-byte words)
     double fx, fy;
     int tgt, terrain;           // target index (output row = tgt * o_n), terrain level index
     uint32_t b01, b23;          // tile-local ids of the four corner columns (rows of `lev`), 16 bits each
@@ -240,6 +240,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     const int c_own = tid % NC, g_own = tid / NC;
     const bool col_thread = tid < NG * NC;
     const int npair = nlev >> 1, ppn = (npair + NG - 1) / NG, lp_own = g_own * ppn;
+    const int o_pitch = (int)o_n;   // output row pitch in elements (host checks that it fits)
     // this thread's brackets (row offsets of the "lo" samples of both levels of a pair, weights)
     int kk[PP];
     double wx[PP], wy[PP];
@@ -366,7 +367,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 const bool two = j + 1 < cnt;
                 const Meta m0 = mt_[j];
                 const Meta m1 = mt_[two ? j + 1 : j];
-                double *o0 = out + (int64_t)m0.tgt * o_n, *o1 = out + (int64_t)m1.tgt * o_n;
+                double *o0 = out + (int64_t)m0.tgt * o_pitch, *o1 = out + (int64_t)m1.tgt * o_pitch;   // 32 x 32 -> 64
                 const bool masked = (m0.terrain | m1.terrain) > 0;                       // warp-uniform
                 const bool same = m0.b01 == m1.b01 && m0.b23 == m1.b23;
                 const char *pa0 = lane_b + (m0.b01 & 0xffffu) * cpitch, *pb0 = lane_b + (m0.b01 >> 16) * cpitch;
@@ -565,7 +566,7 @@ int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int 
                                                  "from column (0,0) of the full coordinate array)");
     const int64_t eb = dtype == MT_F64 ? 8 : 4;
     MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 2 && nlev % 2 == 0 && nlev <= 2 * NG * PP_LARGE && o_n >= nlev &&
-                   o_n % 2 == 0 && n < 2147483647LL,
+                   o_n % 2 == 0 && o_n < 2147483647LL && n < 2147483647LL,
                "mt_setdata_tma: need 2 <= nz <= 254, an even number of levels <= %d and an even output pitch",
                2 * NG * PP_LARGE);
     MT_REQUIRE(row_pitch >= nx && (row_pitch * eb) % 16 == 0 && ((uintptr_t)vert % 16) == 0,

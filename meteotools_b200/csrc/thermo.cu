@@ -308,6 +308,9 @@ __device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const
     return r;
 }
 
+// ALL = true: the whole cyl_td set is requested and qc, qr are present (calc_all_thermaldynamic):
+// the output tests are compile-time true (the kernel is instruction-issue bound).
+template <bool ALL>
 __global__ void __launch_bounds__(256)
 k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restrict__ maxbits,
           double *__restrict__ gbuf, int exact)
@@ -325,24 +328,24 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
         // inputs so that the latency hides behind td_point (ncu: 15 % of the stall samples sat on
         // these two loads when they were issued at their use)
         double ql = 0.0;
-        if (out.Th_v) {
-            if (in.qc && in.qr) ql = __ldg(in.qc + i) + __ldg(in.qr + i);
+        if (ALL || out.Th_v) {
+            if (ALL || (in.qc && in.qr)) ql = __ldg(in.qc + i) + __ldg(in.qr + i);
             else if (in.qc) ql = __ldg(in.qc + i);
             else if (in.qr) ql = __ldg(in.qr + i);
         }
         const TdPoint r = td_point(T, P, qv, &tb);
-        if (out.Th) __stcs(out.Th + i, r.Th);
-        if (out.vapor_s) __stcs(out.vapor_s + i, r.es);
-        if (out.qvs) __stcs(out.qvs + i, r.qvs);
-        if (out.vapor) __stcs(out.vapor + i, r.vap);
-        if (out.RH) __stcs(out.RH + i, r.RH);
-        if (out.Td) __stcs(out.Td + i, r.Td);
-        if (out.Th_es) __stcs(out.Th_es + i, r.Th_es);
-        if (out.Th_v) __stcs(out.Th_v + i, theta_v(r.Th, qv, ql));
-        if (out.Tv) __stcs(out.Tv + i, r.Tv);
-        if (out.rho) __stcs(out.rho + i, r.rho);
-        if (out.moist_dTdz) __stcs(out.moist_dTdz + i, r.dTdz);
-        if (out.Tc) {
+        if (ALL || out.Th) __stcs(out.Th + i, r.Th);
+        if (ALL || out.vapor_s) __stcs(out.vapor_s + i, r.es);
+        if (ALL || out.qvs) __stcs(out.qvs + i, r.qvs);
+        if (ALL || out.vapor) __stcs(out.vapor + i, r.vap);
+        if (ALL || out.RH) __stcs(out.RH + i, r.RH);
+        if (ALL || out.Td) __stcs(out.Td + i, r.Td);
+        if (ALL || out.Th_es) __stcs(out.Th_es + i, r.Th_es);
+        if (ALL || out.Th_v) __stcs(out.Th_v + i, theta_v(r.Th, qv, ql));
+        if (ALL || out.Tv) __stcs(out.Tv + i, r.Tv);
+        if (ALL || out.rho) __stcs(out.rho + i, r.rho);
+        if (ALL || out.moist_dTdz) __stcs(out.moist_dTdz + i, r.dTdz);
+        if (ALL || out.Tc) {
             // SPECULATION: data on a terrain-masked grid hold NaN, and then the reference is
             // certain to run all ten calc_Tc sweeps (k_tc_finish).  The result of that branch --
             // Tc after the nine remaining sweeps and theta_e -- is produced here, while T, p, qv
@@ -353,10 +356,10 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
             m = b > m ? b : m;
             const double tc = tc_finish_point(r.Tc1, r.g, 9, exact, &tb);
             out.Tc[i] = tc;
-            if (out.Th_e) __stcs(out.Th_e + i, r.Th * mt::fm::fexp(mt::fm::fdiv((Lv / Cp) * qv, tc), &tb));
+            if (ALL || out.Th_e) __stcs(out.Th_e + i, r.Th * mt::fm::fexp(mt::fm::fdiv((Lv / Cp) * qv, tc), &tb));
         }
     }
-    if (out.Tc) block_max_to(m, maxbits);
+    if (ALL || out.Tc) block_max_to(m, maxbits);
 }
 
 // sweeps first..9 (+ theta_e): one cooperative launch sized to what is co-resident
@@ -446,8 +449,16 @@ int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *s
     if (out->Tc) MT_CUDA(cudaMemsetAsync(scratch, 0, 16 * sizeof(double), s));
     {
         mt::ProfScope prof("k_td_main", stream);
-        k_td_main<<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits, scratch ? scratch + 16 : nullptr,
-                                                          tc_exact_mode() ? 1 : 0);
+        const bool all = in->qc && in->qr && out->Th && out->vapor_s && out->qvs && out->vapor && out->RH &&
+                         out->Td && out->Th_es && out->Th_v && out->Tv && out->rho && out->moist_dTdz && out->Tc &&
+                         out->Th_e;
+        if (all)
+            k_td_main<true><<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits, scratch + 16,
+                                                                    tc_exact_mode() ? 1 : 0);
+        else
+            k_td_main<false><<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits,
+                                                                     scratch ? scratch + 16 : nullptr,
+                                                                     tc_exact_mode() ? 1 : 0);
         MT_LAUNCH_CHECK();
     }
     if (out->Tc) {
