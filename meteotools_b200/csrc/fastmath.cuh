@@ -24,6 +24,18 @@ struct Tables {
     double ex[64];     // 2^(j/64)
 };
 
+// 64-bit constants that are not encodable as an immediate (non-zero low word) cost two UMOVs per
+// use on sm_100a -- a quarter of the fused cyl_td kernel's instructions were such moves (SASS of
+// k_td_main).  Read from constant memory they are one LDC.64 / half an LDCU.128 each, and the
+// compiler may keep them in uniform registers across the loop.
+struct Consts {
+    double m16, p02, p13, ln2;                       // log1p series -1/6, 1/5, 1/3; ln 2
+    double r64ln2, ln2_64_hi, ln2_64_lo;             // 64/ln2, ln2/64 split (Cody-Waite)
+    double e120, e24, e6;                            // expm1 series 1/120, 1/24, 1/6
+};
+static __constant__ Consts kc = {-1.0 / 6,       0.2,  1.0 / 3, MT_FM_LN2, MT_FM_64_LN2, MT_FM_LN2_64_HI,
+                                 MT_FM_LN2_64_LO, 1.0 / 120, 1.0 / 24, 1.0 / 6};
+
 static __device__ const double2 g_log_table[128] = {MT_FM_LOG_TABLE};
 static __device__ const double g_exp_table[64] = {MT_FM_EXP_TABLE};
 
@@ -51,25 +63,25 @@ __device__ __forceinline__ double flog(double x0, const Tables *t)
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double e = (double)((hi >> 20) - 1023);
     const double u = fma(m, rt.x, -1.0);
-    double q = fma(u, -1.0 / 6, 0.2);
+    double q = fma(u, kc.m16, kc.p02);
     q = fma(u, q, -0.25);
-    q = fma(u, q, 1.0 / 3);
+    q = fma(u, q, kc.p13);
     q = fma(u, q, -0.5);
-    double res = fma(e, MT_FM_LN2, rt.y) + fma(u * u, q, u);
+    double res = fma(e, kc.ln2, rt.y) + fma(u * u, q, u);
     if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) res = slow_log(x);   // rare: <= 0, denormal, +inf
     return isn ? x0 : res;
 }
 
 __device__ __forceinline__ double fexp(double x, const Tables *t)
 {
-    const double kd0 = fma(x, MT_FM_64_LN2, 6755399441055744.0);   // 1.5 * 2^52: rint in the low word
+    const double kd0 = fma(x, kc.r64ln2, 6755399441055744.0);   // 1.5 * 2^52: rint in the low word
     const int k = __double2loint(kd0);
     const double kd = kd0 - 6755399441055744.0;
-    double r = fma(-kd, MT_FM_LN2_64_HI, x);
-    r = fma(-kd, MT_FM_LN2_64_LO, r);
+    double r = fma(-kd, kc.ln2_64_hi, x);
+    r = fma(-kd, kc.ln2_64_lo, r);
     const double ej = t->ex[k & 63];
-    double p = fma(r, 1.0 / 120, 1.0 / 24);
-    p = fma(r, p, 1.0 / 6);
+    double p = fma(r, kc.e120, kc.e24);
+    p = fma(r, p, kc.e6);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
     double res = fma(ej, p * r, ej);

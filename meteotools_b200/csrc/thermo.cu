@@ -128,6 +128,19 @@ k_tc_iter(const double *__restrict__ T, const double *__restrict__ g, double *__
     block_max_to(m, maxbits + iter);
 }
 
+// constants of td_point / tc_finish_point with a non-zero low word, in constant memory (see
+// fastmath.cuh: an immediate costs two UMOVs per use)
+struct TdConsts {
+    double log_1e5, log_A622, log_611_2, kappa, t0, c1767, c6112, eps, LvCp, LvRd, Lv622, g, CpRd, logB, tol_h,
+        c061;
+};
+static __constant__ TdConsts ktd = {11.512925464970229,   // log(100000)
+                                    25.781840139430972,   // log(2.53e11*0.622)
+                                    6.415424237852311,    // log(611.2)
+                                    kappa, 273.15, 17.67, 611.2, 0.622, Lv / Cp, Lv / Rd, Lv * 0.622, g, CpRd,
+                                    8.597851094433691,    // log(5420)
+                                    1e-4, 0.61};
+
 // The remaining `nrest` CERTAIN sweeps of calc_Tc for one point (t = the iterate after sweep
 // `10 - nrest`, gg = the sweep-invariant g), used when the reference is known to run all ten sweeps
 // (some point is NaN, see k_tc_finish).
@@ -156,16 +169,16 @@ __device__ __forceinline__ double tc_finish_point(double t, double gg, int nrest
         Lf = Lf - __fdividef(hf * Df, Df - af);
     }
     double L = (double)Lf;
-    double D = gg - CpRd * L;
-    const double h = L - logB + mt::fm::flog(D, tb);
-    L = L - mt::fm::fdiv(h * D, D - CpRd);
-    D = gg - CpRd * L;
+    double D = gg - ktd.CpRd * L;
+    const double h = L - ktd.logB + mt::fm::flog(D, tb);
+    L = L - mt::fm::fdiv(h * D, D - ktd.CpRd);
+    D = gg - ktd.CpRd * L;
     const double Tcs = mt::fm::fdiv(B, D);
     const float c = __fdividef(af, (float)D);
     const float d = __fdividef((float)(t - Tcs), (float)Tcs);
     // delta_first = log1p(d)
     float dl = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
-    const bool ok = fabs(h) < 1e-4 && fabsf(d) < 0.1f && fabsf(c * dl) < 0.1f && D > 0.0;
+    const bool ok = fabs(h) < ktd.tol_h && fabsf(d) < 0.1f && fabsf(c * dl) < 0.1f && D > 0.0;
     if (!ok || exact) {   // the literal sweeps
         double Lx = log(t), Dx = gg - CpRd * Lx;
         for (int it = 1; it < nrest; ++it) {
@@ -283,28 +296,25 @@ __device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const
 {
     using mt::fm::fexp;
     using mt::fm::flog;
-    constexpr double log_1e5 = 11.512925464970229;       // log(100000)
-    constexpr double log_A622 = 25.781840139430972;      // log(2.53e11*0.622)
-    constexpr double log_611_2 = 6.415424237852311;      // log(611.2)
     TdPoint r;
     using mt::fm::fdiv;
     const double lP = flog(P, tb), lT = flog(T, tb), lq = flog(qv, tb);
-    r.Th = T * fexp(kappa * (log_1e5 - lP), tb);
-    const double Tc_ = T - 273.15;
-    r.es = 611.2 * fexp(fdiv(17.67 * Tc_, Tc_ + 243.5), tb);   // :116
-    r.qvs = fdiv(0.622 * r.es, P - r.es);                      // :151
+    r.Th = T * fexp(ktd.kappa * (ktd.log_1e5 - lP), tb);
+    const double Tc_ = T - ktd.t0;
+    r.es = ktd.c6112 * fexp(fdiv(ktd.c1767 * Tc_, Tc_ + 243.5), tb);   // :116
+    r.qvs = fdiv(ktd.eps * r.es, P - r.es);                    // :151
     r.vap = qv_to_vapor(P, qv);                           // exact class, :168
     r.RH = fdiv(r.vap, r.es);
-    const double lnes = flog(r.vap, tb) - log_611_2;
-    r.Td = fdiv(243.5 * lnes, 17.67 - lnes) + 273.15;
+    const double lnes = flog(r.vap, tb) - ktd.log_611_2;
+    r.Td = fdiv(243.5 * lnes, ktd.c1767 - lnes) + ktd.t0;
     const double rT = fdiv(1.0, T);                       // shared by the three tolerance-class quotients
-    r.Th_es = r.Th * fexp((Lv / Cp) * r.qvs * rT, tb);   // Lv*qvs/Cp/T
+    r.Th_es = r.Th * fexp(ktd.LvCp * r.qvs * rT, tb);    // Lv*qvs/Cp/T
     r.Tv = Tv_from_qv(T, qv);                             // exact class, :335
     r.rho = rho(P, r.Tv);                                 // exact class, :364
-    const double a = (Lv / Rd) * r.qvs * rT;              // Lv*qvs/Rd/T
-    r.dTdz = -g * fdiv(1 + a, Cp + a * (Lv * 0.622) * rT);  // :486
-    r.g = log_A622 - lP - lq + CpRd * lT;
-    r.Tc1 = fdiv(B, r.g - CpRd * lT);                     // first sweep: Tc2 = T
+    const double a = ktd.LvRd * r.qvs * rT;               // Lv*qvs/Rd/T
+    r.dTdz = -ktd.g * fdiv(1 + a, Cp + a * ktd.Lv622 * rT);  // :486
+    r.g = ktd.log_A622 - lP - lq + ktd.CpRd * lT;
+    r.Tc1 = fdiv(B, r.g - ktd.CpRd * lT);                 // first sweep: Tc2 = T
     return r;
 }
 
@@ -341,7 +351,7 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
         if (ALL || out.RH) __stcs(out.RH + i, r.RH);
         if (ALL || out.Td) __stcs(out.Td + i, r.Td);
         if (ALL || out.Th_es) __stcs(out.Th_es + i, r.Th_es);
-        if (ALL || out.Th_v) __stcs(out.Th_v + i, theta_v(r.Th, qv, ql));
+        if (ALL || out.Th_v) __stcs(out.Th_v + i, r.Th * (1 + qv * ktd.c061 - ql));   // theta_v, :309
         if (ALL || out.Tv) __stcs(out.Tv + i, r.Tv);
         if (ALL || out.rho) __stcs(out.rho + i, r.rho);
         if (ALL || out.moist_dTdz) __stcs(out.moist_dTdz + i, r.dTdz);
@@ -356,7 +366,7 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
             m = b > m ? b : m;
             const double tc = tc_finish_point(r.Tc1, r.g, 9, exact, &tb);
             out.Tc[i] = tc;
-            if (ALL || out.Th_e) __stcs(out.Th_e + i, r.Th * mt::fm::fexp(mt::fm::fdiv((Lv / Cp) * qv, tc), &tb));
+            if (ALL || out.Th_e) __stcs(out.Th_e + i, r.Th * mt::fm::fexp(mt::fm::fdiv(ktd.LvCp * qv, tc), &tb));
         }
     }
     if (ALL || out.Tc) block_max_to(m, maxbits);
