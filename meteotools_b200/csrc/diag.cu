@@ -121,6 +121,10 @@ k_stage_a(Lay<LAYOUT> L, GridP g, mt_dyn_in_t in, mt::th::Hydro hyd, StageAOut o
 }
 
 // ------------------------------------------------------------------------------- stage B
+#ifndef MT_STAGEB_MINB
+#define MT_STAGEB_MINB 8   // resident CTAs per SM the interior kernel is compiled for: 64 registers (a few
+                           // spilled words) beat 80 registers at 6 CTAs -- the kernel is load-latency bound
+#endif
 struct StageBIn {
     const double *a, *b, *w, *thr, *p, *rho, *f;  // cyl: a=vr, b=vt ; car: a=u, b=v
 };
@@ -161,7 +165,7 @@ __device__ __forceinline__ double dmarch(const Roll &r, int i, int n, bool first
 //                neighbour loads of a point together (the generic body issues them in small groups
 //                between run-time branches and pays the L2 latency once per group).
 template <int LAYOUT, bool CYL, bool SHELL, bool FULL>
-__global__ void __launch_bounds__(128, SHELL ? 4 : 6)
+__global__ void __launch_bounds__(128, SHELL ? 4 : MT_STAGEB_MINB)
 k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
 {
     constexpr bool ZTR = LAYOUT == MT_LAYOUT_ZTR;
