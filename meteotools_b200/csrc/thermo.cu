@@ -320,8 +320,11 @@ __device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const
 
 // ALL = true: the whole cyl_td set is requested and qc, qr are present (calc_all_thermaldynamic):
 // the output tests are compile-time true (the kernel is instruction-issue bound).
+#ifndef MT_TD_MINB
+#define MT_TD_MINB 4
+#endif
 template <bool ALL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MT_TD_MINB)
 k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restrict__ maxbits,
           double *__restrict__ gbuf, int exact)
 {
@@ -462,13 +465,18 @@ int mt_cyl_td(const mt_td_in_t *in, const mt_td_out_t *out, int64_t n, double *s
         const bool all = in->qc && in->qr && out->Th && out->vapor_s && out->qvs && out->vapor && out->RH &&
                          out->Td && out->Th_es && out->Th_v && out->Tv && out->rho && out->moist_dTdz && out->Tc &&
                          out->Th_e;
+        // two waves of what is resident (grid-stride loop inside)
+        static thread_local int occ = 0;
+        if (occ == 0) {
+            MT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_td_main<true>, 256, 0));
+            if (occ < 1) occ = 1;
+        }
+        const unsigned grid = mt::grid_for(n, 256, 2 * occ);
         if (all)
-            k_td_main<true><<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits, scratch + 16,
-                                                                    tc_exact_mode() ? 1 : 0);
+            k_td_main<true><<<grid, 256, 0, s>>>(*in, *out, n, bits, scratch + 16, tc_exact_mode() ? 1 : 0);
         else
-            k_td_main<false><<<mt::grid_for(n, 256, 8), 256, 0, s>>>(*in, *out, n, bits,
-                                                                     scratch ? scratch + 16 : nullptr,
-                                                                     tc_exact_mode() ? 1 : 0);
+            k_td_main<false><<<grid, 256, 0, s>>>(*in, *out, n, bits, scratch ? scratch + 16 : nullptr,
+                                                  tc_exact_mode() ? 1 : 0);
         MT_LAUNCH_CHECK();
     }
     if (out->Tc) {
