@@ -392,7 +392,8 @@ def main():
     assert all(res[k].shape == (CYL["Nz"], CYL["Ntheta"], CYL["Nr"]) for k in td_names)
     del res
     from meteotools_b200.pipeline import TimeStepStream
-    ts = TimeStepStream(cyl, (NZ, NY, NX), DX, DX, NAMES3D, names2d=("f",), hgt=True, outputs=td_names)
+    ts = TimeStepStream(cyl, (NZ, NY, NX), DX, DX, NAMES3D, names2d=("f",), hgt=True, outputs=td_names,
+                        slots=int(os.environ.get("MT_E2E_SLOTS", 3)))
     n_stream = max(4 * args.e2e_steps, 8)
     for _ in ts.process([step] * 3):
         pass
@@ -444,7 +445,8 @@ def main():
             "e2e": {"value": world * NPTS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": n_stream,
                     "path": "pipeline.TimeStepStream.process (pinned host arrays in -> pinned host arrays out, "
-                            "two slots: D2H of step k overlaps H2D of step k+1)",
+                            "three slots: D2H of step k overlaps H2D of step k+1; the link alone takes 13.9 ms for these bytes, "
+                            "scratch/pcie_probe.py)",
                     "single_step": {"value": world * NPTS / e2e_single_s, "ms_per_step": e2e_single_s * 1e3,
                                     "path": "cylindrical_grid.set_data + calc_all_thermaldynamic + to_host, "
                                             "one step at a time"},

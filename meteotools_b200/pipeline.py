@@ -317,7 +317,7 @@ def dyn_level_sharded(kind, local, f2d, spacings, shard, nz_global, outputs, ran
 
 class TimeStepStream:
     """Process a sequence of WRF time steps end to end (host arrays in, host arrays out) with the
-    PCIe traffic of consecutive steps overlapped: two ``CylStepPipeline`` slots, each on its own
+    PCIe traffic of consecutive steps overlapped: ``slots`` ``CylStepPipeline`` slots, each on its own
     CUDA stream; while step k's results travel device->host, step k+1's source boxes already
     travel host->device (PCIe is full duplex) and its kernels run.  Results are identical to
     calling ``cylindrical_grid.set_data`` + ``calc_all_thermaldynamic`` per step.
@@ -328,7 +328,7 @@ class TimeStepStream:
     """
 
     def __init__(self, grid, src_shape, dx, dy, names3d, names2d=("f",), hgt=True, outputs=None,
-                 dtype=np.float64, dyn_outputs=None, slots=2):
+                 dtype=np.float64, dyn_outputs=None, slots=3):
         t = D.require_cuda()
         self.t = t
         self.outputs = list(outputs) if outputs is not None else list(_lib.TD_OUT)
