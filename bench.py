@@ -276,6 +276,27 @@ def emit(obj):
     out.flush()
 
 
+def bind_near_gpu(local_rank):
+    """Multi-rank runs: keep this rank's threads (and so the first-touch placement of its pinned host
+    buffers) on the CPUs that NVML reports as local to its GPU.  On a multi-socket box the e2e leg
+    otherwise crosses the socket interconnect for half the ranks.  Best effort: silently skipped when
+    NVML or the affinity call is not available or the container restricts the CPU set."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -300,6 +321,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    near = bind_near_gpu(local) if world > 1 and os.environ.get("MT_BENCH_NO_BIND") != "1" else 0
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -441,7 +463,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(),
-            "clocks": clk, "gpu_launches": int(launches), "steps_in_flight": nslots,
+            "clocks": clk, "gpu_launches": int(launches), "steps_in_flight": nslots, "cpus_bound_near_gpu": near,
             "e2e": {"value": world * NPTS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": n_stream,
                     "path": "pipeline.TimeStepStream.process (pinned host arrays in -> pinned host arrays out, "
