@@ -50,7 +50,13 @@ __device__ __forceinline__ void load_tables(Tables *s)
 static __device__ __noinline__ double slow_log(double x) { return log(x); }
 static __device__ __noinline__ double slow_exp(double x) { return exp(x); }
 
-__device__ __forceinline__ double flog(double x0, const Tables *t)
+// Two forms of each function.  The plain form handles its rare arguments itself (a branch to
+// CUDA's function / the IEEE division).  The `_f` form never branches: it ORs "this argument needs
+// the slow path" into `bad` and returns the fast-path value; a caller that evaluates a whole chain
+// of them (the fused cyl_td pass: ~24 calls per point) tests `bad` ONCE and redoes the point with
+// the plain forms -- one branch per point instead of one branch region per call.
+template <bool FLAG>
+__device__ __forceinline__ double flog_t(double x0, const Tables *t, bool &bad)
 {
     // NaN lanes (terrain) compute on 1.0 and get their NaN back at the end.  Without this the
     // compiler folds "x < DBL_MIN || x == inf" and the final NaN select into ONE integer range test
@@ -68,11 +74,14 @@ __device__ __forceinline__ double flog(double x0, const Tables *t)
     q = fma(u, q, kc.p13);
     q = fma(u, q, -0.5);
     double res = fma(e, kc.ln2, rt.y) + fma(u * u, q, u);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) res = slow_log(x);   // rare: <= 0, denormal, +inf
+    const bool rare = (unsigned)(hi - 0x00100000) >= 0x7fe00000u;   // <= 0, denormal, +inf
+    if (FLAG) bad = bad || rare;
+    else if (rare) res = slow_log(x);
     return isn ? x0 : res;
 }
 
-__device__ __forceinline__ double fexp(double x, const Tables *t)
+template <bool FLAG>
+__device__ __forceinline__ double fexp_t(double x, const Tables *t, bool &bad)
 {
     const double kd0 = fma(x, kc.r64ln2, 6755399441055744.0);   // 1.5 * 2^52: rint in the low word
     const int k = __double2loint(kd0);
@@ -86,7 +95,9 @@ __device__ __forceinline__ double fexp(double x, const Tables *t)
     p = fma(r, p, 1.0);
     double res = fma(ej, p * r, ej);
     res = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
-    if (fabs(x) >= 690.0) res = slow_exp(x);                       // rare: overflow / underflow range
+    const bool rare = fabs(x) >= 690.0;                            // overflow / underflow range
+    if (FLAG) bad = bad || rare;
+    else if (rare) res = slow_exp(x);
     return (x != x) ? x : res;
 }
 
@@ -95,7 +106,8 @@ __device__ __forceinline__ double fexp(double x, const Tables *t)
 // zero, denormal, huge or infinite take the IEEE division on a rarely taken branch; NaN propagates.
 static __device__ __noinline__ double slow_div(double a, double b) { return a / b; }
 
-__device__ __forceinline__ double fdiv(double a, double b)
+template <bool FLAG>
+__device__ __forceinline__ double fdiv_t(double a, double b, bool &bad)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
@@ -107,8 +119,26 @@ __device__ __forceinline__ double fdiv(double a, double b)
     // |b| outside [2^-1000, 2^992) incl. 0 and inf -- but not (quiet) NaN, which flows through the
     // fast path as NaN: terrain-masked lanes must not drag their warp into the slow path
     const unsigned hb = (unsigned)__double2hiint(b) & 0x7fffffffu;
-    if (hb - 0x01700000u >= 0x7c800000u && hb <= 0x7ff00000u) res = slow_div(a, b);
+    const bool rare = hb - 0x01700000u >= 0x7c800000u && hb <= 0x7ff00000u;
+    if (FLAG) bad = bad || rare;
+    else if (rare) res = slow_div(a, b);
     return res;
+}
+
+__device__ __forceinline__ double flog(double x, const Tables *t)
+{
+    bool b = false;
+    return flog_t<false>(x, t, b);
+}
+__device__ __forceinline__ double fexp(double x, const Tables *t)
+{
+    bool b = false;
+    return fexp_t<false>(x, t, b);
+}
+__device__ __forceinline__ double fdiv(double a, double b)
+{
+    bool f = false;
+    return fdiv_t<false>(a, b, f);
 }
 
 }  // namespace fm

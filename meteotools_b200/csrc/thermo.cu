@@ -154,8 +154,9 @@ static __constant__ TdConsts ktd = {11.512925464970229,   // log(100000)
 // over T 180..330 K, P 10..1080 hPa, qv 1e-8..0.05 (tests/test_gpu_calc.py); points outside the
 // series' range (|c delta|, |Tc_first/Tc* - 1| >= 0.1, no convergence, non-finite) take the
 // literal sweeps, NaN points (terrain) stay NaN.
-__device__ __forceinline__ double tc_finish_point(double t, double gg, int nrest, int exact,
-                                                  const mt::fm::Tables *tb)
+template <bool FLAG>
+__device__ __forceinline__ double tc_finish_point_t(double t, double gg, int nrest, int exact,
+                                                    const mt::fm::Tables *tb, bool &bad)
 {
     constexpr double logB = 8.597851094433691;  // log(5420)
     if (t != t || gg != gg) return mt::nan_f64();
@@ -170,16 +171,18 @@ __device__ __forceinline__ double tc_finish_point(double t, double gg, int nrest
     }
     double L = (double)Lf;
     double D = gg - ktd.CpRd * L;
-    const double h = L - ktd.logB + mt::fm::flog(D, tb);
-    L = L - mt::fm::fdiv(h * D, D - ktd.CpRd);
+    const double h = L - ktd.logB + mt::fm::flog_t<FLAG>(D, tb, bad);
+    L = L - mt::fm::fdiv_t<FLAG>(h * D, D - ktd.CpRd, bad);
     D = gg - ktd.CpRd * L;
-    const double Tcs = mt::fm::fdiv(B, D);
+    const double Tcs = mt::fm::fdiv_t<FLAG>(B, D, bad);
     const float c = __fdividef(af, (float)D);
     const float d = __fdividef((float)(t - Tcs), (float)Tcs);
     // delta_first = log1p(d)
     float dl = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
     const bool ok = fabs(h) < ktd.tol_h && fabsf(d) < 0.1f && fabsf(c * dl) < 0.1f && D > 0.0;
-    if (!ok || exact) {   // the literal sweeps
+    if (FLAG) {   // the caller redoes the point with the plain form, which runs the literal sweeps
+        bad = bad || !ok || exact;
+    } else if (!ok || exact) {   // the literal sweeps
         double Lx = log(t), Dx = gg - CpRd * Lx;
         for (int it = 1; it < nrest; ++it) {
             Lx = logB - log(Dx);
@@ -193,6 +196,13 @@ __device__ __forceinline__ double tc_finish_point(double t, double gg, int nrest
     }
     const float e = fmaf(dl * dl, fmaf(dl, 0.16666667f, 0.5f), dl);  // expm1(delta)
     return Tcs + Tcs * (double)e;
+}
+
+__device__ __forceinline__ double tc_finish_point(double t, double gg, int nrest, int exact,
+                                                  const mt::fm::Tables *tb)
+{
+    bool b = false;
+    return tc_finish_point_t<false>(t, gg, nrest, exact, tb, b);
 }
 
 // Everything after the first sweep in ONE cooperative launch (replaces nine per-sweep launches,
@@ -292,12 +302,13 @@ struct TdPoint {
     double Th, es, qvs, vap, RH, Td, Th_es, Tv, rho, dTdz, g, Tc1;
 };
 
-__device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const mt::fm::Tables *tb)
+template <bool FLAG>
+__device__ __forceinline__ TdPoint td_point(double T, double P, double qv, const mt::fm::Tables *tb, bool &bad)
 {
-    using mt::fm::fexp;
-    using mt::fm::flog;
+    auto flog = [&](double x, const mt::fm::Tables *t) { return mt::fm::flog_t<FLAG>(x, t, bad); };
+    auto fexp = [&](double x, const mt::fm::Tables *t) { return mt::fm::fexp_t<FLAG>(x, t, bad); };
+    auto fdiv = [&](double a, double b) { return mt::fm::fdiv_t<FLAG>(a, b, bad); };
     TdPoint r;
-    using mt::fm::fdiv;
     const double lP = flog(P, tb), lT = flog(T, tb), lq = flog(qv, tb);
     r.Th = T * fexp(ktd.kappa * (ktd.log_1e5 - lP), tb);
     const double Tc_ = T - ktd.t0;
@@ -346,7 +357,24 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
             else if (in.qc) ql = __ldg(in.qc + i);
             else if (in.qr) ql = __ldg(in.qr + i);
         }
-        const TdPoint r = td_point(T, P, qv, &tb);
+        // fast path without a single branch: every rare-argument test of the ~24 log / exp /
+        // divide calls is OR-ed into `bad`; a point that needs a slow path (never, for physical
+        // input) is redone with the plain forms, which gives what the branchy calls gave
+        bool bad = false;
+        TdPoint r = td_point<true>(T, P, qv, &tb, bad);
+        double tc = 0.0, the = 0.0;
+        if (ALL || out.Tc) {
+            tc = tc_finish_point_t<true>(r.Tc1, r.g, 9, exact, &tb, bad);
+            if (ALL || out.Th_e) the = r.Th * mt::fm::fexp_t<true>(mt::fm::fdiv_t<true>(ktd.LvCp * qv, tc, bad), &tb, bad);
+        }
+        if (bad) {   // the same point through the plain (self-guarding) forms
+            bool unused = false;
+            r = td_point<false>(T, P, qv, &tb, unused);
+            if (ALL || out.Tc) {
+                tc = tc_finish_point(r.Tc1, r.g, 9, exact, &tb);
+                if (ALL || out.Th_e) the = r.Th * mt::fm::fexp(mt::fm::fdiv(ktd.LvCp * qv, tc), &tb);
+            }
+        }
         if (ALL || out.Th) __stcs(out.Th + i, r.Th);
         if (ALL || out.vapor_s) __stcs(out.vapor_s + i, r.es);
         if (ALL || out.qvs) __stcs(out.qvs + i, r.qvs);
@@ -367,9 +395,8 @@ k_td_main(mt_td_in_t in, mt_td_out_t out, int64_t n, unsigned long long *__restr
             gbuf[i] = r.g;
             const unsigned long long b = absbits(r.Tc1 - T);
             m = b > m ? b : m;
-            const double tc = tc_finish_point(r.Tc1, r.g, 9, exact, &tb);
             out.Tc[i] = tc;
-            if (ALL || out.Th_e) __stcs(out.Th_e + i, r.Th * mt::fm::fexp(mt::fm::fdiv(ktd.LvCp * qv, tc), &tb));
+            if (ALL || out.Th_e) __stcs(out.Th_e + i, the);
         }
     }
     if (ALL || out.Tc) block_max_to(m, maxbits);
