@@ -101,7 +101,9 @@ __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"
 
 // PP = level pairs per column thread (>= ceil(nlev / 2 / NG)): the brackets of a thread's own
 // (column, level pair) set live in registers for all variables of the item.
-template <typename T, bool INCLUSIVE, bool ROUND, int PP>
+// EXACT: nlev == 2 * NG * PP, every thread owns exactly PP level pairs (no guards in the column
+// phases; with PP = 5 the 60 levels are one step of the 30-lane level loop of phase C).
+template <typename T, bool INCLUSIVE, bool ROUND, int PP, bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, int LP, int stages,
               int stage_bytes, int org_x, int org_y, const double *__restrict__ levels, int decreasing,
@@ -239,7 +241,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     // consecutive level pairs from (tid / 80) * ppn
     const int c_own = tid % NC, g_own = tid / NC;
     const bool col_thread = tid < NG * NC;
-    const int npair = nlev >> 1, ppn = (npair + NG - 1) / NG, lp_own = g_own * ppn;
+    const int npair = nlev >> 1, ppn = EXACT ? PP : (npair + NG - 1) / NG, lp_own = g_own * ppn;
     const int o_pitch = (int)o_n;   // output row pitch in elements (host checks that it fits)
     // this thread's brackets (row offsets of the "lo" samples of both levels of a pair, weights)
     int kk[PP];
@@ -318,7 +320,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 const int lp = lp_own + i;
                 int k0 = klo_missing, k1 = klo_missing;
                 wx[i] = wy[i] = nan_f64();
-                if (i < ppn && lp < npair) {
+                if (EXACT || (i < ppn && lp < npair)) {
                     bracket(lev_s[2 * lp], k0, wx[i]);
                     bracket(lev_s[2 * lp + 1], k1, wy[i]);
                 }
@@ -342,7 +344,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
 #pragma unroll
                 for (int i = 0; i < PP; ++i) {
                     const int lp = lp_own + i;
-                    if (i < ppn && lp < npair) {
+                    if (EXACT || (i < ppn && lp < npair)) {
                         const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;
                         const double f00 = (double)fc[ka], f01 = (double)fc[ka + dhi];
                         const double f10 = (double)fc[kb], f11 = (double)fc[kb + dhi];
@@ -374,6 +376,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 const char *pc0 = lane_b + (m0.b23 & 0xffffu) * cpitch, *pd0 = lane_b + (m0.b23 >> 16) * cpitch;
                 const char *pa1 = lane_b + (m1.b01 & 0xffffu) * cpitch, *pb1 = lane_b + (m1.b01 >> 16) * cpitch;
                 const char *pc1 = lane_b + (m1.b23 & 0xffffu) * cpitch, *pd1 = lane_b + (m1.b23 >> 16) * cpitch;
+                constexpr bool ONE_STEP = EXACT && 2 * NG * PP <= 64;
                 for (int l = lane * 2, lo8 = 0; l < nlev; l += 64, lo8 += 512) {
                     const double2 a0 = *reinterpret_cast<const double2 *>(pa0 + lo8);
                     const double2 b0 = *reinterpret_cast<const double2 *>(pb0 + lo8);
@@ -407,6 +410,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                     }
                     __stcs(reinterpret_cast<double2 *>(o0 + l), r0);
                     if (two) __stcs(reinterpret_cast<double2 *>(o1 + l), r1);
+                    if (ONE_STEP) break;
                 }
             }
             lev_sel ^= 1;   // no barrier here: the next variable's B writes the other `lev` buffer
@@ -602,20 +606,21 @@ int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int 
     const unsigned grid = (unsigned)grid64;
     const bool rf = (flags & MT_IL_ROUND_F32) != 0, inc = (flags & MT_IL_INCLUSIVE) != 0;
     mt::ProfScope prof("k_setdata_tma", stream);
-    const bool small = nlev <= 2 * NG * PP_SMALL;
-#define ST_LAUNCH(T, INC, RND, PPV)                                                                                \
+    const bool small = nlev <= 2 * NG * PP_SMALL, exact_small = nlev == 2 * NG * PP_SMALL;
+#define ST_LAUNCH(T, INC, RND, PPV, EX)                                                                              \
     do {                                                                                                           \
-        MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC, RND, PPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC, RND, PPV, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)L.total));                                                               \
-        k_setdata_tma<T, INC, RND, PPV><<<grid, NTHREADS, L.total, s>>>(                                           \
+        k_setdata_tma<T, INC, RND, PPV, EX><<<grid, NTHREADS, L.total, s>>>(                                           \
             P, nvar, (int)nz, (int)nlev, L.LP, L.stages, L.stage_bytes, (int)org_x, (int)org_y, levels, direction, \
             pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n, L.off_lev,  \
             L.lev_bytes, L.off_meta, L.off_misc);                                                                  \
     } while (0)
 #define ST_DISPATCH2(T, INC, RND)                      \
     do {                                               \
-        if (small) ST_LAUNCH(T, INC, RND, PP_SMALL);   \
-        else ST_LAUNCH(T, INC, RND, PP_LARGE);         \
+        if (exact_small) ST_LAUNCH(T, INC, RND, PP_SMALL, true);   \
+        else if (small) ST_LAUNCH(T, INC, RND, PP_SMALL, false);    \
+        else ST_LAUNCH(T, INC, RND, PP_LARGE, false);               \
     } while (0)
 #define ST_DISPATCH(T)                              \
     do {                                            \
