@@ -33,3 +33,26 @@ def test_spline_set_data_pipeline_matches_reference():
     ref = oracle.interp2D_fast_layers(dx, dx, xTR, yTR, lev)
     ref = co.cyl_terrain_mask(ref, g["o_cyl_hgt_idx"])
     assert_same(ref, g["o_cyl_u_k2"], "cyl u, k=2")
+
+
+def test_set_data_order_contract_without_gpu():
+    """Argument contract of the spline branch, checked on the host: an order the reference does not
+    handle ends in NameError (its `tmp` stays undefined, cylindrical_grid.py:110-127); a supported
+    order without a CUDA device fails loudly (no CPU fallback)."""
+    import pytest
+    from meteotools_b200.exceptions import BackendError
+    from meteotools_b200.grids import cartesian_grid, cylindrical_grid
+    import torch
+    cyl = cylindrical_grid(dict(SD))
+    cyl.set_horizontal_location(40000.0, 40000.0)
+    z = np.zeros((5, 40, 40))
+    with pytest.raises(NameError):
+        cyl.set_data(2000.0, 2000.0, z, ver_interp_order=3, u=z)
+    car = cartesian_grid(dict(Nx=10, Ny=9, Nz=10, dx=3000, dy=3000, dz=600, z_start=100, vertical_coord_type="z",
+                              SOR_parameter=1.9, max_iteration_times=10, iteration_tolerance=0.05))
+    car.set_horizontal_location(40000.0, 40000.0)
+    with pytest.raises(NameError):
+        car.set_data(2000.0, 2000.0, z, vertical_interp_order=4, u=z)
+    if not torch.cuda.is_available():
+        with pytest.raises(BackendError):
+            cyl.set_data(2000.0, 2000.0, z, ver_interp_order=2, u=z)
