@@ -106,6 +106,33 @@ def bench_fd(shape, reps):
     return rows
 
 
+def bench_interplevel(reps):
+    """SURVEY 8(d) S2 variant A / the "pressure-level interp" of S4: mt_interplevel over ALL columns of a
+    (60, 1000, 1000) field, 4 variables per launch, to 60 height levels and to 60 pressure levels
+    (decreasing coordinate).  Bytes = 8 * columns * (nz * (V + 1) + nlev * V)."""
+    lib = _lib.load()
+    nz, ny, nx, V, nlev = 60, 1000, 1000, 4, 60
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    k = torch.arange(nz, device="cuda", dtype=torch.float64).reshape(-1, 1, 1)
+    hgt = 1500.0 * torch.rand((ny, nx), generator=gen, device="cuda", dtype=torch.float64)
+    z3d = hgt[None] + (20000.0 - hgt[None]) * (k / (nz - 1)) ** 1.5
+    p3d = 1e5 * torch.exp(-z3d / 8000.0)
+    flds = [torch.randn((nz, ny, nx), generator=gen, device="cuda", dtype=torch.float64) for _ in range(V)]
+    outs = [torch.empty((ny, nx, nlev), device="cuda", dtype=torch.float64) for _ in range(V)]
+    rows = []
+    for name, vert, lev in (("height levels", z3d, np.arange(nlev) * 300.0 + 100.0),
+                            ("pressure levels (decreasing coordinate)", p3d, np.linspace(98000.0, 9000.0, nlev))):
+        lv = D.to_device(lev)
+        order = 1 if lev[1] > lev[0] else -1
+        call = lambda: _lib.check(lib.mt_interplevel(  # noqa: E731
+            D.ptr_array(flds), V, D.ptr(vert), _lib.MT_F64, nz, ny, nx, 0, ny, 0, nx, D.ptr(lv), nlev, order, -1,
+            D.ptr_array(outs), 1, nx * nlev, nlev, 0, D.stream()))
+        ms = timed(call, reps)
+        rows.append(row(f"mt_interplevel, {V} variables, ({nz},{ny},{nx}) -> {nlev} {name}", ms,
+                        8.0 * ny * nx * (nz * (V + 1) + nlev * V), V * nlev * ny * nx))
+    return rows
+
+
 def bench_S1_legacy(reps):
     """config[0]: 400x400 -> 200r x 360theta through the LEGACY host-pointer symbol (H2D+kernel+D2H)."""
     import ctypes as ct
@@ -217,6 +244,7 @@ def main():
     rows += bench_S1_legacy(20)
     rows += bench_dyn("cyl", (60, 360, 300), (250.0, 2 * np.pi / 360, 1000.0), reps * 3)
     rows += bench_fd((80, 1000, 1000), reps)
+    rows += bench_interplevel(reps)
     rows += bench_dyn("car", (80, 2000, 2000), (250.0, 2000.0, 2000.0), reps)
     print(json.dumps(dict(peak_gbs=PEAK, peak_source=PEAK_SRC, rows=rows), indent=1))
 

@@ -355,6 +355,27 @@ def test_interplevel_device(golden_setdata):
                 "non-monotone inclusive")
 
 
+def test_interplevel_python_wrapper(golden_setdata):
+    """meteotools_b200.interpolation.interplevel (the wrf.interplevel call of the reference's grids)."""
+    import torch
+    from meteotools_b200.interpolation import interplevel
+    g = golden_setdata
+    z3d, T, p3d, plev = g["s_z3d"], g["s_T"], g["s_p3d"], g["s_plev"]
+    zlev = np.arange(10) * 600.0 + 100.0
+    assert_same(interplevel(T, z3d, zlev), g["o_interplevel_z"], "height")
+    assert_same(interplevel(T, p3d, plev), g["o_interplevel_p"], "pressure")
+    assert_same(interplevel(T, p3d, 85000.0), g["o_interplevel_p"][1:2], "scalar level")
+    got32 = interplevel(T.astype(np.float32), z3d.astype(np.float32), zlev)
+    assert got32.dtype == np.float32
+    assert_same(got32, oracle.interplevel(T.astype(np.float32), z3d.astype(np.float32), zlev), "float32")
+    dev = interplevel(torch.from_numpy(T).cuda(), torch.from_numpy(z3d).cuda(), zlev)
+    assert dev.is_cuda and dev.dtype == torch.float64
+    assert_same(dev.cpu().numpy(), g["o_interplevel_z"], "device tensors")
+    from meteotools_b200.exceptions import DimensionError
+    with pytest.raises(DimensionError):
+        interplevel(T, z3d[:, :5], zlev)
+
+
 def test_time_step_stream_matches_grid_api(golden_setdata):
     """pipeline.TimeStepStream (two overlapped slots, host in -> host out) == the grid methods."""
     from meteotools_b200.grids import cylindrical_grid
