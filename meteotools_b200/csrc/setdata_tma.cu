@@ -57,9 +57,11 @@ struct __align__(64) TmaParams {
     double *out[MT_MAX_VARS];
 };
 
-struct __align__(16) Meta {   // one staged target (two 16-byte words)
+struct __align__(16) Meta {   // one staged target (two 16-byte words; a third word measured slower:
+                              // phase C is bound by shared-memory wavefronts as much as by issue slots)
     double fx, fy;
-    int tgt, terrain;           // target index (output row = tgt * o_n), terrain level index
+    int tgt;                    // target index (output row = tgt * o_n)
+    int terrain;                // terrain level index; bit 30: same four corners as the predecessor
     uint32_t b01, b23;          // tile-local ids of the four corner columns (rows of `lev`), 16 bits each
 };
 static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
@@ -97,6 +99,15 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
+#ifdef MT_TMA_TIMING
+// phase clocks of consumer warp 0 (debug builds only: scratch/tma_timing.py)
+__device__ unsigned long long g_tma_timing[8];
+#define TMARK(var) const long long var = clock64()
+#define TACC(i, a, b) tacc[i] += (unsigned long long)((b) - (a))
+#else
+#define TMARK(var)
+#define TACC(i, a, b)
+#endif
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
 // PP = level pairs per column thread (>= ceil(nlev / 2 / NG)): the brackets of a thread's own
@@ -178,18 +189,22 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 case 4: {
                     Meta *mt_ = meta + slot_meta * MAXT;
 #pragma unroll
-                    for (int k = 0; k < TS; ++k)
+                    for (int k = 0; k < TS; ++k) {
+                        const unsigned act = __ballot_sync(0xffffffffu, tgt[k] >= 0);
                         if (tgt[k] >= 0) {
                             Meta m;
-                            m.fx = sw[k].x, m.fy = sw[k].y, m.tgt = tgt[k], m.terrain = ster[k];
-                            // corner columns as element offsets / LP (column ids); the consumer
-                            // multiplies by the column pitch
+                            m.fx = sw[k].x, m.fy = sw[k].y, m.tgt = tgt[k];
                             const uint32_t r0 = (uint32_t)(six[k].z - nit.y) * BX, r1 = (uint32_t)(six[k].w - nit.y) * BX;
                             const uint32_t c0 = (uint32_t)(six[k].x - nit.x), c1 = (uint32_t)(six[k].y - nit.x);
                             m.b01 = (r0 + c0) | ((r0 + c1) << 16);
                             m.b23 = (r1 + c0) | ((r1 + c1) << 16);
+                            // the predecessor of an odd position is the previous lane's target
+                            const uint32_t p01 = __shfl_up_sync(act, m.b01, 1), p23 = __shfl_up_sync(act, m.b23, 1);
+                            const bool same = (lane & 1) && p01 == m.b01 && p23 == m.b23;
+                            m.terrain = ster[k] | (same ? (1 << 30) : 0);
                             mt_[lane + 32 * k] = m;
                         }
+                    }
                     __syncwarp();
                     break;
                 }
@@ -249,8 +264,14 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     int c_slot = 0;
     uint32_t c_par = 0;
     int lev_sel = 0;   // `lev` is double-buffered: B of variable v + 1 may overlap C of variable v
+#ifdef MT_TMA_TIMING
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int n = 0;; ++n) {
+        TMARK(ta);
         mbar_wait(full + c_slot, c_par);
+        TMARK(tb0);
+        TACC(0, ta, tb0);   // wait for the coordinate tile
         if (s_itemid[n & 3] < 0) break;
         const int cnt = s_item4[n & 3].w;
         const T *vt = raw + (size_t)c_slot * stage_elems + c_own;
@@ -331,11 +352,16 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
         cons_sync();
         if (tid == 0) mbar_arrive(empty + c_slot);
         if (++c_slot == stages) c_slot = 0, c_par ^= 1u;
+        TMARK(tb1);
+        TACC(1, tb0, tb1);   // monotonicity + brackets (incl. their two barriers)
 
         const Meta *mt_ = meta + (n % NMETA) * MAXT;
         for (int v = 0; v < nvar; ++v) {
             unsigned char *levb_w = smem + off_lev + lev_sel * lev_bytes;   // [NC][LP] doubles
+            TMARK(t0);
             mbar_wait(full + c_slot, c_par);
+            TMARK(t1);
+            TACC(2, t0, t1);   // wait for the variable's tile
             // B: level-interpolated columns, one level PAIR per step (branch-free, brackets from
             // registers, conflict-free 16-byte stores)
             if (col_thread) {
@@ -356,38 +382,44 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                     }
                 }
             }
+            TMARK(t2);
+            TACC(3, t1, t2);   // B
             cons_sync();   // the only block barrier per variable: `lev` complete, tile consumed
+            TMARK(t3);
+            TACC(4, t2, t3);   // barrier
             if (tid == 0) mbar_arrive(empty + c_slot);  // the ring slot may be refilled
             if (++c_slot == stages) c_slot = 0, c_par ^= 1u;
             // C: bilinear, one warp per target, two consecutive targets per step; the item's targets
             // are sorted by source cell, so a pair usually shares its four corner columns: one set
             // of shared-memory loads then serves both
             double *__restrict__ out = P.out[v];
-            const char *lane_b = reinterpret_cast<const char *>(levb_w) + lane * 16;   // this lane's level pair
-            const int cpitch = LP * 8;
+            const uint32_t lane_a = smem_u32(levb_w) + lane * 16;   // this lane's level pair, as a shared address
+            const uint32_t cpitch = (uint32_t)LP * 8u;
+            auto lds2 = [](uint32_t addr) {
+                double2 r;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+                return r;
+            };
             for (int j = 2 * warp; j < cnt; j += 2 * (NCONS / 32)) {
                 const bool two = j + 1 < cnt;
                 const Meta m0 = mt_[j];
                 const Meta m1 = mt_[two ? j + 1 : j];
                 double *o0 = out + (int64_t)m0.tgt * o_pitch, *o1 = out + (int64_t)m1.tgt * o_pitch;   // 32 x 32 -> 64
-                const bool masked = (m0.terrain | m1.terrain) > 0;                       // warp-uniform
-                const bool same = m0.b01 == m1.b01 && m0.b23 == m1.b23;
-                const char *pa0 = lane_b + (m0.b01 & 0xffffu) * cpitch, *pb0 = lane_b + (m0.b01 >> 16) * cpitch;
-                const char *pc0 = lane_b + (m0.b23 & 0xffffu) * cpitch, *pd0 = lane_b + (m0.b23 >> 16) * cpitch;
-                const char *pa1 = lane_b + (m1.b01 & 0xffffu) * cpitch, *pb1 = lane_b + (m1.b01 >> 16) * cpitch;
-                const char *pc1 = lane_b + (m1.b23 & 0xffffu) * cpitch, *pd1 = lane_b + (m1.b23 >> 16) * cpitch;
+                const bool same = !two || (m1.terrain >> 30) != 0;
+                const int ter0 = m0.terrain & 0x3fffffff, ter1 = m1.terrain & 0x3fffffff;
+                const bool masked = (ter0 | ter1) > 0;                                   // warp-uniform
+                const uint32_t pa0 = lane_a + (m0.b01 & 0xffffu) * cpitch, pb0 = lane_a + (m0.b01 >> 16) * cpitch;
+                const uint32_t pc0 = lane_a + (m0.b23 & 0xffffu) * cpitch, pd0 = lane_a + (m0.b23 >> 16) * cpitch;
+                const uint32_t pa1 = lane_a + (m1.b01 & 0xffffu) * cpitch, pb1 = lane_a + (m1.b01 >> 16) * cpitch;
+                const uint32_t pc1 = lane_a + (m1.b23 & 0xffffu) * cpitch, pd1 = lane_a + (m1.b23 >> 16) * cpitch;
                 constexpr bool ONE_STEP = EXACT && 2 * NG * PP <= 64;
                 for (int l = lane * 2, lo8 = 0; l < nlev; l += 64, lo8 += 512) {
-                    const double2 a0 = *reinterpret_cast<const double2 *>(pa0 + lo8);
-                    const double2 b0 = *reinterpret_cast<const double2 *>(pb0 + lo8);
-                    const double2 c0 = *reinterpret_cast<const double2 *>(pc0 + lo8);
-                    const double2 d0 = *reinterpret_cast<const double2 *>(pd0 + lo8);
+                    const double2 a0 = lds2(pa0 + lo8), b0 = lds2(pb0 + lo8);
+                    const double2 c0 = lds2(pc0 + lo8), d0 = lds2(pd0 + lo8);
                     double2 a1 = a0, b1 = b0, c1 = c0, d1 = d0;
                     if (!same) {
-                        a1 = *reinterpret_cast<const double2 *>(pa1 + lo8);
-                        b1 = *reinterpret_cast<const double2 *>(pb1 + lo8);
-                        c1 = *reinterpret_cast<const double2 *>(pc1 + lo8);
-                        d1 = *reinterpret_cast<const double2 *>(pd1 + lo8);
+                        a1 = lds2(pa1 + lo8), b1 = lds2(pb1 + lo8);
+                        c1 = lds2(pc1 + lo8), d1 = lds2(pd1 + lo8);
                     }
                     double2 r0, r1;
                     {   // fastcompute.f90:100-102
@@ -403,19 +435,25 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                         r1.y = (t1y - t0y) * m1.fy + t0y;
                     }
                     if (masked) {   // terrain: level index below hgt_idx -> NaN (cylindrical_grid.py:171-181)
-                        if (m0.terrain > l) r0.x = nan_f64();
-                        if (m0.terrain > l + 1) r0.y = nan_f64();
-                        if (m1.terrain > l) r1.x = nan_f64();
-                        if (m1.terrain > l + 1) r1.y = nan_f64();
+                        if (ter0 > l) r0.x = nan_f64();
+                        if (ter0 > l + 1) r0.y = nan_f64();
+                        if (ter1 > l) r1.x = nan_f64();
+                        if (ter1 > l + 1) r1.y = nan_f64();
                     }
                     __stcs(reinterpret_cast<double2 *>(o0 + l), r0);
                     if (two) __stcs(reinterpret_cast<double2 *>(o1 + l), r1);
                     if (ONE_STEP) break;
                 }
             }
+            TMARK(t4);
+            TACC(5, t3, t4);   // C
             lev_sel ^= 1;   // no barrier here: the next variable's B writes the other `lev` buffer
         }
     }
+#ifdef MT_TMA_TIMING
+    if (lane == 0 && (warp == 0 || warp == 7 || warp == 14))
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_tma_timing[i], tacc[i]);
+#endif
 }
 
 // targets whose coordinates are NaN / the legacy sentinel: no stencil, just the fill value
@@ -658,5 +696,16 @@ int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dt
                             plan_ix, plan_w, n, order, items, nitems, nflagged, hgt_idx, out, o_n, flags, counter,
                             stream);
 }
+
+#ifdef MT_TMA_TIMING
+int mt_setdata_tma_timing(unsigned long long *out8, int reset)
+{
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return MT_ECUDA;
+    if (out8 && cudaMemcpyFromSymbol(out8, g_tma_timing, sizeof(z)) != cudaSuccess) return MT_ECUDA;
+    if (reset && cudaMemcpyToSymbol(g_tma_timing, z, sizeof(z)) != cudaSuccess) return MT_ECUDA;
+    return MT_OK;
+}
+#endif
 
 }  // extern "C"
