@@ -383,8 +383,9 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
 }
 
 // nanmean over theta + anomaly (cylindrical_grid.py:225-229).  One thread per (z, r); the sum
-// runs over theta in index order.  NOTE: NumPy's pairwise summation is NOT reproduced bit for
-// bit (reduction order differs): tolerance 1e-10 relative, stated in the tests.
+// runs over theta in index order.  theta is a strided axis of the reference's (z, theta, r) arrays,
+// where NumPy's reduction adds sequentially (pairwise blocks are used along the contiguous axis
+// only): the result is bit-identical to np.nanmean(axis=1) (tests assert equality).
 template <int LAYOUT>
 __global__ void __launch_bounds__(128)
 k_azimuthal(Lay<LAYOUT> L, const double *__restrict__ var, double *__restrict__ sym,
