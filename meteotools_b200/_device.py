@@ -6,6 +6,7 @@ operators -- if CUDA is unavailable the functions raise ``BackendError``.
 from __future__ import annotations
 
 import ctypes as ct
+import sys
 
 import numpy as np
 
@@ -39,7 +40,8 @@ def ptr(t):
 
 
 def is_tensor(x):
-    t = _torch
+    # torch may have been imported by the caller only (never through torch() above)
+    t = _torch or sys.modules.get("torch")
     return t is not None and isinstance(x, t.Tensor)
 
 

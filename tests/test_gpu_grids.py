@@ -317,6 +317,23 @@ def test_set_data_car_golden(golden_setdata):
     assert_same(car.u, g["o_sd_car_u"], "car u")
 
 
+def test_set_data_car_device_tensors(golden_setdata):
+    """Cartesian set_data fed with CUDA tensors (2-D field first: the tensor test must not depend on
+    torch having been imported through the package)."""
+    import torch
+    g = golden_setdata
+    from meteotools_b200.grids import cartesian_grid
+    dx = float(g["s_dx"])
+    car = cartesian_grid(dict(Nx=10, Ny=9, Nz=10, dx=3000, dy=3000, dz=600, z_start=100,
+                              vertical_coord_type="z", SOR_parameter=1.9, max_iteration_times=10,
+                              iteration_tolerance=0.05))
+    car.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+    car.set_data(dx, dx, torch.from_numpy(g["s_z3d"]).cuda(), hgt=torch.from_numpy(g["s_hgt"]).cuda(),
+                 u=torch.from_numpy(g["s_u"]).cuda())
+    assert_same(car.hgt, g["o_sd_car_hgt"], "car hgt")
+    assert_same(car.u, g["o_sd_car_u"], "car u")
+
+
 def test_interplevel_device(golden_setdata):
     """mt_interplevel alone: increasing (height) and decreasing (pressure) coordinates, descending
     level list, inclusive switch, non-monotone columns (literal scan) -- against the oracle."""
