@@ -1,0 +1,124 @@
+"""Randomised API parity of meteotools_b200.interpolation against the oracle's restatement of the
+reference wrappers (same signatures): random extents, spacings, target shapes (1-D / 2-D / 3-D),
+leading "layer" dimensions, float32 / integer data, NaN targets, targets exactly on nodes and on the
+last node, NaN holes in the data.  Bit-exact (assert_same); seeds are fixed, so a failure names its
+case."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+def _targets(rng, n_axis, d, shape):
+    """Targets inside [0, d*(n-1)] with some exact nodes, the last node and NaNs mixed in."""
+    hi = d * (n_axis - 1)
+    t = rng.random(shape) * hi
+    flat = t.reshape(-1)
+    k = flat.size
+    if k >= 4:
+        flat[rng.integers(0, k)] = d * rng.integers(0, n_axis)      # exact node
+        flat[rng.integers(0, k)] = hi                               # last node
+        flat[rng.integers(0, k)] = 0.0
+        if rng.random() < 0.5:
+            flat[rng.integers(0, k)] = np.nan
+    return t
+
+
+def _data(rng, shape, kind):
+    a = rng.standard_normal(shape) * 10
+    if kind == "f32":
+        a = a.astype(np.float32)
+    elif kind == "int":
+        a = np.rint(a).astype(np.int64)
+    elif kind == "holes":
+        a[rng.random(shape) < 0.05] = np.nan
+    return a
+
+
+KINDS = ["f64", "f32", "int", "holes"]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_interp1d(seed):
+    import meteotools_b200.interpolation as I
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(3, 200))
+    d = float(rng.choice([1.0, 0.5, 2000.0, 3.0]))
+    kind = KINDS[seed % 4]
+    tshape = tuple(rng.integers(1, 7, size=int(rng.integers(1, 3))))
+    x = _targets(rng, n, d, tshape)
+    a = _data(rng, (n,), kind)
+    assert_same(I.interp1D_fast(d, x, a), oracle.interp1D_fast(d, x, a), f"interp1D_fast seed {seed}")
+    lead = tuple(rng.integers(1, 5, size=int(rng.integers(1, 3))))
+    al = _data(rng, lead + (n,), kind)
+    assert_same(I.interp1D_fast_layers(d, x, al), oracle.interp1D_fast_layers(d, x, al), f"1D layers seed {seed}")
+    # unequal axis, increasing or decreasing
+    xin = np.cumsum(0.1 + rng.random(n))
+    if seed % 2:
+        xin = xin[::-1].copy()
+    lo, hi = xin.min(), xin.max()
+    xo = lo + rng.random(tshape) * (hi - lo)
+    xo.reshape(-1)[0] = xin[int(rng.integers(0, n))]
+    assert_same(I.interp1D_nonequal(xin, xo, a), oracle.interp1D_nonequal(xin, xo, a), f"nonequal seed {seed}")
+    assert_same(I.interp1D_nonequal_layers(xin, xo, al), oracle.interp1D_nonequal_layers(xin, xo, al),
+                f"nonequal layers seed {seed}")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_interp2d(seed):
+    import meteotools_b200.interpolation as I
+    rng = np.random.default_rng(200 + seed)
+    ny, nx = int(rng.integers(2, 90)), int(rng.integers(2, 90))
+    dx, dy = float(rng.choice([1.0, 2000.0, 0.25])), float(rng.choice([1.0, 3.0, 1500.0]))
+    kind = KINDS[seed % 4]
+    tshape = tuple(rng.integers(1, 9, size=int(rng.integers(1, 4))))
+    x, y = _targets(rng, nx, dx, tshape), _targets(rng, ny, dy, tshape)
+    a = _data(rng, (ny, nx), kind)
+    assert_same(I.interp2D_fast(dx, dy, x, y, a), oracle.interp2D_fast(dx, dy, x, y, a), f"interp2D_fast seed {seed}")
+    lead = tuple(rng.integers(1, 6, size=int(rng.integers(1, 3))))
+    al = _data(rng, lead + (ny, nx), kind)
+    assert_same(I.interp2D_fast_layers(dx, dy, x, y, al), oracle.interp2D_fast_layers(dx, dy, x, y, al),
+                f"2D layers seed {seed}")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_interp3d(seed):
+    import meteotools_b200.interpolation as I
+    rng = np.random.default_rng(300 + seed)
+    nz, ny, nx = (int(v) for v in rng.integers(2, 30, size=3))
+    dx, dy, dz = float(rng.choice([1.0, 2000.0])), float(rng.choice([1.0, 3.0])), float(rng.choice([1.0, 250.0]))
+    kind = KINDS[seed % 4]
+    tshape = tuple(rng.integers(1, 7, size=int(rng.integers(1, 4))))
+    x, y, z = _targets(rng, nx, dx, tshape), _targets(rng, ny, dy, tshape), _targets(rng, nz, dz, tshape)
+    a = _data(rng, (nz, ny, nx), kind)
+    assert_same(I.interp3D_fast(dx, dy, dz, x, y, z, a), oracle.interp3D_fast(dx, dy, dz, x, y, z, a),
+                f"interp3D_fast seed {seed}")
+    lead = tuple(rng.integers(1, 4, size=int(rng.integers(1, 3))))
+    al = _data(rng, lead + (nz, ny, nx), kind)
+    assert_same(I.interp3D_fast_layers(dx, dy, dz, x, y, z, al), oracle.interp3D_fast_layers(dx, dy, dz, x, y, z, al),
+                f"3D layers seed {seed}")
+
+
+FD_NAMES = ("FD2", "FD4", "FD2_front", "FD2_back", "FD2_2", "FD2_2_front", "FD2_2_back")
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_fd_family(seed):
+    """Every member of the FD family (calc/differential.py) on random ranks, extents, axes and
+    spacings, NaN holes included, against the numpy restatement: bit-exact."""
+    import meteotools_b200.calc as C
+    from oracle import calc_oracle as co
+    rng = np.random.default_rng(400 + seed)
+    rank = int(rng.integers(1, 5))
+    shape = tuple(int(v) for v in rng.integers(5, 40 if rank < 3 else 14, size=rank))
+    axis = int(rng.integers(-rank, rank))
+    delta = float(rng.choice([1.0, 0.7, 250.0, 2000.0, 2 * np.pi / 360]))
+    v = rng.standard_normal(shape) * 10
+    if seed % 3 == 0:
+        v[rng.random(shape) < 0.03] = np.nan
+    for name in FD_NAMES:
+        assert_same(getattr(C, name)(v, delta, axis), getattr(co, name)(v, delta, axis),
+                    f"{name} {shape} axis {axis} seed {seed}")
