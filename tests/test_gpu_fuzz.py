@@ -122,3 +122,55 @@ def test_fuzz_fd_family(seed):
     for name in FD_NAMES:
         assert_same(getattr(C, name)(v, delta, axis), getattr(co, name)(v, delta, axis),
                     f"{name} {shape} axis {axis} seed {seed}")
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_fuzz_cyl_set_data(seed):
+    """cylindrical_grid.set_data on random source / target geometries (source extents, model level
+    count, even and odd target level counts -> TMA kernel or two-kernel path, radii, centres off
+    the cell corners, 1..5 variables, terrain on / off, float32 sources, host arrays or resident
+    tensors) against the oracle pipeline interplevel -> interp2D_fast_layers -> terrain mask."""
+    import torch
+    from meteotools_b200.grids import cylindrical_grid
+    from oracle import calc_oracle as co
+    rng = np.random.default_rng(500 + seed)
+    nz = int(rng.integers(3, 41))
+    ny, nx = int(rng.integers(40, 130)), int(rng.integers(40, 130))
+    dx = float(rng.choice([2000.0, 1000.0, 3000.0]))
+    Nz = int(rng.integers(2, 41))
+    Nr, Nt = int(rng.integers(4, 40)), int(rng.integers(4, 60))
+    ztop = 12000.0
+    rmax_ok = (min(ny, nx) - 1) * dx / 2 - 2 * dx
+    dr = float(min(rng.choice([500.0, 1000.0, 1500.0]), rmax_ok / Nr))
+    settings = dict(Nr=Nr, Ntheta=Nt, Nz=Nz, dr=dr, dtheta=2 * np.pi / Nt, dz=float(ztop * 0.9 / Nz),
+                    z_start=float(rng.choice([0.0, 50.0, 200.0])), r_start=0, theta_start=0,
+                    vertical_coord_type="z", dt=300)
+    hgt = 800.0 * rng.random((ny, nx)) * (rng.random() < 0.8)
+    k = np.arange(nz).reshape(-1, 1, 1)
+    z3d = hgt[None] + (ztop - hgt[None]) * (k / (nz - 1)) ** 1.4
+    nvar = int(rng.integers(1, 6))
+    f32 = seed % 5 == 3
+    dt_ = np.float32 if f32 else np.float64
+    fields = {f"v{i}": (rng.standard_normal((nz, ny, nx)) * 5 + 0.001 * z3d).astype(dt_) for i in range(nvar)}
+    vert = z3d.astype(dt_)
+    cyl = cylindrical_grid(settings)
+    half = Nr * dr + dx
+    cx = float(half + rng.random() * ((nx - 1) * dx - 2 * half))
+    cy = float(half + rng.random() * ((ny - 1) * dx - 2 * half))
+    cyl.set_horizontal_location(cx, cy)
+    with_hgt = seed % 3 != 2
+    resident = seed % 4 == 1
+    kw = {k_: (torch.from_numpy(v).cuda() if resident else v) for k_, v in fields.items()}
+    vv = torch.from_numpy(vert).cuda() if resident else vert
+    if with_hgt:
+        cyl.set_data(dx, dx, vv, hgt=(torch.from_numpy(hgt).cuda() if resident else hgt), **kw)
+    else:
+        cyl.set_data(dx, dx, vv, **kw)
+    hidx = None
+    if with_hgt:
+        hidx = co.cyl_terrain_index(oracle.interp2D_fast(dx, dx, cyl.xTR, cyl.yTR, hgt), cyl.z_start, cyl.dz)
+    for name, a in fields.items():
+        ref = oracle.interp2D_fast_layers(dx, dx, cyl.xTR, cyl.yTR, oracle.interplevel(a, vert, cyl.z))
+        if hidx is not None:
+            ref = co.cyl_terrain_mask(ref, hidx)
+        assert_same(getattr(cyl, name), ref, f"seed {seed} {name} nz={nz} Nz={Nz} src=({ny},{nx}) f32={f32}")
