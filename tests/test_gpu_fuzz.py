@@ -174,3 +174,68 @@ def test_fuzz_cyl_set_data(seed):
         if hidx is not None:
             ref = co.cyl_terrain_mask(ref, hidx)
         assert_same(getattr(cyl, name), ref, f"seed {seed} {name} nz={nz} Nz={Nz} src=({ny},{nx}) f32={f32}")
+
+
+DYN_EXACT_CYL = ["vr", "vt", "wind_speed", "Tv", "rho", "coriolis_force", "centrifugal_force", "radial_PG_force",
+                 "agradient_force", "kinetic_energy", "zeta_r", "zeta_t", "zeta_z", "abs_zeta_z", "div_hori", "div",
+                 "density_factor", "shear_deform", "stretch_deform", "strain_region"]
+DYN_EXACT_CAR = ["wind_speed", "kinetic_energy", "zeta_r", "zeta_t", "zeta_z", "abs_zeta_z", "div_hori", "div",
+                 "density_factor", "Tv", "rho", "shear_deform", "stretch_deform"]
+
+
+def _dyn_fields(rng, shape, dz, z_start):
+    zz = (np.arange(shape[0]) * dz + z_start).reshape(-1, 1, 1)
+    f = {k: 10 * rng.standard_normal(shape) for k in ("u", "v", "w")}
+    f["p"] = 1e5 * np.exp(-zz / 8000.0) + rng.standard_normal(shape)
+    f["T"] = 300 - 6.5e-3 * zz + rng.standard_normal(shape)
+    f["qv"] = 1e-3 + 1e-3 * np.abs(rng.standard_normal(shape))
+    for k in ("qc", "qr", "qi", "qs", "qg"):
+        f[k] = 1e-4 * np.abs(rng.standard_normal(shape))
+    f["f"] = 5e-5 + 1e-6 * rng.standard_normal(shape[1:])
+    return f
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_dynamics_sets(seed):
+    """The fused cyl_d / car_d sets (stage A + marching stage B with its segments, compact shell
+    launch and straight-line instantiation) on random small grids, minimum extents included."""
+    from conftest import assert_close
+    from meteotools_b200.grids import cartesian_grid, cylindrical_grid
+    from oracle import calc_oracle as co
+    rng = np.random.default_rng(600 + seed)
+    nz, n1, n2 = (int(v) for v in rng.integers(3, 34, size=3))
+    if seed == 0:
+        nz, n1, n2 = 3, 3, 3                      # the smallest grid FD2 accepts
+    dz = float(rng.choice([250.0, 300.0, 500.0]))
+    f = _dyn_fields(rng, (nz, n1, n2), dz, 100.0)
+    if seed % 2 == 0:
+        dr = float(rng.choice([1000.0, 1500.0]))
+        cyl = cylindrical_grid(dict(Nr=n2, Ntheta=n1, Nz=nz, dr=dr, dtheta=2 * np.pi / n1, dz=dz, z_start=100,
+                                    r_start=0, theta_start=0, vertical_coord_type="z", dt=300))
+        for k, v in f.items():
+            setattr(cyl, k, v.copy())
+        cyl.calc_diagnostics()
+        with np.errstate(all="ignore"):
+            ref = co.cyl_d_set(f, dict(r=cyl.r, theta=cyl.theta, dr=cyl.dr, dtheta=cyl.dtheta, dz=cyl.dz))
+            ref2 = co.cyl_d_set(dict(f, Th=np.asarray(cyl.Th)), dict(r=cyl.r, theta=cyl.theta, dr=cyl.dr,
+                                                                   dtheta=cyl.dtheta, dz=cyl.dz))
+        for k in DYN_EXACT_CYL:
+            assert_same(getattr(cyl, k), ref[k], f"cyl seed {seed} {(nz, n1, n2)} {k}")
+        assert_close(cyl.Th_rho, ref["Th_rho"], 1e-10, f"cyl seed {seed} Th_rho")
+        # with the GPU's own Th as input the whole chain is reproduced bit for bit
+        assert_same(cyl.Th_rho, ref2["Th_rho"], f"cyl seed {seed} Th_rho from the GPU's Th")
+        assert_same(cyl.PV, ref2["PV"], f"cyl seed {seed} PV from the GPU's Th")
+    else:
+        dx = float(rng.choice([2000.0, 3000.0]))
+        car = cartesian_grid(dict(Nx=n2, Ny=n1, Nz=nz, dx=dx, dy=dx, dz=dz, z_start=100, vertical_coord_type="z",
+                                  SOR_parameter=1.9, max_iteration_times=10, iteration_tolerance=0.05))
+        for k, v in f.items():
+            setattr(car, k, v.copy())
+        car.calc_diagnostics()
+        with np.errstate(all="ignore"):
+            ref = co.car_d_set(f, dict(dx=dx, dy=dx, dz=dz))
+            ref2 = co.car_d_set(dict(f, Th=np.asarray(car.Th)), dict(dx=dx, dy=dx, dz=dz))
+        for k in DYN_EXACT_CAR:
+            assert_same(getattr(car, k), ref[k], f"car seed {seed} {(nz, n1, n2)} {k}")
+        assert_same(car.Th_rho, ref2["Th_rho"], f"car seed {seed} Th_rho from the GPU's Th")
+        assert_same(car.PV, ref2["PV"], f"car seed {seed} PV from the GPU's Th")
