@@ -239,3 +239,38 @@ def test_fuzz_dynamics_sets(seed):
             assert_same(getattr(car, k), ref[k], f"car seed {seed} {(nz, n1, n2)} {k}")
         assert_same(car.Th_rho, ref2["Th_rho"], f"car seed {seed} Th_rho from the GPU's Th")
         assert_same(car.PV, ref2["PV"], f"car seed {seed} PV from the GPU's Th")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_cyl_td_set(seed):
+    """The fused cyl_td pass on random grid shapes (odd point counts: the scalar tails of the vector
+    loops), wide physical ranges, with and without NaN (terrain) -- the two branches of calc_Tc's
+    stop test and the speculation in k_td_main -- and with / without qc, qr (the generic kernel)."""
+    from conftest import assert_close
+    from meteotools_b200.grids import cylindrical_grid
+    from oracle import calc_oracle as co
+    rng = np.random.default_rng(700 + seed)
+    nz, nt, nr = (int(v) for v in rng.integers(3, 22, size=3))
+    shape = (nz, nt, nr)
+    T = 200.0 + 120.0 * rng.random(shape)
+    p = 2000.0 + 1.0e5 * rng.random(shape)
+    qv = 10.0 ** (-7 + 5.5 * rng.random(shape))
+    qc, qr = 1e-4 * rng.random(shape), 1e-4 * rng.random(shape)
+    if seed % 2 == 0:                                   # masked points: the ten sweeps are certain
+        hole = rng.random(shape) < 0.1
+        for a in (T, p, qv, qc, qr):
+            a[hole] = np.nan
+    td = cylindrical_grid(dict(Nr=nr, Ntheta=nt, Nz=nz, dr=1000.0, dtheta=2 * np.pi / nt, dz=250.0, z_start=100,
+                               r_start=0, theta_start=0, vertical_coord_type="z", dt=300))
+    td.T, td.p, td.qv = T.copy(), p.copy(), qv.copy()
+    with_ql = seed % 4 < 2
+    if with_ql:
+        td.qc, td.qr = qc.copy(), qr.copy()
+    td.calc_all_thermaldynamic()
+    with np.errstate(all="ignore"):
+        ref = co.cyl_td_set(T, p, qv, qc if with_ql else None, qr if with_ql else None)
+    assert int(td._tc_scratch[15].item()) == ref["_Tc_iters"], "calc_Tc sweep count"
+    for k in ("vapor", "Tv", "rho"):
+        assert_same(getattr(td, k), ref[k], f"seed {seed} {shape} {k}")
+    for k in ("Th", "vapor_s", "qvs", "RH", "Td", "Th_es", "Th_v", "Tc", "Th_e", "moist_dTdz"):
+        assert_close(getattr(td, k), ref[k], 1e-10, f"seed {seed} {shape} {k}")
