@@ -360,7 +360,12 @@ int mt_azimuthal_mean(const double *var, const mt_grid_t *g, double *sym, double
  * reduced axis k), the kernel behind calc_Zaverage / calc_Raverage / calc_RZaverage
  * (calc/averages.py:13-114):
  *   out[a*o_a + b*o_b] = ( sum_k var[a*s_a + b*s_b + k*s_k] * w[k], NaN products skipped ) / D
- *   mode 0: D = denom;  mode 1: D = sum of w[k] over the terms that were not skipped (nanmean). */
+ *   mode 0: D = denom;  mode 1: D = sum of w[k] over the terms that were not skipped (nanmean).
+ *   mode | MT_WSUM_PAIRWISE: the terms are added in the order NumPy uses along the CONTIGUOUS axis
+ *   of the reference's array (pairwise blocks of 8 accumulators, halving recursion above 128
+ *   terms); without the flag they are added sequentially, which is NumPy's order along a strided
+ *   axis.  With the right flag the sum is bit-identical to the reference's np.nansum. */
+#define MT_WSUM_PAIRWISE 2
 int mt_axis_wsum(const double *var, int64_t n_a, int64_t n_b, int64_t n_k, int64_t s_a, int64_t s_b,
                  int64_t s_k, const double *w, int mode, double denom, double *out, int64_t o_a,
                  int64_t o_b, mt_stream_t stream);

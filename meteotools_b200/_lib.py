@@ -24,6 +24,7 @@ MT_F64, MT_F32 = 0, 1
 MT_IL_INCLUSIVE, MT_IL_ROUND_F32, MT_IL_SPLINE2, MT_IL_SPLINE3 = 1, 2, 4, 8
 MT_MAX_VARS = 16
 MT_NANSUM_SCRATCH = 2048
+MT_WSUM_PAIRWISE = 2
 MT_TMA_TILE_W_F64, MT_TMA_TILE_W_F32, MT_TMA_TILE_H = 14, 12, 4   # source cells per tile of mt_setdata_tma
 
 

@@ -35,7 +35,9 @@ def _check_axis(var_axis, var, axis, name):  # check_arrays.py:11-14, :33-38
 
 def axis_wsum(var, axis, w, mode=0, denom=1.0):
     """Device reduction of a dense C-order array along ``axis``: see mt_axis_wsum.  Returns a CUDA
-    tensor with that axis removed."""
+    tensor with that axis removed.  The terms are added in NumPy's order for a C-order array --
+    pairwise along the last (contiguous) axis, sequentially along the others -- so the result is
+    bit-identical to the reference's ``np.nansum(var * w, axis)``."""
     v = D.to_device(var)
     shape = tuple(int(s) for s in v.shape)
     nd = len(shape)
@@ -45,6 +47,8 @@ def axis_wsum(var, axis, w, mode=0, denom=1.0):
     n = shape[axis]
     wd = D.to_device(np.ascontiguousarray(w, dtype=np.float64))
     out = D.empty(shape[:axis] + shape[axis + 1:] if nd > 1 else (1,))
+    if axis == nd - 1:
+        mode = int(mode) | _lib.MT_WSUM_PAIRWISE
     _lib.check(_lib.load().mt_axis_wsum(D.ptr(v), outer, inner, n, n * inner, 1, inner, D.ptr(wd), int(mode),
                                         float(denom), D.ptr(out), inner, 1, D.stream()), "mt_axis_wsum")
     return out
@@ -88,4 +92,10 @@ def calc_RZaverage(var, z_axis, r_axis, rmin=np.nan, rmax=np.nan, zmin=np.nan, z
         with np.errstate(all="ignore"):
             denom = float(np.nansum(r_select * r_axis))
         return float(D.to_host(axis_wsum(tmp, 0, r_select * r_axis, 0, denom))[0])
-    return float(D.to_host(axis_wsum(tmp, 0, r_select.astype(np.float64), 1))[0])
+    # np.nanmean(tmp[r_select]) (:51): the selection is compacted first, so the pairwise blocks of
+    # the sum start at the first selected radius (a range of a monotone axis is one run)
+    idx = np.flatnonzero(r_select)
+    if idx.size == 0:
+        return float('nan')
+    run = tmp[int(idx[0]):int(idx[-1]) + 1]
+    return float(D.to_host(axis_wsum(run, 0, np.ones(run.shape[0]), 1))[0])

@@ -5,9 +5,11 @@
 //   * integrated kinetic energy (cylindrical_grid.py:554-600);
 //   * the 1-c-1 smoothers of cartesian_grid.py:142-229 (Jacobi passes over a padded copy whose
 //     ghost cells stay frozen at the INITIAL edge values).
-// Sums are NaN-skipping exactly where the reference uses nansum / nanmean.  The ORDER of a sum is
-// not NumPy's (pairwise blocks of 8 on contiguous axes): these outputs are tolerance-class
-// (1e-10 relative, north star); the smoothers are pure +,*,/ in the reference's order: bit-exact.
+// Sums are NaN-skipping exactly where the reference uses nansum / nanmean, and the sums along one
+// axis are added in NumPy's order -- sequentially along a strided axis, in pairwise blocks along
+// the contiguous one -- so they are bit-identical to the reference's.  The full-grid sums (IKE,
+// the last step of calc_RZaverage) use a block tree and stay tolerance-class (1e-10 relative,
+// north star); the smoothers are pure +,*,/ in the reference's order: bit-exact.
 #include "common.cuh"
 
 namespace {
@@ -45,33 +47,98 @@ k_axis_wsum(const double *__restrict__ var, int64_t n_f, int64_t n_s, int64_t n_
     }
 }
 
-// Warp-per-output variant for a contiguous reduction axis (s_k == 1): lanes stride over k.
-template <int MODE>
-__global__ void __launch_bounds__(256)
-k_axis_wsum_warp(const double *__restrict__ var, int64_t n_f, int64_t n_s, int64_t n_k, int64_t s_f,
-                 int64_t s_s, const double *__restrict__ w, double denom, double *__restrict__ out,
-                 int64_t o_f, int64_t o_s)
+// MT_WSUM_PAIRWISE: the axis that is CONTIGUOUS IN THE REFERENCE'S ARRAY (the last axis of its C-order
+// array, whatever the strides of the device layout are).  There np.nansum(..., axis=-1) adds PAIRWISE (DOUBLE_pairwise_sum of
+// numpy/core/src/umath/loops_utils.h.src): fewer than 8 terms sequentially from 0; up to 128 terms
+// in eight interleaved accumulators r[j] += a[i + j] combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+// plus the remainder in order; longer runs split at n/2 rounded down to a multiple of 8, left half
+// first.  NaN terms take part as 0.0 in their position.  One thread per output follows exactly that
+// order (checked against NumPy for 1 .. 6.5 M terms with a Python mirror of this routine), so the
+// result is bit-identical to the reference's; rows are short (a grid axis), the loads go through L1.
+template <class Term>
+__device__ __forceinline__ double numpy_pairwise_leaf(Term term, int64_t lo, int64_t n)   // n <= 128
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (n < 8) {
+        double res = 0.0;
+        for (int64_t i = 0; i < n; ++i) res += term(lo + i);
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = term(lo + j);
+        const int64_t m = n - (n % 8);
+        for (int64_t i = 8; i < m; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += term(lo + i + j);
+        }
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (int64_t i = m; i < n; ++i) res += term(lo + i);
+        return res;
+    }
+    return 0.0;   // not reached
+}
+
+template <class Term>
+__device__ double numpy_pairwise(Term term, int64_t lo, int64_t n)
+{
+    if (n <= 128) return numpy_pairwise_leaf(term, lo, n);
+    // depth-first, left half first, with an explicit stack (2^40 terms would need 34 frames)
+    int64_t st_lo[40], st_n[40];
+    double st_acc[40];
+    int st_state[40], sp = 0;
+    st_lo[0] = lo, st_n[0] = n, st_state[0] = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int64_t cn = st_n[sp], clo = st_lo[sp];
+        if (cn <= 128) {
+            ret = numpy_pairwise_leaf(term, clo, cn);
+            --sp;
+            continue;
+        }
+        int64_t n2 = cn / 2;
+        n2 -= n2 % 8;
+        if (st_state[sp] == 0) {          // descend into the left half
+            st_state[sp] = 1;
+            ++sp;
+            st_lo[sp] = clo, st_n[sp] = n2, st_state[sp] = 0;
+        } else if (st_state[sp] == 1) {   // left done: keep it, descend into the right half
+            st_acc[sp] = ret;
+            st_state[sp] = 2;
+            ++sp;
+            st_lo[sp] = clo + n2, st_n[sp] = cn - n2, st_state[sp] = 0;
+        } else {                          // both done
+            ret = st_acc[sp] + ret;
+            --sp;
+        }
+    }
+    return ret;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_axis_wsum_pairwise(const double *__restrict__ var, int64_t n_f, int64_t n_s, int64_t n_k, int64_t s_f,
+                     int64_t s_s, int64_t s_k, const double *__restrict__ w, double denom,
+                     double *__restrict__ out, int64_t o_f, int64_t o_s)
+{
     const int64_t total = n_f * n_s;
-    for (int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; q < total; q += warps) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total;
+         q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = q / n_f, f = q - s * n_f;
         const double *p = var + f * s_f + s * s_s;
-        double acc = 0.0, wsum = 0.0;
-        for (int64_t k = lane; k < n_k; k += 32) {
-            const double wk = __ldg(w + k);
-            const double t = __ldg(p + k) * wk;
-            if (!isnan(t)) {
-                acc += t;
-                wsum += wk;
+        const double acc = numpy_pairwise(
+            [&](int64_t k) {
+                const double t = __ldg(p + k * s_k) * __ldg(w + k);
+                return isnan(t) ? 0.0 : t;
+            },
+            0, n_k);
+        double wsum = 0.0;   // MODE 1: the weights are 0 / 1 selectors, their sum is exact in any order
+        if (MODE == 1)
+            for (int64_t k = 0; k < n_k; ++k) {
+                const double wk = __ldg(w + k);
+                if (!isnan(__ldg(p + k * s_k) * wk)) wsum += wk;
             }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-        }
-        if (lane == 0) out[f * o_f + s * o_s] = acc / (MODE == 0 ? denom : wsum);
+        out[f * o_f + s * o_s] = acc / (MODE == 0 ? denom : wsum);
     }
 }
 
@@ -235,7 +302,9 @@ int mt_axis_wsum(const double *var, int64_t n_a, int64_t n_b, int64_t n_k, int64
                  int64_t o_b, mt_stream_t stream)
 {
     MT_REQUIRE(var && w && out && n_a >= 1 && n_b >= 1 && n_k >= 1, "mt_axis_wsum: bad arguments");
-    MT_REQUIRE(mode == 0 || mode == 1, "mt_axis_wsum: mode must be 0 (fixed denominator) or 1 (weight sum)");
+    MT_REQUIRE(mode >= 0 && mode <= 3, "mt_axis_wsum: mode = (0: fixed denominator | 1: weight sum) + MT_WSUM_PAIRWISE");
+    const bool pairwise = (mode & MT_WSUM_PAIRWISE) != 0;
+    mode &= 1;
     cudaStream_t s = (cudaStream_t)stream;
     // the kept axis with the smaller stride becomes the thread-fastest one
     int64_t n_f = n_a, s_f = s_a, o_f = o_a, n_s = n_b, s_s = s_b, o_s = o_b;
@@ -244,12 +313,12 @@ int mt_axis_wsum(const double *var, int64_t n_a, int64_t n_b, int64_t n_k, int64
         n_s = n_a, s_s = s_a, o_s = o_a;
     }
     mt::ProfScope prof("k_axis_wsum", stream);
-    if (s_k == 1 && n_k >= 32) {
-        const unsigned grid = mt::grid_for(n_a * n_b * 32, 256, 8);
+    if (pairwise) {   // the reference reduces along its contiguous axis: NumPy's pairwise order
+        const unsigned grid = mt::grid_for(n_a * n_b, 128, 8);
         if (mode == 0)
-            k_axis_wsum_warp<0><<<grid, 256, 0, s>>>(var, n_f, n_s, n_k, s_f, s_s, w, denom, out, o_f, o_s);
+            k_axis_wsum_pairwise<0><<<grid, 128, 0, s>>>(var, n_f, n_s, n_k, s_f, s_s, s_k, w, denom, out, o_f, o_s);
         else
-            k_axis_wsum_warp<1><<<grid, 256, 0, s>>>(var, n_f, n_s, n_k, s_f, s_s, w, denom, out, o_f, o_s);
+            k_axis_wsum_pairwise<1><<<grid, 128, 0, s>>>(var, n_f, n_s, n_k, s_f, s_s, s_k, w, denom, out, o_f, o_s);
     } else {
         const unsigned grid = mt::grid_for(n_a * n_b, 256, 8);
         if (mode == 0)

@@ -609,7 +609,8 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
     # ------------------------------------------------------------ range averages (8f-1)
     def _wsum3(self, varname, axis, w, mode, denom):
         """mt_axis_wsum over one logical axis (0: z, 1: theta, 2: r) of a 3-D field in the grid's
-        layout; returns a dense C-order CUDA tensor over the two kept axes."""
+        layout; returns a dense C-order CUDA tensor over the two kept axes.  Axis 2 is the
+        contiguous axis of the reference's (z, theta, r) array: NumPy's pairwise order there."""
         var = self.device(varname)
         n = (self.Nz, self.Ntheta, self.Nr)
         if self._layout == _lib.MT_LAYOUT_TRZ:
@@ -619,6 +620,8 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         ka, kb = [i for i in range(3) if i != axis]
         out = D.empty((n[ka], n[kb]))
         wd = D.to_device(np.ascontiguousarray(w, dtype=np.float64))
+        if axis == 2:
+            mode = int(mode) | _lib.MT_WSUM_PAIRWISE
         _lib.check(_lib.load().mt_axis_wsum(D.ptr(var), n[ka], n[kb], n[axis], st[ka], st[kb], st[axis],
                                             D.ptr(wd), int(mode), float(denom), D.ptr(out), n[kb], 1,
                                             D.stream()), 'mt_axis_wsum')

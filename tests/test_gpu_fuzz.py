@@ -274,3 +274,33 @@ def test_fuzz_cyl_td_set(seed):
         assert_same(getattr(td, k), ref[k], f"seed {seed} {shape} {k}")
     for k in ("Th", "vapor_s", "qvs", "RH", "Td", "Th_es", "Th_v", "Tc", "Th_e", "moist_dTdz"):
         assert_close(getattr(td, k), ref[k], 1e-10, f"seed {seed} {shape} {k}")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_range_averages(seed):
+    """calc_Zaverage / calc_Raverage / calc_RZaverage on random ranks, axes, ranges and NaN patterns:
+    the sums follow NumPy's order for C-order arrays (sequential along strided axes, pairwise blocks
+    -- < 8, <= 128 and > 128 terms -- along the contiguous one), so they equal the numpy oracle bit
+    for bit."""
+    import meteotools_b200.calc as C
+    from oracle import calc_oracle as co
+    rng = np.random.default_rng(800 + seed)
+    rank = int(rng.integers(1, 4))
+    shape = tuple(int(v) for v in rng.choice([3, 7, 8, 9, 37, 128, 129, 300, 517], size=rank))
+    if rank == 3:
+        shape = tuple(min(v, 129) for v in shape)
+    a = rng.standard_normal(shape) * 100
+    a[rng.random(shape) < 0.05] = np.nan
+    for axis in range(rank):
+        ax = np.cumsum(0.1 + rng.random(shape[axis]))
+        lo, hi = ax[int(rng.integers(0, max(1, shape[axis] // 3)))], ax[-1 - int(rng.integers(0, max(1, shape[axis] // 3)))]
+        with np.errstate(all="ignore"):
+            assert_same(C.calc_Zaverage(a, ax, axis, lo, hi), co.Zaverage(a, ax, axis, lo, hi), f"Z seed {seed} {shape} axis {axis}")
+            assert_same(C.calc_Raverage(a, ax, axis, lo, hi), co.Raverage(a, ax, axis, lo, hi), f"R seed {seed} {shape} axis {axis}")
+    if rank == 2:
+        zax, rax = np.cumsum(0.1 + rng.random(shape[0])), np.cumsum(0.1 + rng.random(shape[1]))
+        for rw in (True, False):
+            with np.errstate(all="ignore"):
+                got = C.calc_RZaverage(a, zax, rax, rax[1], rax[-2], zax[0], zax[-1], r_weight=rw)
+                ref = co.RZaverage(a, zax, rax, rax[1], rax[-2], zax[0], zax[-1], r_weight=rw)
+            assert_same(np.float64(got), np.float64(ref), f"RZ seed {seed} {shape} r_weight={rw}")

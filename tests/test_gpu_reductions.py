@@ -20,19 +20,19 @@ def test_calc_averages(golden_reductions):
     from meteotools_b200.exceptions import DimensionError
     g = golden_reductions
     a, ax = g["r_a"], g["r_ax"]
-    # strided axes: NumPy adds sequentially there and so does the kernel -> bit-identical; only the
-    # contiguous axis (NumPy's pairwise blocks) is held to the tolerance
+    # sums along one axis follow NumPy's order for a C-order array (sequential along strided axes,
+    # pairwise blocks along the contiguous one): bit-identical to the reference
     assert_same(C.calc_Zaverage(a, ax, 1, ax[4], ax[30]), g["o_Zavg_1"], "Zaverage axis 1")
     assert_same(C.calc_Zaverage(a, ax, 1), g["o_Zavg_1_full"], "Zaverage full range")
     assert_same(C.calc_Raverage(a, ax, 1, ax[2], ax[35]), g["o_Ravg_1"], "Raverage axis 1")
     assert_same(C.calc_Zaverage(np.ascontiguousarray(np.moveaxis(a, 1, 0)), ax, 0, ax[4], ax[30]), g["o_Zavg_0"], "axis 0")
     a2 = np.ascontiguousarray(np.moveaxis(a, 1, 2))
-    assert_close(C.calc_Zaverage(a2, ax, 2, ax[4], ax[30]), g["o_Zavg_2"], TOL, "contiguous axis (warp kernel)")
-    assert_close(C.calc_Raverage(torch.from_numpy(a2).cuda(), ax, 2), g["o_Ravg_2"], TOL, "CUDA tensor input")
-    assert_close(C.calc_Zaverage(a[2, :, 1], ax, 0, ax[1], ax[20]), g["o_Zavg_1d"], TOL, "1-D")
+    assert_same(C.calc_Zaverage(a2, ax, 2, ax[4], ax[30]), g["o_Zavg_2"], "contiguous axis (warp kernel)")
+    assert_same(C.calc_Raverage(torch.from_numpy(a2).cuda(), ax, 2), g["o_Ravg_2"], "CUDA tensor input")
+    assert_same(C.calc_Zaverage(a[2, :, 1], ax, 0, ax[1], ax[20]), g["o_Zavg_1d"], "1-D")
     zr, zax = g["r_zr"], g["r_zax"]
-    assert_close(C.calc_RZaverage(zr, zax, ax, ax[3], ax[33], zax[1], zax[6]), g["o_RZavg"], TOL, "RZaverage")
-    assert_close(C.calc_RZaverage(zr, zax, ax, ax[3], ax[33], zax[1], zax[6], r_weight=False), g["o_RZavg_now"], TOL,
+    assert_same(C.calc_RZaverage(zr, zax, ax, ax[3], ax[33], zax[1], zax[6]), g["o_RZavg"], "RZaverage")
+    assert_same(C.calc_RZaverage(zr, zax, ax, ax[3], ax[33], zax[1], zax[6], r_weight=False), g["o_RZavg_now"],
                  "RZaverage unweighted")
     with pytest.raises(ValueError):
         C.calc_Zaverage(a, ax[::-1], 1)
@@ -45,10 +45,10 @@ def test_calc_averages(golden_reductions):
     for axis in range(3):
         axv = np.cumsum(0.1 + rng.random(big.shape[axis]))
         with np.errstate(all="ignore"):
-            assert_close(C.calc_Zaverage(big, axv, axis, axv[3], axv[-4]), co.Zaverage(big, axv, axis, axv[3], axv[-4]),
-                         TOL, f"big Zaverage axis {axis}")
-            assert_close(C.calc_Raverage(big, axv, axis, axv[3], axv[-4]), co.Raverage(big, axv, axis, axv[3], axv[-4]),
-                         TOL, f"big Raverage axis {axis}")
+            assert_same(C.calc_Zaverage(big, axv, axis, axv[3], axv[-4]), co.Zaverage(big, axv, axis, axv[3], axv[-4]),
+                        f"big Zaverage axis {axis}")
+            assert_same(C.calc_Raverage(big, axv, axis, axv[3], axv[-4]), co.Raverage(big, axv, axis, axv[3], axv[-4]),
+                        f"big Raverage axis {axis}")
 
 
 def _cyl(g, names):
@@ -75,7 +75,7 @@ def test_cyl_reductions(golden_reductions):
     cyl.calc_vertical_average("prof", 200., 1600.)
     for k in ("sym_vt", "asy_vt", "axisymmetry_vt", "sym_f", "asy_f", "axisymmetry_f", "sym_ring", "asy_ring",
               "axisymmetry_ring", "havg_T", "havg_qv", "havg_f", "zavg_T", "zavg_prof"):
-        assert_close(getattr(cyl, k), g[f"o_rcyl_{k}"], TOL, k)
+        assert_same(getattr(cyl, k), g[f"o_rcyl_{k}"], k)
     cyl.calc_IKE(rmin=2000., rmax=10000., zmin=200., zmax=1800.)
     assert_close(cyl.IKE, g["o_rcyl_IKE_range"], TOL, "IKE range")
     cyl.calc_IKE()
@@ -116,7 +116,7 @@ def test_car_averages_and_smoothers(golden_reductions):
     car.calc_horizontal_average("f", ymin=2000.)
     car.calc_vertical_average("T", zmax=1200.)
     for k in ("havg_T", "havg_f", "zavg_T"):
-        assert_close(getattr(car, k), g[f"o_rcar_{k}"], TOL, k)
+        assert_same(getattr(car, k), g[f"o_rcar_{k}"], k)
     for ax in range(3):
         car.smooth1d("u", axis=ax, center_weight=2, passes=3)
         assert_same(car.smooth1d_u, g[f"o_rcar_smooth1d_u_{ax}"], f"smooth1d axis {ax}")
