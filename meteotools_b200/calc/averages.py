@@ -6,7 +6,8 @@ Semantics kept from the reference: the averaging axis must increase strictly (Va
 match ``var``'s extent (DimensionError); NaN limits mean "from the first / to the last point";
 NaNs in ``var`` are skipped in the SUM but calc_Zaverage still divides by the number of SELECTED
 points (:113) and calc_Raverage by ``nansum(select*r)`` (:81-82), exactly as written there.
-The order of the additions is not NumPy's pairwise order: results agree to 1e-10 relative.
+The additions follow NumPy's order for a C-order array (sequential along strided axes, pairwise
+blocks along the last axis): the results are bit-identical to the reference's.
 """
 import numpy as np
 
