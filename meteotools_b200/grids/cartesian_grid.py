@@ -70,6 +70,7 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
     _interp2d_var = cylindrical_grid._interp2d_var
     _setdata3d = cylindrical_grid._setdata3d
     _plan_for = cylindrical_grid._plan_for
+    _fused_items_for = cylindrical_grid._fused_items_for
 
     @timer
     def set_data(self, src_dx, src_dy, src_vertical, vertical_interp_order=1, inclusive=False, **vardict):

@@ -186,21 +186,29 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 srcs = [stage(s, use32) for _, s in batch]
                 outs = [self._new() for _ in batch]
                 mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
-                fits = trz and nz <= 254 and self.Nz % 2 == 0 and spline_order == 1
+                fits = nz <= 254 and self.Nz % 2 == 0 and spline_order == 1
                 if fits and mode == "tma" and lib.mt_setdata_tma_supported(dtype, nz, self.Nz, snx):
-                    # one warp-specialised TMA kernel, no intermediate in HBM (csrc/setdata_tma.cu)
+                    # one warp-specialised TMA kernel, no intermediate in HBM (csrc/setdata_tma.cu).
+                    # It writes target-major, level-fastest rows; a (z, y, x) grid takes them through
+                    # the tiled transpose of mt_permute3 (two near-copy passes instead of one
+                    # bilinear launch per variable on the level-major path).
                     tw_, th_, al_, mt_ = _lib.tma_tile(dtype)
                     order_t, items_t, nitems, nflag, counter = self._fused_items_for(
                         plan, tw_, th_, max_targets=mt_, spatial=True, align=al_, org_x=ox)
+                    rows = outs if trz else [D.empty((n, self.Nz)) for _ in batch]
                     _lib.check(lib.mt_setdata_tma(D.ptr_array(srcs), len(batch), D.ptr(vert_d), dtype, nz, sny,
                                                   snx, snx, oy, ox, D.ptr(levels), self.Nz, direction,
                                                   D.ptr(plan[0]), D.ptr(plan[1]), n, D.ptr(order_t),
                                                   D.ptr(items_t), nitems, nflag, D.ptr(hgt_idx),
-                                                  D.ptr_array(outs), self.Nz, flags, D.ptr(counter),
+                                                  D.ptr_array(rows), self.Nz, flags, D.ptr(counter),
                                                   D.stream()), 'mt_setdata_tma')
+                    if not trz:
+                        n1, n2 = self._grid_shape3()[1:]
+                        outs = [D.permute3(r_, (self.Nz, n1, n2), (1, n2 * self.Nz, self.Nz)) for r_ in rows]
                     for (name, _), o in zip(batch, outs):
                         self._put(name, o)
                     continue
+                fits = fits and trz
                 if fits and mode == "fused":   # first-generation fused kernel (cp.async), kept for A/B runs
                     th_ = 2 if os.environ.get("MT_SETDATA_TILE") == "16x2" else 4
                     order_t, items_t, nitems, nflag, counter = self._fused_items_for(plan, 16, th_)
