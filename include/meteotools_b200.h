@@ -213,8 +213,9 @@ int mt_setdata_fused(const void *const *fields, int nvar, const void *vert, int 
  * `direction` must be 0 or 1 (decided by the caller from column (0,0) of the full coordinate
  * array).  mt_setdata_tma_supported() tells whether a shape can take this path (otherwise use
  * mt_setdata: same results, two kernels).
- * The number of target levels must be even and <= 96 (the brackets of a thread's level pairs live
- * in registers); at most MT_TMA_MAX_TARGETS targets per item. */
+ * At most 96 target levels (the brackets of a thread's level pairs live in registers); an odd level
+ * count or output pitch is accepted (8-byte instead of 16-byte stores); at most MT_TMA_MAX_TARGETS
+ * targets per item. */
 #define MT_TMA_TILE_W_F64 14
 #define MT_TMA_TILE_W_F32 12
 #define MT_TMA_TILE_H 4

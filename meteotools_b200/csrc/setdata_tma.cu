@@ -131,8 +131,8 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     uint64_t *empty = full + 8;                                               // [8]
     int4 *s_item4 = reinterpret_cast<int4 *>(empty + 8);                      // [4]
     int *s_itemid = reinterpret_cast<int *>(s_item4 + 4);                     // [4]
-    double *lev_s = reinterpret_cast<double *>(s_itemid + 4);                 // [nlev]
-    unsigned char *mono_s = reinterpret_cast<unsigned char *>(lev_s + nlev);  // [2][NC]
+    double *lev_s = reinterpret_cast<double *>(s_itemid + 4);                 // [nlev + 1]
+    unsigned char *mono_s = reinterpret_cast<unsigned char *>(lev_s + nlev + 1);  // [2][NC]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NT = nvar + 1;
@@ -143,7 +143,9 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int l = tid; l < nlev; l += NTHREADS) lev_s[l] = levels[l];
+    // an odd level count is handled as pairs too: the last level is its own partner (the second
+    // half of that pair is computed and never stored)
+    for (int l = tid; l <= nlev; l += NTHREADS) lev_s[l] = levels[min(l, nlev - 1)];
     if (tid < 2 * NC) mono_s[tid] = 1;
     __syncthreads();
 
@@ -256,7 +258,8 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     // consecutive level pairs from (tid / 80) * ppn
     const int c_own = tid % NC, g_own = tid / NC;
     const bool col_thread = tid < NG * NC;
-    const int npair = nlev >> 1, ppn = EXACT ? PP : (npair + NG - 1) / NG, lp_own = g_own * ppn;
+    const int npair = (nlev + 1) >> 1, ppn = EXACT ? PP : (npair + NG - 1) / NG, lp_own = g_own * ppn;
+    const bool wide = ((nlev | (int)o_n) & 1) == 0;   // even rows: 16-byte stores; else two 8-byte stores
     const int o_pitch = (int)o_n;   // output row pitch in elements (host checks that it fits)
     // this thread's brackets (row offsets of the "lo" samples of both levels of a pair, weights)
     int kk[PP];
@@ -440,8 +443,17 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                         if (ter1 > l) r1.x = nan_f64();
                         if (ter1 > l + 1) r1.y = nan_f64();
                     }
-                    __stcs(reinterpret_cast<double2 *>(o0 + l), r0);
-                    if (two) __stcs(reinterpret_cast<double2 *>(o1 + l), r1);
+                    if (EXACT || wide) {
+                        __stcs(reinterpret_cast<double2 *>(o0 + l), r0);
+                        if (two) __stcs(reinterpret_cast<double2 *>(o1 + l), r1);
+                    } else {   // odd level count / odd row pitch: rows are only 8-byte aligned
+                        __stcs(o0 + l, r0.x);
+                        if (l + 1 < nlev) __stcs(o0 + l + 1, r0.y);
+                        if (two) {
+                            __stcs(o1 + l, r1.x);
+                            if (l + 1 < nlev) __stcs(o1 + l + 1, r1.y);
+                        }
+                    }
                     if (ONE_STEP) break;
                 }
             }
@@ -558,7 +570,8 @@ bool make_layout(int dtype, int64_t nz, int64_t nlev, Layout *L)
     }();
     const size_t eb = dtype == MT_F64 ? 8 : 4;
     const size_t stage = ((size_t)NC * nz * eb + 127) & ~size_t(127);
-    const int LP = (int)((nlev % 4 == 2) ? nlev : nlev + 2);  // even; LP = 2 (mod 4): 2-way conflicts at worst
+    const int64_t ne = (nlev + 1) & ~int64_t(1);               // levels rounded up to whole pairs
+    const int LP = (int)((ne % 4 == 2) ? ne : ne + 2);         // even; LP = 2 (mod 4): 2-way conflicts at worst
     const size_t lev_bytes = ((size_t)NC * LP * 8 + 127) & ~size_t(127);
     for (int stages = want; stages >= 2; --stages) {
         size_t off = stage * stages;
@@ -567,7 +580,7 @@ bool make_layout(int dtype, int64_t nz, int64_t nlev, Layout *L)
         const size_t off_meta = off;
         off += (size_t)NMETA * MAXT * sizeof(Meta);
         const size_t off_misc = off;
-        off += 16 * 8 + 4 * 16 + 4 * 4 + (size_t)nlev * 8 + 2 * NC;
+        off += 16 * 8 + 4 * 16 + 4 * 4 + (size_t)(nlev + 1) * 8 + 2 * NC;
         const size_t total = off + 128;  // slack for the 128-byte alignment of the base
         if (total <= 227 * 1024) {
             L->stages = stages, L->stage_bytes = (int)stage, L->LP = LP;
@@ -586,7 +599,7 @@ int supported_impl(int dtype, int64_t nz, int64_t nlev, int64_t row_pitch)
 {
     if (dtype != MT_F64 && dtype != MT_F32) return 0;
     const int64_t eb = dtype == MT_F64 ? 8 : 4;
-    if (nz < 2 || nz > 254 || nlev < 2 || nlev % 2 != 0 || nlev > 2 * NG * PP_LARGE || (row_pitch * eb) % 16 != 0)
+    if (nz < 2 || nz > 254 || nlev < 1 || nlev > 2 * NG * PP_LARGE || (row_pitch * eb) % 16 != 0)
         return 0;
     Layout L;
     if (!make_layout(dtype, nz, nlev, &L)) return 0;
@@ -607,10 +620,10 @@ int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int 
     MT_REQUIRE(direction == 0 || direction == 1, "mt_setdata_tma: direction must be 0 or 1 (decided by the caller "
                                                  "from column (0,0) of the full coordinate array)");
     const int64_t eb = dtype == MT_F64 ? 8 : 4;
-    MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 2 && nlev % 2 == 0 && nlev <= 2 * NG * PP_LARGE && o_n >= nlev &&
-                   o_n % 2 == 0 && o_n < 2147483647LL && n < 2147483647LL,
-               "mt_setdata_tma: need 2 <= nz <= 254, an even number of levels <= %d and an even output pitch",
-               2 * NG * PP_LARGE);
+    MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 1 && nlev <= 2 * NG * PP_LARGE && o_n >= nlev &&
+                   o_n < 2147483647LL && n < 2147483647LL,
+               "mt_setdata_tma: need 2 <= nz <= 254 and 1..%d target levels", 2 * NG * PP_LARGE);
+    const bool wide_rows = nlev % 2 == 0 && o_n % 2 == 0;   // 16-byte stores need 16-byte aligned rows
     MT_REQUIRE(row_pitch >= nx && (row_pitch * eb) % 16 == 0 && ((uintptr_t)vert % 16) == 0,
                "mt_setdata_tma: source rows must be 16-byte aligned (row pitch %lld elements)", (long long)row_pitch);
     Layout L;
@@ -622,8 +635,10 @@ int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int 
     if (rc != MT_OK) return rc;
     OutPtrs op;
     for (int v = 0; v < nvar; ++v) {
-        MT_REQUIRE(fields[v] && out[v] && ((uintptr_t)out[v] % 16 == 0) && ((uintptr_t)fields[v] % 16 == 0),
-                   "mt_setdata_tma: field %d is null or not 16-byte aligned", v);
+        MT_REQUIRE(fields[v] && out[v] && ((uintptr_t)out[v] % (wide_rows ? 16 : 8) == 0) &&
+                       ((uintptr_t)fields[v] % 16 == 0),
+                   "mt_setdata_tma: field %d is null or not aligned (sources 16 bytes, outputs %d)", v,
+                   wide_rows ? 16 : 8);
         rc = tensor_map_for(fields[v], dtype, nz, ny, nx, row_pitch, BY, &P.maps[v + 1]);
         if (rc != MT_OK) return rc;
         P.out[v] = out[v];
@@ -644,7 +659,7 @@ int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int 
     const unsigned grid = (unsigned)grid64;
     const bool rf = (flags & MT_IL_ROUND_F32) != 0, inc = (flags & MT_IL_INCLUSIVE) != 0;
     mt::ProfScope prof("k_setdata_tma", stream);
-    const bool small = nlev <= 2 * NG * PP_SMALL, exact_small = nlev == 2 * NG * PP_SMALL;
+    const bool small = nlev <= 2 * NG * PP_SMALL, exact_small = nlev == 2 * NG * PP_SMALL && wide_rows;
 #define ST_LAUNCH(T, INC, RND, PPV, EX)                                                                              \
     do {                                                                                                           \
         MT_CUDA(cudaFuncSetAttribute(k_setdata_tma<T, INC, RND, PPV, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

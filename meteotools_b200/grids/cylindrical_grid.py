@@ -186,7 +186,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 srcs = [stage(s, use32) for _, s in batch]
                 outs = [self._new() for _ in batch]
                 mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
-                fits = nz <= 254 and self.Nz % 2 == 0 and spline_order == 1
+                fits = nz <= 254 and spline_order == 1
                 if fits and mode == "tma" and lib.mt_setdata_tma_supported(dtype, nz, self.Nz, snx):
                     # one warp-specialised TMA kernel, no intermediate in HBM (csrc/setdata_tma.cu).
                     # It writes target-major, level-fastest rows; a (z, y, x) grid takes them through
@@ -208,7 +208,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                     for (name, _), o in zip(batch, outs):
                         self._put(name, o)
                     continue
-                fits = fits and trz
+                fits = fits and trz and self.Nz % 2 == 0
                 if fits and mode == "fused":   # first-generation fused kernel (cp.async), kept for A/B runs
                     th_ = 2 if os.environ.get("MT_SETDATA_TILE") == "16x2" else 4
                     order_t, items_t, nitems, nflag, counter = self._fused_items_for(plan, 16, th_)

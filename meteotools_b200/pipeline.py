@@ -96,7 +96,7 @@ class CylStepPipeline:
         self.direction = -1
         import os
         mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
-        fits = g.Nz % 2 == 0 and self.nz <= 254
+        fits = self.nz <= 254
         self.mode = "split"
         if fits and mode == "tma" and self.lib.mt_setdata_tma_supported(self.mt_dtype, self.nz, g.Nz,
                                                                           self.region[1]):
@@ -105,7 +105,7 @@ class CylStepPipeline:
             self.f_order, self.f_items, self.f_nitems, self.f_nflag, _ = \
                 g._fused_items_for(self.plan, tw_, th_, max_targets=mt_, spatial=True, align=al_,
                                    org_x=self.region[3])
-        elif fits and mode == "fused":
+        elif fits and g.Nz % 2 == 0 and mode == "fused":
             self.mode = "fused"
             self.tile_h = 2 if os.environ.get("MT_SETDATA_TILE") == "16x2" else 4
             self.f_order, self.f_items, self.f_nitems, self.f_nflag, _ = \

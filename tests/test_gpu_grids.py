@@ -231,7 +231,7 @@ def lib_profile_names(lib, fn):
 
 
 @pytest.mark.parametrize("case", ["pressure", "nonmonotone_inclusive", "resident_odd", "many_vars", "levels72",
-                                  "levels100", "levels_dense", "levels_descending"])
+                                  "levels100", "levels_dense", "levels_descending", "levels_odd", "levels_one"])
 def test_set_data_tma_against_oracle(case, monkeypatch):
     """mt_setdata_tma on shapes the golden file does not hold: decreasing (pressure) coordinate,
     non-monotone columns + the inclusive bracket test, resident device sources with the cylinder
@@ -244,7 +244,8 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
     from meteotools_b200.grids import cylindrical_grid
     monkeypatch.setenv("MT_SETDATA", "tma")
     rng = np.random.default_rng({"pressure": 1, "nonmonotone_inclusive": 2, "resident_odd": 3, "many_vars": 4,
-                                 "levels72": 5, "levels100": 6, "levels_dense": 7, "levels_descending": 8}[case])
+                                 "levels72": 5, "levels100": 6, "levels_dense": 7, "levels_descending": 8,
+                                 "levels_odd": 9, "levels_one": 10}[case])
     nz, ny, nx, dx = 14, 70, 84, 2000.0
     settings = dict(Nr=30, Ntheta=40, Nz=12, dr=1100, dtheta=2 * np.pi / 40, dz=450, z_start=150,
                     r_start=0, theta_start=0, vertical_coord_type="z", dt=300)
@@ -261,6 +262,10 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
         settings.update(Nz=72, dz=95, z_start=40)
     if case == "levels100":
         settings.update(Nz=100, dz=70, z_start=40)
+    if case == "levels_odd":      # odd level count: 8-byte stores, the last level is its own partner
+        settings.update(Nz=61, dz=100, z_start=40)
+    if case == "levels_one":
+        settings.update(Nz=1, dz=100, z_start=2500)
     if case == "levels_dense":
         settings.update(Nz=40, dz=11, z_start=3000)
     if case == "levels_descending":   # height coordinate, levels from the top down: every bracket is searched
@@ -285,7 +290,7 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
     if case not in ("resident_odd", "pressure", "levels_descending"):
         hgt_c = oracle.interp2D_fast(dx, dx, cyl.xTR, cyl.yTR, hgt)
         hidx = co.cyl_terrain_index(hgt_c, cyl.z_start, cyl.dz)
-    if case in ("levels72", "levels100"):
+    if case in ("levels72", "levels100", "levels_odd", "levels_one"):
         import ctypes as ct
         from meteotools_b200 import _lib
         lib = _lib.load()
@@ -296,7 +301,7 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
         lib.mt_profile_fetch(buf, len(buf))
         lib.mt_profile_enable(0)
         names = buf.value.decode()
-        assert ("k_setdata_tma" in names) == (case == "levels72"), names
+        assert ("k_setdata_tma" in names) == (case != "levels100"), names
     for name, a in fields.items():
         levf = oracle.interplevel(a, vert, cyl.z, inclusive=inclusive)
         ref = oracle.interp2D_fast_layers(dx, dx, cyl.xTR, cyl.yTR, levf)
