@@ -110,16 +110,22 @@ def upload_box(a, y0, y1, x0, x1, out=None):
     same dtype, pitch = box_pitch(x1-x0) (valid columns first, the padding is never read), with
     one strided DMA (mt_upload_box_pitched); no host-side crop copy."""
     t = require_cuda()
-    a = np.asarray(a)
-    if a.dtype not in (np.float32, np.float64) or not a.flags.c_contiguous:
-        a = np.ascontiguousarray(a, dtype=np.float64)
-    nz, ny, nx = a.shape
-    pitch = box_pitch(x1 - x0, a.dtype.itemsize)
+    if is_tensor(a):   # a resident source: device-to-device strided copy of its box
+        a = a.contiguous()
+        if a.dtype not in (t.float32, t.float64):
+            a = cast_f64(a)
+        f32, itemsize, src = a.dtype == t.float32, a.element_size(), ct.c_void_p(a.data_ptr())
+    else:
+        a = np.asarray(a)
+        if a.dtype not in (np.float32, np.float64) or not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        f32, itemsize, src = a.dtype == np.float32, a.dtype.itemsize, ct.c_void_p(a.ctypes.data)
+    nz, ny, nx = (int(v) for v in a.shape)
+    pitch = box_pitch(x1 - x0, itemsize)
     if out is None:
-        out = t.empty((nz, y1 - y0, pitch), dtype=t.float32 if a.dtype == np.float32 else t.float64,
-                      device="cuda")
+        out = t.empty((nz, y1 - y0, pitch), dtype=t.float32 if f32 else t.float64, device="cuda")
     assert tuple(out.shape) == (nz, y1 - y0, pitch), (tuple(out.shape), (nz, y1 - y0, pitch))
-    _lib.check(_lib.load().mt_upload_box_pitched(ct.c_void_p(a.ctypes.data), a.dtype.itemsize, nz, ny, nx, y0, y1,
+    _lib.check(_lib.load().mt_upload_box_pitched(src, itemsize, nz, ny, nx, y0, y1,
                                                  x0, x1, ptr(out), pitch, stream()), "mt_upload_box_pitched")
     out._mt_keepalive = a   # the async DMA reads `a` until the stream reaches this point
     return out

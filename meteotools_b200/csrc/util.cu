@@ -88,6 +88,8 @@ int mt_permute3(const double *src, double *dst, int64_t n0, int64_t n1, int64_t 
 
 }  // extern "C"
 
+// (The source may also be a DEVICE array: set_data stages the box of a resident source whose rows are
+// not 16-byte aligned -- an odd nx of float64 -- so that the TMA kernel can read it.)
 // Strided host->device upload of the column box [y0,y1)x[x0,x1) of a C-order (nz,ny,nx) HOST
 // array into a dense (nz, y1-y0, x1-x0) device array: one cudaMemcpy3DAsync (DMA straight from
 // the caller's buffer -- at PCIe speed when it is pinned), no host-side crop copy.
@@ -104,7 +106,7 @@ extern "C" int mt_upload_box(const void *host, int elem_bytes, int64_t nz, int64
     p.dstPtr = make_cudaPitchedPtr(dev, (size_t)(x1 - x0) * elem_bytes, (size_t)(x1 - x0) * elem_bytes, (size_t)(y1 - y0));
     p.dstPos = make_cudaPos(0, 0, 0);
     p.extent = make_cudaExtent((size_t)(x1 - x0) * elem_bytes, (size_t)(y1 - y0), (size_t)nz);
-    p.kind = cudaMemcpyHostToDevice;
+    p.kind = cudaMemcpyDefault;   // host (pinned or pageable) or device source: decided from the pointer
     MT_CUDA(cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
     return MT_OK;
 }
@@ -124,7 +126,7 @@ extern "C" int mt_upload_box_pitched(const void *host, int elem_bytes, int64_t n
                                    (size_t)(y1 - y0));
     p.dstPos = make_cudaPos(0, 0, 0);
     p.extent = make_cudaExtent((size_t)(x1 - x0) * elem_bytes, (size_t)(y1 - y0), (size_t)nz);
-    p.kind = cudaMemcpyHostToDevice;
+    p.kind = cudaMemcpyDefault;   // host (pinned or pageable) or device source: decided from the pointer
     MT_CUDA(cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
     return MT_OK;
 }

@@ -151,15 +151,22 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         n = xd.numel()
         plan = self._plan_for(dx, dy, nx, ny)
         trz = self._layout == _lib.MT_LAYOUT_TRZ
-        if on_dev:   # resident sources: region = the full array
+        # resident sources are used in place (region = the full array) unless their rows are not
+        # 16-byte aligned for some field (odd nx): then the box is staged device-to-device like a
+        # host source, so that the TMA kernel can still read it
+        in_place = on_dev and all((nx * (4 if is_f32(a) else 8)) % 16 == 0 for a in [vert] + list(sources))
+        if in_place:
             sny, snx, oy, ox = ny, nx, 0, 0
-        else:        # host sources: region = the box, rows padded to D.box_pitch (never read)
+        else:        # region = the box, rows padded to D.box_pitch (never read)
             sny, snx, oy, ox = y1 - y0, D.box_pitch(x1 - x0), y0, x0
 
         def stage(a, want32):
-            if on_dev:
+            if on_dev and in_place:
                 a = a.contiguous()
                 return a if (is_f32(a) and want32) else D.cast_f64(a)
+            if on_dev:
+                b = D.upload_box(a, y0, y1, x0, x1)
+                return b if (is_f32(a) and want32) else D.cast_f64(b)
             a = np.asarray(a)
             if a.dtype == np.float32 and not want32:
                 return D.cast_f64(D.upload_box(a, y0, y1, x0, x1))

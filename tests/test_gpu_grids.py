@@ -231,7 +231,8 @@ def lib_profile_names(lib, fn):
 
 
 @pytest.mark.parametrize("case", ["pressure", "nonmonotone_inclusive", "resident_odd", "many_vars", "levels72",
-                                  "levels100", "levels_dense", "levels_descending", "levels_odd", "levels_one"])
+                                  "levels100", "levels_dense", "levels_descending", "levels_odd", "levels_one",
+                                  "resident_oddnx"])
 def test_set_data_tma_against_oracle(case, monkeypatch):
     """mt_setdata_tma on shapes the golden file does not hold: decreasing (pressure) coordinate,
     non-monotone columns + the inclusive bracket test, resident device sources with the cylinder
@@ -245,8 +246,10 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
     monkeypatch.setenv("MT_SETDATA", "tma")
     rng = np.random.default_rng({"pressure": 1, "nonmonotone_inclusive": 2, "resident_odd": 3, "many_vars": 4,
                                  "levels72": 5, "levels100": 6, "levels_dense": 7, "levels_descending": 8,
-                                 "levels_odd": 9, "levels_one": 10}[case])
+                                 "levels_odd": 9, "levels_one": 10, "resident_oddnx": 11}[case])
     nz, ny, nx, dx = 14, 70, 84, 2000.0
+    if case == "resident_oddnx":   # rows of a resident float64 source not 16-byte aligned: the box is staged
+        nx = 85
     settings = dict(Nr=30, Ntheta=40, Nz=12, dr=1100, dtheta=2 * np.pi / 40, dz=450, z_start=150,
                     r_start=0, theta_start=0, vertical_coord_type="z", dt=300)
     hgt = 900.0 * rng.random((ny, nx))
@@ -279,15 +282,23 @@ def test_set_data_tma_against_oracle(case, monkeypatch):
     cx, cy = (33 * dx + 517.0, 34 * dx + 1311.0) if case != "resident_odd" else (nx * dx - 35e3, 34.5e3)
     cyl.set_horizontal_location(cx, cy)
     kw = dict(fields)
-    if case == "resident_odd":
+    if case in ("resident_odd", "resident_oddnx"):
+        from meteotools_b200 import _lib as _l
+        _l.load().mt_profile_enable(1)
         cyl.set_data(dx, dx, torch.from_numpy(vert).cuda(), inclusive=inclusive,
                      **{k_: torch.from_numpy(v).cuda() for k_, v in kw.items()})
+        torch.cuda.synchronize()
+        import ctypes as _ct
+        _buf = _ct.create_string_buffer(1 << 16)
+        _l.load().mt_profile_fetch(_buf, len(_buf))
+        _l.load().mt_profile_enable(0)
+        assert "k_setdata_tma" in _buf.value.decode(), _buf.value.decode()
     elif case in ("pressure", "levels_descending"):
         cyl.set_data(dx, dx, vert, inclusive=inclusive, **kw)
     else:
         cyl.set_data(dx, dx, vert, inclusive=inclusive, hgt=hgt, **kw)
     hidx = None
-    if case not in ("resident_odd", "pressure", "levels_descending"):
+    if case not in ("resident_odd", "resident_oddnx", "pressure", "levels_descending"):
         hgt_c = oracle.interp2D_fast(dx, dx, cyl.xTR, cyl.yTR, hgt)
         hidx = co.cyl_terrain_index(hgt_c, cyl.z_start, cyl.dz)
     if case in ("levels72", "levels100", "levels_odd", "levels_one"):
