@@ -395,6 +395,9 @@ int mt_smooth_pass(const double *v0, const double *cur, double *out, int64_t n0,
 /* ---- staging helpers used by the host-facing wrappers -----------------------------------------
  * out[i] = in[i] as double (f32 -> f64 upcast on the device; exact). */
 int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream);
+/* float64 -> float32, round to nearest (what the reference's netCDF cache stores: 'f4',
+ * grids/grid_general.py:119-129): for results that leave the device as float32. */
+int mt_cast_f64_f32(const double *in, float *out, int64_t n, mt_stream_t stream);
 /* dense 3-D permutation copy: dst (memory order b0,b1,b2) <- src (a0,a1,a2) with
  * dst[i,j,k] = src[...] given src element strides for dst's index order. */
 int mt_permute3(const double *src, double *dst, int64_t n0, int64_t n1, int64_t n2, int64_t s0,

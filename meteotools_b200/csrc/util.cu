@@ -14,6 +14,16 @@ k_cast_f32_f64(const float *__restrict__ in, double *__restrict__ out, int64_t n
         out[i] = (double)__ldg(in + i);
 }
 
+// float64 -> float32 (round to nearest, what NumPy's astype and the reference's netCDF cache 'f4'
+// write do): results that leave the device as float32 take half the PCIe bytes.
+__global__ void __launch_bounds__(256)
+k_cast_f64_f32(const double *__restrict__ in, float *__restrict__ out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)__ldg(in + i);
+}
+
 // dst is dense (n0, n1, n2); dst[i,j,k] = src[i*s0 + j*s1 + k*s2].
 // Tiles of 32x32 over (the axis that is contiguous in src) x (k); generic fallback otherwise.
 __global__ void __launch_bounds__(256)
@@ -66,6 +76,16 @@ int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream)
     if (n == 0) return MT_OK;
     mt::ProfScope prof("k_cast_f32_f64", stream);
     k_cast_f32_f64<<<mt::grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+int mt_cast_f64_f32(const double *in, float *out, int64_t n, mt_stream_t stream)
+{
+    MT_REQUIRE(in && out && n >= 0, "mt_cast_f64_f32: bad arguments");
+    if (n == 0) return MT_OK;
+    mt::ProfScope prof("k_cast_f64_f32", stream);
+    k_cast_f64_f32<<<mt::grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(in, out, n);
     MT_LAUNCH_CHECK();
     return MT_OK;
 }

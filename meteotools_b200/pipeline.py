@@ -325,10 +325,14 @@ class TimeStepStream:
         ts = TimeStepStream(grid, (nz, ny, nx), dx, dy, names3d, names2d=("f",), outputs=[...])
         for k, result in ts.process(steps):      # steps: iterable of dict(z3d=, vars3d=, f=, hgt=)
             ...                                  # result: dict name -> (Nz, Ntheta, Nr) ndarray
+
+    ``out_dtype=np.float32``: the results are rounded to float32 on the device (as the reference's
+    netCDF cache does when it stores them, grid_general.py:119-129) and travel as float32: half the
+    download, which is what bounds the stream.  The default keeps the reference's float64 arrays.
     """
 
     def __init__(self, grid, src_shape, dx, dy, names3d, names2d=("f",), hgt=True, outputs=None,
-                 dtype=np.float64, dyn_outputs=None, slots=3):
+                 dtype=np.float64, dyn_outputs=None, slots=3, out_dtype=np.float64):
         t = D.require_cuda()
         self.t = t
         self.outputs = list(outputs) if outputs is not None else list(_lib.TD_OUT)
@@ -338,8 +342,15 @@ class TimeStepStream:
                                    td_outputs=[o for o in self.outputs if o in _lib.TD_OUT] or None,
                                    dyn_outputs=dyn_outputs, resident=False)
             pool = {**pipe.out3d, **pipe.td_out, **pipe.dyn_out}
-            host = {k: t.empty(pool[k].shape, dtype=pool[k].dtype, pin_memory=True) for k in self.outputs}
-            self.slots.append(dict(pipe=pipe, pool=pool, host=host, stream=t.cuda.Stream(), event=None, key=None))
+            self.out32 = np.dtype(out_dtype) == np.float32
+            narrow = {}
+            if self.out32:   # float64 results are narrowed on the device before the download
+                narrow = {k: t.empty(pool[k].shape, dtype=t.float32, device="cuda") for k in self.outputs
+                          if pool[k].dtype == t.float64}
+            host = {k: t.empty(pool[k].shape, dtype=narrow[k].dtype if k in narrow else pool[k].dtype,
+                               pin_memory=True) for k in self.outputs}
+            self.slots.append(dict(pipe=pipe, pool=pool, host=host, narrow=narrow, stream=t.cuda.Stream(),
+                                   event=None, key=None))
 
     def _collect(self, slot):
         slot["event"].synchronize()
@@ -366,7 +377,12 @@ class TimeStepStream:
                 slot["pipe"].upload(step["z3d"], step["vars3d"], v2d)
                 slot["pipe"].run()
                 for k, h in slot["host"].items():
-                    h.copy_(slot["pool"][k], non_blocking=True)
+                    src = slot["pool"][k]
+                    if k in slot["narrow"]:
+                        _lib.check(slot["pipe"].lib.mt_cast_f64_f32(D.ptr(src), D.ptr(slot["narrow"][k]), src.numel(),
+                                                                    D.stream()), "mt_cast_f64_f32")
+                        src = slot["narrow"][k]
+                    h.copy_(src, non_blocking=True)
                 ev = self.t.cuda.Event()
                 ev.record(slot["stream"])
             slot["event"], slot["key"] = ev, key

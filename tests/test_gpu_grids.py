@@ -443,6 +443,30 @@ def test_time_step_stream_matches_grid_api(golden_setdata):
     assert seen == list(range(5))
 
 
+def test_time_step_stream_float32_results(golden_setdata):
+    """out_dtype=float32: the same results, rounded to float32 on the device (what astype does)."""
+    from meteotools_b200.grids import cylindrical_grid
+    from meteotools_b200.pipeline import TimeStepStream
+    g = golden_setdata
+    dx = float(g["s_dx"])
+    src = dict(z3d=g["s_z3d"], f=g["s_f"], hgt=g["s_hgt"],
+               vars3d=dict(T=g["s_T"] + 280.0, p=1e5 * np.exp(-g["s_z3d"] / 8000.0),
+                           qv=1e-3 + 1e-4 * np.abs(g["s_u"])))
+    outs = ["Th", "Tc", "rho"]
+    res = {}
+    for od in (np.float64, np.float32):
+        cyl = cylindrical_grid(dict(SD))
+        cyl.set_horizontal_location(float(g["s_cx"]), float(g["s_cy"]))
+        ts = TimeStepStream(cyl, g["s_z3d"].shape, dx, dx, ["T", "p", "qv"], names2d=("f",), hgt=True, outputs=outs,
+                            out_dtype=od)
+        for _, r in ts.process([src, src]):
+            res[od] = {k: v.copy() for k, v in r.items()}
+    for k in outs:
+        assert res[np.float32][k].dtype == np.float32
+        with np.errstate(all="ignore"):
+            assert_same(res[np.float32][k], res[np.float64][k].astype(np.float32), f"float32 results {k}")
+
+
 def test_time_step_stream_float32_sources(golden_setdata):
     """float32 host sources are staged as float32 (half the PCIe bytes), widened in the
     kernel, and give exactly what the grid API gives for the same float32 arrays (wrf-python's
