@@ -398,6 +398,13 @@ int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream)
 /* float64 -> float32, round to nearest (what the reference's netCDF cache stores: 'f4',
  * grids/grid_general.py:119-129): for results that leave the device as float32. */
 int mt_cast_f64_f32(const double *in, float *out, int64_t n, mt_stream_t stream);
+/* The rows mt_setdata_tma writes (n targets x nlev levels, level-fastest) -> the (z, y, x) layout of
+ * a Cartesian grid, all variables of a set_data call in ONE launch: out[v][k*n + i] = rows[v][i*nlev + k],
+ * and, when z and hgt are given, NaN where z[k] <= hgt[i] (the reference's terrain mask,
+ * grids/cartesian_grid.py:127-136, otherwise a separate pass per variable).  nvar <= MT_MAX_VARS,
+ * nlev <= 96; z and hgt are both NULL or both set. */
+int mt_rows_to_levels(const double *const *rows, double *const *out, int nvar, int64_t n, int64_t nlev,
+                      const double *z, const double *hgt, mt_stream_t stream);
 /* dense 3-D permutation copy: dst (memory order b0,b1,b2) <- src (a0,a1,a2) with
  * dst[i,j,k] = src[...] given src element strides for dst's index order. */
 int mt_permute3(const double *src, double *dst, int64_t n0, int64_t n1, int64_t n2, int64_t s0,

@@ -299,7 +299,10 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             int K = 0;
             double ww_prev = 0.0;
             bool have_prev = false;
-            auto bracket = [&](double want, int &klo, double &w2) {
+            // Two passes: (1) the rows of all the thread's levels (a dependent chain of shared-memory
+            // loads: search, then walk), (2) their weights -- 2 * PP independent divisions that
+            // overlap instead of one division at the end of every walk.
+            auto find_row = [&](double want, int &klo) {
                 int kp = -1;
                 if (is_mono) {
                     const double ww = sgn * want;
@@ -331,24 +334,32 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                         }
                     }
                 }
-                w2 = nan_f64();
-                klo = klo_missing;
-                if (kp >= 0) {
-                    klo = kp - im;
-                    const double vlo = (double)vt[klo * NC], vhi = (double)vt[klo * NC + dhi];
-                    w2 = (want - vlo) / (vhi - vlo);
-                }
+                klo = kp >= 0 ? kp - im : klo_missing;
+                return kp >= 0;
             };
+            unsigned found = 0;
 #pragma unroll
             for (int i = 0; i < PP; ++i) {
                 const int lp = lp_own + i;
                 int k0 = klo_missing, k1 = klo_missing;
-                wx[i] = wy[i] = nan_f64();
                 if (EXACT || (i < ppn && lp < npair)) {
-                    bracket(lev_s[2 * lp], k0, wx[i]);
-                    bracket(lev_s[2 * lp + 1], k1, wy[i]);
+                    if (find_row(lev_s[2 * lp], k0)) found |= 1u << (2 * i);
+                    if (find_row(lev_s[2 * lp + 1], k1)) found |= 2u << (2 * i);
                 }
                 kk[i] = (k0 * NC) | ((k1 * NC) << 16);   // nz <= 254: k * 80 < 65536
+            }
+            // missing bracket: the weight is NaN (the quotient of two valid rows is computed and dropped)
+#pragma unroll
+            for (int i = 0; i < PP; ++i) {
+                const int lp = lp_own + i;
+                const bool act = EXACT || (i < ppn && lp < npair);
+                const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;
+                const double want0 = act ? lev_s[2 * lp] : 0.0, want1 = act ? lev_s[2 * lp + 1] : 0.0;
+                const double a0 = (double)vt[ka], a1 = (double)vt[ka + dhi];
+                const double b0 = (double)vt[kb], b1 = (double)vt[kb + dhi];
+                const double q0 = (want0 - a0) / (a1 - a0), q1 = (want1 - b0) / (b1 - b0);
+                wx[i] = (found >> (2 * i)) & 1u ? q0 : nan_f64();
+                wy[i] = (found >> (2 * i + 1)) & 1u ? q1 : nan_f64();
             }
         }
         if (tid < NC) mono_s[((n + 1) & 1) * NC + tid] = 1;

@@ -66,6 +66,49 @@ k_permute3_t02(const double *__restrict__ src, double *__restrict__ dst, int64_t
     }
 }
 
+
+// Batched (targets, levels) -> (levels, targets) transpose of the rows mt_setdata_tma writes, for a
+// (z, y, x) grid, with the Cartesian terrain mask (z[k] <= hgt[i] -> NaN, cartesian_grid.py:127-136)
+// applied on the way: ONE launch for all variables of a set_data call instead of one transpose and
+// one masking pass per variable.  A tile = 32 consecutive targets x all levels: contiguous in the
+// source (flat coalesced read), 256-byte segments per level in the destination.
+struct RowsToLevels {
+    const double *rows[MT_MAX_VARS];
+    double *out[MT_MAX_VARS];
+};
+constexpr int RTL_TGT = 32, RTL_MAXLEV = 96;
+
+__global__ void __launch_bounds__(256)
+k_rows_to_levels(RowsToLevels P, int nvar, int64_t n, int nlev, const double *__restrict__ z,
+                 const double *__restrict__ hgt)
+{
+    __shared__ double tile[RTL_TGT][RTL_MAXLEV + 1];
+    __shared__ double z_s[RTL_MAXLEV];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (z && tid < nlev) z_s[tid] = z[tid];
+    const int64_t ntile = (n + RTL_TGT - 1) / RTL_TGT, nwork = ntile * nvar;
+    for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int v = (int)(w % nvar);           // the variables of a tile back to back: hgt stays in L1
+        const int64_t i0 = (w / nvar) * RTL_TGT;
+        const int cnt = (int)min((int64_t)RTL_TGT, n - i0);
+        const double *__restrict__ src = P.rows[v] + i0 * nlev;
+        __syncthreads();
+        for (int e = tid; e < cnt * nlev; e += 256) {
+            const int r = e / nlev;
+            tile[r][e - r * nlev] = __ldcs(src + e);
+        }
+        __syncthreads();
+        if (lane < cnt) {
+            const double h = z ? __ldg(hgt + i0 + lane) : 0.0;
+            double *__restrict__ dst = P.out[v] + i0 + lane;
+            for (int k = warp; k < nlev; k += 8) {
+                double val = tile[lane][k];
+                if (z && z_s[k] <= h) val = mt::nan_f64();
+                __stcs(dst + (int64_t)k * n, val);
+            }
+        }
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -86,6 +129,24 @@ int mt_cast_f64_f32(const double *in, float *out, int64_t n, mt_stream_t stream)
     if (n == 0) return MT_OK;
     mt::ProfScope prof("k_cast_f64_f32", stream);
     k_cast_f64_f32<<<mt::grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+int mt_rows_to_levels(const double *const *rows, double *const *out, int nvar, int64_t n, int64_t nlev,
+                      const double *z, const double *hgt, mt_stream_t stream)
+{
+    MT_REQUIRE(rows && out && nvar >= 1 && nvar <= MT_MAX_VARS && n > 0 && nlev >= 1 && nlev <= RTL_MAXLEV,
+               "mt_rows_to_levels: need 1..%d variables and 1..%d levels", MT_MAX_VARS, RTL_MAXLEV);
+    MT_REQUIRE((z == nullptr) == (hgt == nullptr), "mt_rows_to_levels: z and hgt go together");
+    RowsToLevels P;
+    for (int v = 0; v < nvar; ++v) {
+        MT_REQUIRE(rows[v] && out[v] && rows[v] != out[v], "mt_rows_to_levels: variable %d: null or in place", v);
+        P.rows[v] = rows[v], P.out[v] = out[v];
+    }
+    const int64_t nwork = (n + RTL_TGT - 1) / RTL_TGT * nvar;
+    mt::ProfScope prof("k_rows_to_levels", stream);
+    k_rows_to_levels<<<mt::grid_for(nwork, 1, 8), 256, 0, (cudaStream_t)stream>>>(P, nvar, n, (int)nlev, z, hgt);
     MT_LAUNCH_CHECK();
     return MT_OK;
 }

@@ -90,7 +90,15 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
                             spline_order=vertical_interp_order)
         if 'hgt' in self.varlist2D:
             self.set_terrain()
-            self.terrain_mask_vars()
+            self.terrain_mask_vars(skip=self.__dict__.pop('_masked_in_setdata', ()))
+
+    def _fused_terrain_mask(self, names):
+        """The variables of this set_data call are masked (z <= hgt -> NaN, :127-136) inside the
+        batched transpose of ``_setdata3d``; ``terrain_mask_vars`` then only visits the others."""
+        if 'hgt' not in self.varlist2D:
+            return None
+        self.__dict__.setdefault('_masked_in_setdata', set()).update(names)
+        return D.to_device(self.z), self.device('hgt')
 
     def set_terrain(self):  # :127-131 (the mask itself is applied by the kernel)
         pass
@@ -99,11 +107,13 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
     def terrain_mask(self):
         return self.z.reshape(-1, 1, 1) <= np.asarray(self.hgt)[None]
 
-    def terrain_mask_vars(self):  # :134-136
+    def terrain_mask_vars(self, skip=()):  # :134-136
         lib = _lib.load()
         n = self.Ny * self.Nx
         zd, hd = D.to_device(self.z), self.device('hgt')
         for varname in self.varlist3D:
+            if varname in skip:      # masked already by the transpose of this set_data call
+                continue
             t = self.device(varname)
             self._fields[varname].host = None
             _lib.check(lib.mt_terrain_mask_car(D.ptr(t), self.Nz, n, n, 1, D.ptr(zd), D.ptr(hd), D.stream()),

@@ -209,7 +209,14 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                                                   D.ptr(items_t), nitems, nflag, D.ptr(hgt_idx),
                                                   D.ptr_array(rows), self.Nz, flags, D.ptr(counter),
                                                   D.stream()), 'mt_setdata_tma')
-                    if not trz:
+                    if not trz and self.Nz <= 96:
+                        # (z, y, x) grid: one batched transpose for the whole batch, the Cartesian
+                        # terrain mask applied on the way when the grid has a terrain height
+                        zh = self._fused_terrain_mask([nm for nm, _ in batch])
+                        _lib.check(lib.mt_rows_to_levels(D.ptr_array(rows), D.ptr_array(outs), len(batch), n, self.Nz,
+                                                         D.ptr(zh[0]) if zh else None, D.ptr(zh[1]) if zh else None,
+                                                         D.stream()), 'mt_rows_to_levels')
+                    elif not trz:
                         n1, n2 = self._grid_shape3()[1:]
                         outs = [D.permute3(r_, (self.Nz, n1, n2), (1, n2 * self.Nz, self.Nz)) for r_ in rows]
                     for (name, _), o in zip(batch, outs):
@@ -241,6 +248,11 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                     raise ValueError("Error on input data")
                 for (name, _), o in zip(batch, outs):
                     self._put(name, o)
+
+    def _fused_terrain_mask(self, names):
+        """(z, hgt) device arrays when the transpose of a (z, y, x) grid should mask terrain on the way
+        (Cartesian grids only; this grid masks by level index inside the kernel)."""
+        return None
 
     def _plan_for(self, dx, dy, nx, ny):
         """Per-target stencil (indices + weights), built once per (grid location, source grid)."""

@@ -176,6 +176,60 @@ def test_fuzz_cyl_set_data(seed):
         assert_same(getattr(cyl, name), ref, f"seed {seed} {name} nz={nz} Nz={Nz} src=({ny},{nx}) f32={f32}")
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_car_set_data(seed):
+    """cartesian_grid.set_data on random geometries: the TMA kernel's rows go through ONE batched
+    transpose that also applies the terrain mask (mt_rows_to_levels) -- against the oracle pipeline
+    interplevel -> interp2D_fast_layers -> z <= hgt mask (cartesian_grid.py:127-136).  Target counts
+    that are not multiples of the 32-target tile, odd level counts, 1..5 variables, float32 sources,
+    resident tensors, and a variable set by an EARLIER call that the later call's terrain must mask too."""
+    import torch
+    from meteotools_b200.grids import cartesian_grid
+    rng = np.random.default_rng(900 + seed)
+    nz = int(rng.integers(3, 41))
+    ny, nx = int(rng.integers(40, 120)), int(rng.integers(40, 120))
+    dx = float(rng.choice([2000.0, 1000.0, 3000.0]))
+    Nz = int(rng.integers(2, 41))
+    Ny, Nx = int(rng.integers(3, 45)), int(rng.integers(3, 45))
+    ztop = 12000.0
+    dxt = float(min(rng.choice([700.0, 1500.0, 2500.0]), (nx - 5) * dx / Nx, (ny - 5) * dx / Ny))
+    car = cartesian_grid(dict(Nx=Nx, Ny=Ny, Nz=Nz, dx=dxt, dy=dxt, dz=float(ztop * 0.9 / Nz),
+                              z_start=float(rng.choice([0.0, 50.0, 200.0])), vertical_coord_type="z",
+                              SOR_parameter=1.9, max_iteration_times=10, iteration_tolerance=0.05))
+    hx, hy = Nx * dxt / 2 + dx, Ny * dxt / 2 + dx
+    cx = float(hx + rng.random() * ((nx - 1) * dx - 2 * hx))
+    cy = float(hy + rng.random() * ((ny - 1) * dx - 2 * hy))
+    car.set_horizontal_location(cx, cy)
+    hgt = 900.0 * rng.random((ny, nx))
+    k = np.arange(nz).reshape(-1, 1, 1)
+    z3d = hgt[None] + (ztop - hgt[None]) * (k / (nz - 1)) ** 1.4
+    nvar = int(rng.integers(1, 6))
+    f32 = seed % 4 == 3
+    dt_ = np.float32 if f32 else np.float64
+    fields = {f"v{i}": (rng.standard_normal((nz, ny, nx)) * 5 + 0.001 * z3d).astype(dt_) for i in range(nvar)}
+    vert = z3d.astype(dt_)
+    resident = seed % 3 == 1
+    dev = (lambda a: torch.from_numpy(a).cuda()) if resident else (lambda a: a)
+    with_hgt = seed % 5 != 4
+    two_calls = seed % 2 == 0 and nvar >= 2
+    kw = {k_: dev(v) for k_, v in fields.items()}
+    if two_calls:      # v0 first, without terrain; the second call brings hgt and must mask v0 as well
+        first = {"v0": kw.pop("v0")}
+        car.set_data(dx, dx, dev(vert), **first)
+    if with_hgt:
+        car.set_data(dx, dx, dev(vert), hgt=dev(hgt), **kw)
+    else:
+        car.set_data(dx, dx, dev(vert), **kw)
+    hgt_c = oracle.interp2D_fast(dx, dx, car.xTR, car.yTR, hgt) if with_hgt else None
+    for name, a in fields.items():
+        ref = oracle.interp2D_fast_layers(dx, dx, car.xTR, car.yTR, oracle.interplevel(a, vert, car.z))
+        if with_hgt:
+            ref = np.where(car.z.reshape(-1, 1, 1) <= hgt_c[None], np.nan, ref)
+        got = getattr(car, name)
+        assert got.shape == (Nz, Ny, Nx)
+        assert_same(got, ref, f"seed {seed} {name} nz={nz} grid=({Nz},{Ny},{Nx}) f32={f32} two_calls={two_calls}")
+
+
 DYN_EXACT_CYL = ["vr", "vt", "wind_speed", "Tv", "rho", "coriolis_force", "centrifugal_force", "radial_PG_force",
                  "agradient_force", "kinetic_energy", "zeta_r", "zeta_t", "zeta_z", "abs_zeta_z", "div_hori", "div",
                  "density_factor", "shear_deform", "stretch_deform", "strain_region"]
