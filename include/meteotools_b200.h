@@ -238,6 +238,15 @@ int mt_upload_box_pitched(const void *host, int elem_bytes, int64_t nz, int64_t 
  * var[k,j,i] = NaN where z[k] <= hgt[j,i]. */
 int mt_terrain_index_cyl(const double *hgt, int64_t nt, int64_t nr, double z_start, double dz,
                          int32_t *hgt_idx, mt_stream_t stream);
+/* The 2-D part of a cylindrical set_data step in one launch: out2d[f][i] = bilinear interpolation of the
+ * C-order (ny, nx) field src2d[f] at target i through the plan of mt_interp2d_plan (the same indices and
+ * weights as interp2D_fast, fastcompute.f90:9-58; flagged targets get the sentinel / NaN), f < nfield <= 4;
+ * when hgt_field >= 0 that field's result also gives hgt_idx exactly as mt_terrain_index_cyl does
+ * (cylindrical_grid.py:141-170; the fix-up runs in the last block to finish: `ticket` is one int32 that
+ * is zero before the first launch and is left zero).  Targets are the nt x nr grid in C order. */
+int mt_cyl_prelude(const double *const *src2d, double *const *out2d, int nfield, int64_t ny, int64_t nx,
+                   const int32_t *plan_ix, const double *plan_w, int64_t nt, int64_t nr, int hgt_field,
+                   double z_start, double dz, int32_t *hgt_idx, int32_t *ticket, mt_stream_t stream);
 int mt_terrain_mask_cyl(double *var, int64_t nz, int64_t n, int64_t s_z, int64_t s_n,
                         const int32_t *hgt_idx, mt_stream_t stream);
 int mt_terrain_mask_car(double *var, int64_t nz, int64_t n, int64_t s_z, int64_t s_n,

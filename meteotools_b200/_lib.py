@@ -147,6 +147,8 @@ _SIGS = {
     "mt_azimuthal_mean": (c_int, [c_vp, ct.POINTER(mt_grid_t), c_vp, c_vp, c_vp]),
     "mt_cast_f32_f64": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mt_cast_f64_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "mt_cyl_prelude": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_dbl,
+                       c_vp, c_vp, c_vp]),
     "mt_rows_to_levels": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mt_permute3": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "mt_upload_box": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),

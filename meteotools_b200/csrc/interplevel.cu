@@ -325,7 +325,7 @@ __global__ void k_terrain_index(const double *__restrict__ hgt, int64_t n, doubl
 
 // edge / corner fix-up of cylindrical_grid.py:141-163, one block.  The four edges only read
 // interior neighbours (independent of each other); the corners read the UPDATED edges.
-__global__ void k_terrain_fix(int32_t *__restrict__ h, int nt, int nr)
+__device__ __forceinline__ void terrain_fix_block(volatile int32_t *h, int nt, int nr)
 {
 #define H(t, r) h[(int64_t)(t) * nr + (r)]
     for (int r = 1 + threadIdx.x; r < nr - 1; r += blockDim.x) {
@@ -351,6 +351,55 @@ __global__ void k_terrain_fix(int32_t *__restrict__ h, int nt, int nr)
         H(nt - 1, nr - 1) = max(H(nt - 1, nr - 1), max(H(nt - 2, nr - 1), H(nt - 1, nr - 2)));
     }
 #undef H
+}
+
+__global__ void k_terrain_fix(int32_t *h, int nt, int nr) { terrain_fix_block(h, nt, nr); }
+
+// The 2-D part of a cylindrical set_data step in ONE launch (it was four: two bilinear launches,
+// the index, its fix-up -- 23 us of launch-latency-bound kernels in a 0.49 ms step): the 2-D fields
+// through the plan (interp2D_fast, fastcompute.f90:9-58 -- the plan holds exactly the indices and
+// weights k_interp2d_pt derives), the terrain index of field `hgt_field` (cylindrical_grid.py:167-169)
+// and, by the last block to finish, the edge / corner fix-up (:141-163).
+struct Prelude2D {
+    const double *src[4];
+    double *out[4];
+};
+__global__ void __launch_bounds__(256)
+k_cyl_prelude(Prelude2D P, int nfield, int64_t nx, const int4 *__restrict__ pix, const double2 *__restrict__ pw,
+              int64_t n, int nt, int nr, int hgt_field, double z_start, double dz, int32_t *idx, int32_t *ticket)
+{
+    __shared__ int s_last;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 ix = pix[i];
+        const double2 w = pw[i];
+        const int64_t a00 = ix.z * nx + ix.x, a10 = ix.z * nx + ix.y, a01 = ix.w * nx + ix.x, a11 = ix.w * nx + ix.y;
+        for (int f = 0; f < nfield; ++f) {
+            double v;
+            if (ix.x < 0) {
+                v = (ix.x == -1) ? MT_SENTINEL : nan_f64();
+            } else {
+                const double *__restrict__ sp = P.src[f];
+                const double t0 = (sp[a10] - sp[a00]) * w.x + sp[a00];   // fastcompute.f90:100
+                const double t1 = (sp[a11] - sp[a01]) * w.x + sp[a01];   // :101
+                v = (t1 - t0) * w.y + t0;                                // :102
+            }
+            P.out[f][i] = v;
+            if (f == hgt_field) {
+                const double q = np_floor_divide(v - z_start, dz) + 1.0;
+                const int32_t k = isnan(q) ? INT32_MIN : (int32_t)q;  // NaN -> INT_MIN like x86 cvttsd2si
+                idx[i] = k < 0 ? 0 : k;
+            }
+        }
+    }
+    if (hgt_field < 0) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    terrain_fix_block(idx, nt, nr);
+    if (threadIdx.x == 0) *ticket = 0;   // ready for the next launch
 }
 
 __global__ void k_terrain_mask_cyl(double *__restrict__ var, int nz, int64_t n, int64_t s_z,
@@ -562,6 +611,28 @@ int mt_terrain_index_cyl(const double *hgt, int64_t nt, int64_t nr, double z_sta
                                                                                   dz, hgt_idx);
     MT_LAUNCH_CHECK();
     k_terrain_fix<<<1, 1024, 0, (cudaStream_t)stream>>>(hgt_idx, (int)nt, (int)nr);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+int mt_cyl_prelude(const double *const *src2d, double *const *out2d, int nfield, int64_t ny, int64_t nx,
+                   const int32_t *plan_ix, const double *plan_w, int64_t nt, int64_t nr, int hgt_field,
+                   double z_start, double dz, int32_t *hgt_idx, int32_t *ticket, mt_stream_t stream)
+{
+    MT_REQUIRE(src2d && out2d && plan_ix && plan_w && nfield >= 1 && nfield <= 4, "mt_cyl_prelude: 1..4 fields");
+    MT_REQUIRE(fits_int(ny) && fits_int(nx) && nt >= 2 && nr >= 2 && fits_int(nt) && fits_int(nr),
+               "mt_cyl_prelude: bad extents");
+    MT_REQUIRE(hgt_field < nfield && (hgt_field < 0 || (hgt_idx && ticket)),
+               "mt_cyl_prelude: hgt_field needs hgt_idx and a zero-initialised ticket");
+    Prelude2D P;
+    for (int f = 0; f < nfield; ++f) {
+        MT_REQUIRE(src2d[f] && out2d[f], "mt_cyl_prelude: field %d is null", f);
+        P.src[f] = src2d[f], P.out[f] = out2d[f];
+    }
+    mt::ProfScope prof("k_cyl_prelude", stream);
+    k_cyl_prelude<<<mt::grid_for(nt * nr, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        P, nfield, nx, reinterpret_cast<const int4 *>(plan_ix), reinterpret_cast<const double2 *>(plan_w), nt * nr,
+        (int)nt, (int)nr, hgt_field, z_start, dz, hgt_idx, ticket);
     MT_LAUNCH_CHECK();
     return MT_OK;
 }

@@ -112,6 +112,10 @@ class CylStepPipeline:
                 g._fused_items_for(self.plan, 16, self.tile_h)
         # the work-item counter is per pipeline: pipelines of one grid may run on different streams
         self.f_counter = t.zeros((1,), dtype=t.int32, device="cuda")
+        # the 2-D part of the step (bilinear of the 2-D fields, terrain index + fix-up) is one launch
+        self.f_ticket = t.zeros((1,), dtype=t.int32, device="cuda")
+        self._keys2d = list(self.out2d)
+        self._out2d_ptrs = D.ptr_array([self.out2d[k] for k in self._keys2d]) if self._keys2d else None
         if not resident:   # persistent device staging for the uploaded boxes
             shp = (self.nz, y1 - y0, self.region[1])
             self.stage3d = {k: t.empty(shp, dtype=self.t_dtype, device="cuda") for k in self.names3d}
@@ -149,6 +153,7 @@ class CylStepPipeline:
         self._src3d = [vars3d[k] for k in self.names3d]
         self._src2d = vars2d
         self._src_ptrs = D.ptr_array(self._src3d)
+        self._src2d_ptrs = D.ptr_array([vars2d[k] for k in self._keys2d]) if self._keys2d else None
 
     def _build_structs(self):
         g = self.g
@@ -176,13 +181,19 @@ class CylStepPipeline:
         lib, g, s = self.lib, self.g, D.stream()
         y0, y1, x0, x1 = self.box
         sny, snx, oy, ox = self.region
-        for k, o in self.out2d.items():   # 2-D fields: bilinear only
-            _lib.check(lib.mt_interp2d_layers(D.ptr(self._src2d[k]), 1, self.ny, self.nx, 0, self.nx, 1,
-                                              self.dx, self.dy, D.ptr(self.xd), D.ptr(self.yd), self.n,
-                                              D.ptr(o), 0, 1, s), "mt_interp2d_layers")
-        if self.has_hgt:
-            _lib.check(lib.mt_terrain_index_cyl(D.ptr(self.out2d["hgt"]), g.Ntheta, g.Nr, g.z_start, g.dz,
-                                                D.ptr(self.hgt_idx), s), "mt_terrain_index_cyl")
+        if 1 <= len(self._keys2d) <= 4:   # 2-D fields (bilinear only) + terrain index: one launch
+            _lib.check(lib.mt_cyl_prelude(self._src2d_ptrs, self._out2d_ptrs, len(self._keys2d), self.ny, self.nx,
+                                          D.ptr(self.plan[0]), D.ptr(self.plan[1]), g.Ntheta, g.Nr,
+                                          self._keys2d.index("hgt") if self.has_hgt else -1, g.z_start, g.dz,
+                                          D.ptr(self.hgt_idx), D.ptr(self.f_ticket), s), "mt_cyl_prelude")
+        else:
+            for k, o in self.out2d.items():
+                _lib.check(lib.mt_interp2d_layers(D.ptr(self._src2d[k]), 1, self.ny, self.nx, 0, self.nx, 1,
+                                                  self.dx, self.dy, D.ptr(self.xd), D.ptr(self.yd), self.n,
+                                                  D.ptr(o), 0, 1, s), "mt_interp2d_layers")
+            if self.has_hgt:
+                _lib.check(lib.mt_terrain_index_cyl(D.ptr(self.out2d["hgt"]), g.Ntheta, g.Nr, g.z_start, g.dz,
+                                                    D.ptr(self.hgt_idx), s), "mt_terrain_index_cyl")
         if self.mode == "tma":
             _lib.check(lib.mt_setdata_tma(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype,
                                           self.nz, sny, snx, snx, oy, ox, D.ptr(self.levels), g.Nz, self.direction,
