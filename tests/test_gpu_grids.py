@@ -499,3 +499,83 @@ def test_time_step_stream_float32_sources(golden_setdata):
             assert_same(res[name], getattr(ref, name), f"step {k} {name}")
         n += 1
     assert n == 3
+
+
+@pytest.mark.parametrize("n,nlev,nvar,mask", [(1, 1, 1, False), (31, 7, 2, True), (32, 60, 3, True), (1000, 96, 16, False),
+                                              (4097, 61, 5, True)])
+def test_rows_to_levels_abi(n, nlev, nvar, mask):
+    """mt_rows_to_levels through the C ABI: out[v][k, i] = rows[v][i, k], NaN where z[k] <= hgt[i]
+    (cartesian_grid.py:127-136); target counts off the 32-target tile, 1 and 96 levels, 16 variables,
+    NaN already present in the rows."""
+    import torch
+    from meteotools_b200 import _device as D, _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n * 131 + nlev)
+    rows = [rng.standard_normal((n, nlev)) for _ in range(nvar)]
+    rows[0][rng.random((n, nlev)) < 0.05] = np.nan
+    z = np.sort(rng.random(nlev)) * 3000.0
+    hgt = rng.random(n) * 2000.0
+    if n > 2:
+        hgt[1] = z[nlev // 2]          # equality masks (<=)
+    d_rows = [torch.from_numpy(r).cuda() for r in rows]
+    d_out = [torch.full((nlev, n), -7.0, dtype=torch.float64, device="cuda") for _ in range(nvar)]
+    dz, dh = torch.from_numpy(z).cuda(), torch.from_numpy(hgt).cuda()
+    _lib.check(lib.mt_rows_to_levels(D.ptr_array(d_rows), D.ptr_array(d_out), nvar, n, nlev,
+                                     D.ptr(dz) if mask else None, D.ptr(dh) if mask else None, D.stream()),
+               "mt_rows_to_levels")
+    for r, o in zip(rows, d_out):
+        ref = r.T.copy()
+        if mask:
+            ref = np.where(z[:, None] <= hgt[None, :], np.nan, ref)
+        assert_same(o.cpu().numpy(), ref, f"rows_to_levels n={n} nlev={nlev}")
+    # contract errors: too many levels, z without hgt
+    assert lib.mt_rows_to_levels(D.ptr_array(d_rows), D.ptr_array(d_out), nvar, n, 97, None, None, D.stream()) != 0
+    assert lib.mt_rows_to_levels(D.ptr_array(d_rows), D.ptr_array(d_out), nvar, n, nlev, D.ptr(dz), None,
+                                 D.stream()) != 0
+    assert b"mt_rows_to_levels" in lib.mt_last_error()
+
+
+@pytest.mark.parametrize("nt,nr,with_hgt", [(2, 2, True), (5, 3, True), (48, 40, True), (360, 300, True), (37, 11, False)])
+def test_cyl_prelude_abi(nt, nr, with_hgt):
+    """mt_cyl_prelude (one launch) == mt_interp2d_layers per field + mt_terrain_index_cyl (index and the
+    edge / corner fix-up by the last block), bit for bit, launched repeatedly (the ticket is left zero);
+    NaN targets get the flagged fill values."""
+    import torch
+    from meteotools_b200 import _device as D, _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(nt * 1000 + nr)
+    ny, nx, dx = 57, 64, 2000.0
+    n = nt * nr
+    xs = rng.random(n) * (nx - 1) * dx
+    ys = rng.random(n) * (ny - 1) * dx
+    xs[0], ys[0] = 3 * dx, 5 * dx               # exactly on a node
+    if n > 6:
+        xs[5] = np.nan
+        ys[5] = np.nan
+    xd, yd = torch.from_numpy(xs).cuda(), torch.from_numpy(ys).cuda()
+    fields = [rng.standard_normal((ny, nx)), 1500.0 * rng.random((ny, nx)), rng.standard_normal((ny, nx))]
+    src = [torch.from_numpy(f).cuda() for f in fields]
+    ix = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+    w = torch.empty((n, 2), dtype=torch.float64, device="cuda")
+    _lib.check(lib.mt_interp2d_plan(D.ptr(xd), D.ptr(yd), n, dx, dx, nx, ny, D.ptr(ix), D.ptr(w), D.stream()), "plan")
+    z_start, dz = 100.0, 300.0
+    ref = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in fields]
+    for s_, o in zip(src, ref):
+        _lib.check(lib.mt_interp2d_layers(D.ptr(s_), 1, ny, nx, 0, nx, 1, dx, dx, D.ptr(xd), D.ptr(yd), n, D.ptr(o), 0, 1,
+                                          D.stream()), "mt_interp2d_layers")
+    ref_idx = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(lib.mt_terrain_index_cyl(D.ptr(ref[1]), nt, nr, z_start, dz, D.ptr(ref_idx), D.stream()), "terrain")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for rep in range(3):
+        out = [torch.full((n,), -1.0, dtype=torch.float64, device="cuda") for _ in fields]
+        idx = torch.full((n,), -5, dtype=torch.int32, device="cuda")
+        _lib.check(lib.mt_cyl_prelude(D.ptr_array(src), D.ptr_array(out), len(src), ny, nx, D.ptr(ix), D.ptr(w), nt, nr,
+                                      1 if with_hgt else -1, z_start, dz, D.ptr(idx) if with_hgt else None,
+                                      D.ptr(ticket) if with_hgt else None, D.stream()), "mt_cyl_prelude")
+        for o, r in zip(out, ref):
+            assert_same(o.cpu().numpy(), r.cpu().numpy(), f"prelude field rep {rep}")
+        if with_hgt:
+            assert np.array_equal(idx.cpu().numpy(), ref_idx.cpu().numpy())
+            assert int(ticket.item()) == 0
+    assert lib.mt_cyl_prelude(D.ptr_array(src), D.ptr_array(out), 5, ny, nx, D.ptr(ix), D.ptr(w), nt, nr, -1, z_start, dz,
+                              None, None, D.stream()) != 0
