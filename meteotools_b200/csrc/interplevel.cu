@@ -156,12 +156,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <typename T, bool INCLUSIVE>
+// LM = level-major output (the layout wrf.interplevel returns: out[lev*o_lev + cy*o_y + cx], columns
+// contiguous): warps over levels, lanes over the tile's columns, bracket tables stored [lev][TC];
+// otherwise the dense level-fastest rows [column][nlev]: warps over columns, lanes over levels.
+template <typename T, bool INCLUSIVE, bool LM>
 __global__ void __launch_bounds__(256)
 k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz, int64_t ny, int64_t nx,
                    int64_t y0, int64_t x0, int by, int bx, const double *__restrict__ levels, int nlev,
                    int levels_order, int direction, int round_f32, int TC, int off_w2, int off_lev,
-                   int off_kp, int off_mono, int off_col)
+                   int off_kp, int off_mono, int off_col, int64_t o_lev, int64_t o_y)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int pitch = TC + 1;
@@ -171,6 +174,7 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
     unsigned char *kps = smem_raw + off_kp;                                      // [TC][nlev]
     unsigned char *mono_s = smem_raw + off_mono;                                 // [TC]
     long long *coloff = reinterpret_cast<long long *>(smem_raw + off_col);       // [TC]
+    long long *outoff = coloff + TC;                                             // [TC] (LM only)
     const int tile_elems = nz * pitch;
     const int tc_shift = __ffs(TC) - 1;  // TC is a power of two
 
@@ -193,6 +197,8 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
             const int64_t c = c0 + tid;
             const int64_t cy = c / bx;
             coloff[tid] = (y0 + cy) * nx + (x0 + (c - cy * bx));
+            if (LM) outoff[tid] = cy * o_y + (c - cy * bx);
+            mono_s[tid] = 1;
         }
         __syncthreads();
         // t = 0: coordinate, t = v+1: variable v.  Consecutive threads copy consecutive columns
@@ -211,56 +217,71 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
         cp_async_wait<1>();
         __syncthreads();
         const T *vt = tiles;  // coordinate tile
-        if (tid < tc) {       // monotone (in the chosen direction) per column
-            bool mono = true;
-            double prev = sgn * (double)vt[tid];
-            for (int k = 1; k < nz; ++k) {
-                const double cur = sgn * (double)vt[k * pitch + tid];
-                mono = mono && (cur >= prev);
-                prev = cur;
-            }
-            mono_s[tid] = mono ? 1 : 0;
+        // (column, level group) ownership for the column phases: thread -> column tid % TC and the
+        // `per` consecutive levels from (tid / TC) * per -- the decomposition of k_setdata_tma
+        const int j_own = tid & (TC - 1), g_own = tid >> tc_shift, ngrp = nthr >> tc_shift;
+        if (j_own < tc) {   // monotone (in the chosen direction) per column: 1/ngrp of the rows each
+            const int rows = (nz - 1 + ngrp - 1) / ngrp;
+            const int k0 = g_own * rows, k1 = min(k0 + rows, nz - 1);
+            bool ok = true;
+            for (int k = k0; k < k1; ++k)
+                ok = ok && (sgn * (double)vt[(k + 1) * pitch + j_own] >= sgn * (double)vt[k * pitch + j_own]);
+            if (!ok) mono_s[j_own] = 0;
         }
         __syncthreads();
-        // bracket every (column, level) pair: a warp per column, lanes over the levels (no integer
-        // division in the hot loops: ncu showed this kernel issue-bound, 54 % issue slots)
-        for (int j = warp; j < tc; j += nwarps)
-        for (int lev = lane; lev < nlev; lev += 32) {
-            const int e = j * nlev + lev;
-            const double want = lev_s[lev];
-            int kp = -1;
-            if (mono_s[j]) {
-                const double ww = sgn * want;  // upper bound: first K with vv[K] > ww
-                int lo = 0, hi = nz;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (sgn * (double)vt[mid * pitch + j] > ww) hi = mid;
-                    else lo = mid + 1;
-                }
-                const int K = lo;
-                if (K >= 1 && K <= nz - 1) {
-                    if (INCLUSIVE) kp = K;
-                    else if (sgn * (double)vt[(K - 1) * pitch + j] < ww) kp = K;
-                } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * pitch + j] == ww) {
-                    kp = nz - 1;
-                }
-            } else {
-                for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
-                    const double vlo = (double)vt[(q - im) * pitch + j], vhi = (double)vt[(q - ip) * pitch + j];
-                    const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
-                    if (hit) {
-                        kp = q;
-                        break;
+        // brackets of the thread's levels: one binary search, then the bracket WALKS forward while
+        // the levels ascend along the coordinate (the upper bound K = first row with v[K] > want
+        // only moves forward); any other order searches again.  Non-monotone columns: the literal
+        // scan.
+        if (j_own < tc) {
+            const int per = (nlev + ngrp - 1) / ngrp;
+            const int l0 = g_own * per, l1 = min(l0 + per, nlev);
+            const bool is_mono = mono_s[j_own] != 0;
+            int K = 0;
+            double ww_prev = 0.0;
+            bool have_prev = false;
+            for (int lev = l0; lev < l1; ++lev) {
+                const double want = lev_s[lev];
+                int kp = -1;
+                if (is_mono) {
+                    const double ww = sgn * want;  // upper bound: first K with vv[K] > ww
+                    if (have_prev && ww >= ww_prev) {
+                        while (K < nz && sgn * (double)vt[K * pitch + j_own] <= ww) ++K;
+                    } else {
+                        int lo = 0, hi = nz;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sgn * (double)vt[mid * pitch + j_own] > ww) hi = mid;
+                            else lo = mid + 1;
+                        }
+                        K = lo;
+                    }
+                    ww_prev = ww, have_prev = true;
+                    if (K >= 1 && K <= nz - 1) {
+                        if (INCLUSIVE) kp = K;
+                        else if (sgn * (double)vt[(K - 1) * pitch + j_own] < ww) kp = K;
+                    } else if (INCLUSIVE && K == nz && sgn * (double)vt[(nz - 1) * pitch + j_own] == ww) {
+                        kp = nz - 1;
+                    }
+                } else {
+                    for (int q = nz - 1; q >= 1; --q) {  // literal DINTERP3DZ scan from the top
+                        const double vlo = (double)vt[(q - im) * pitch + j_own], vhi = (double)vt[(q - ip) * pitch + j_own];
+                        const bool hit = INCLUSIVE ? (vlo <= want && vhi >= want) : (vlo < want && vhi > want);
+                        if (hit) {
+                            kp = q;
+                            break;
+                        }
                     }
                 }
+                double w2 = 0.0;
+                if (kp >= 0) {
+                    const double vlo = (double)vt[(kp - im) * pitch + j_own], vhi = (double)vt[(kp - ip) * pitch + j_own];
+                    w2 = (want - vlo) / (vhi - vlo);
+                }
+                const int e = LM ? lev * TC + j_own : j_own * nlev + lev;
+                kps[e] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
+                w2s[e] = w2;
             }
-            double w2 = 0.0;
-            if (kp >= 0) {
-                const double vlo = (double)vt[(kp - im) * pitch + j], vhi = (double)vt[(kp - ip) * pitch + j];
-                w2 = (want - vlo) / (vhi - vlo);
-            }
-            kps[e] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
-            w2s[e] = w2;
         }
         for (int v = 0; v < nvar; ++v) {
             const int t = v + 1;
@@ -273,21 +294,28 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
             }
             __syncthreads();  // tile t has landed for every thread
             const T *ft = tiles + (t & 1) * tile_elems;
-            double *__restrict__ o = ptrs.out[v] + c0 * nlev;
-            for (int j = warp; j < tc; j += nwarps)
-            for (int lev = lane; lev < nlev; lev += 32) {
-                const int e = j * nlev + lev;
+            auto value = [&](int e, int j) {
                 const int kp = kps[e];
-                double r;
-                if (kp == 255) {
-                    r = nan_f64();
-                } else {
+                double r = nan_f64();
+                if (kp != 255) {
                     const double w2 = w2s[e];
                     const double w1 = 1.0 - w2;
                     r = w1 * (double)ft[(kp - im) * pitch + j] + w2 * (double)ft[(kp - ip) * pitch + j];
                     if (round_f32) r = (double)(float)r;
                 }
-                o[e] = r;
+                return r;
+            };
+            if (LM) {   // a level's columns are contiguous in the output: lanes over columns
+                double *__restrict__ o = ptrs.out[v];
+                for (int lev = warp; lev < nlev; lev += nwarps)
+                    for (int j = lane; j < tc; j += 32) __stcs(o + lev * o_lev + outoff[j], value(lev * TC + j, j));
+            } else {
+                double *__restrict__ o = ptrs.out[v] + c0 * nlev;
+                for (int j = warp; j < tc; j += nwarps)
+                    for (int lev = lane; lev < nlev; lev += 32) {
+                        const int e = j * nlev + lev;
+                        o[e] = value(e, j);
+                    }
             }
         }
     }
@@ -482,7 +510,9 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
     const int rf = (flags & MT_IL_ROUND_F32) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     // hot path: dense level-fastest box output -> shared-memory tiled kernel
-    if (o_lev == 1 && o_x == nlev && o_y == (int64_t)bx * nlev && nz <= 254) {
+    const bool rows_lf = o_lev == 1 && o_x == nlev && o_y == (int64_t)bx * nlev;
+    const bool level_major = !rows_lf && o_x == 1;   // what wrf.interplevel returns: (nlev, ny, nx)
+    if ((rows_lf || level_major) && nz <= 254) {
         const size_t eb = dtype == MT_F64 ? 8 : 4;
         struct Lay { size_t w2, lev, kp, mono, col, total; };
         auto layout = [&](int tc) {
@@ -493,7 +523,7 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
             L.kp = L.lev + (size_t)nlev * 8;
             L.mono = L.kp + (size_t)tc * nlev;
             L.col = (L.mono + tc + 7) & ~size_t(7);
-            L.total = L.col + (size_t)tc * 8;
+            L.total = L.col + 2 * (size_t)tc * 8;
             return L;
         };
         int TC = 64;
@@ -504,13 +534,18 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
             const int ctas = (int)(220 * 1024 / L.total);
             const unsigned grid_t = mt::grid_for(ntiles, 1, ctas < 1 ? 1 : (ctas > 8 ? 8 : ctas));
             mt::ProfScope prof("k_interplevel_tile", stream);
-#define ILT_LAUNCH(T, INC)                                                                                  \
+#define ILT_LAUNCH2(T, INC, LMV)                                                                            \
     do {                                                                                                    \
-        MT_CUDA(cudaFuncSetAttribute(k_interplevel_tile<T, INC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        MT_CUDA(cudaFuncSetAttribute(k_interplevel_tile<T, INC, LMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)L.total));                                                        \
-        k_interplevel_tile<T, INC><<<grid_t, 256, L.total, s>>>(                                            \
+        k_interplevel_tile<T, INC, LMV><<<grid_t, 256, L.total, s>>>(                                       \
             p, nvar, vert, (int)nz, ny, nx, y0, x0, by, bx, levels, (int)nlev, levels_order, direction, rf,  \
-            TC, (int)L.w2, (int)L.lev, (int)L.kp, (int)L.mono, (int)L.col);                                 \
+            TC, (int)L.w2, (int)L.lev, (int)L.kp, (int)L.mono, (int)L.col, o_lev, o_y);                     \
+    } while (0)
+#define ILT_LAUNCH(T, INC)                      \
+    do {                                        \
+        if (level_major) ILT_LAUNCH2(T, INC, true); \
+        else ILT_LAUNCH2(T, INC, false);        \
     } while (0)
             if (dtype == MT_F64) {
                 if (flags & MT_IL_INCLUSIVE) ILT_LAUNCH(double, true);
@@ -520,6 +555,7 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
                 else ILT_LAUNCH(float, false);
             }
 #undef ILT_LAUNCH
+#undef ILT_LAUNCH2
             MT_LAUNCH_CHECK();
             return MT_OK;
         }
