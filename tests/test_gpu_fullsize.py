@@ -103,6 +103,31 @@ def test_S2_set_data_full_size():
         assert 0.005 < np.isnan(ref).mean() < 0.2
 
 
+def test_S2_cartesian_set_data_and_full_domain_interplevel():
+    """The same 1000 x 1000 x 60 source onto a Cartesian (60, 400, 400) grid (TMA kernel + the batched
+    transpose with the terrain mask fused), and interpolation.interplevel over ALL 10^6 columns in the
+    level-major layout wrf.interplevel returns (tile kernel, walking brackets) -- one variable each,
+    bit for bit against the CPU pipeline."""
+    import bench
+    from meteotools_b200.grids import cartesian_grid
+    from meteotools_b200.interpolation import interplevel
+    step = bench.make_step(11, pinned=False)
+    car = cartesian_grid(dict(Nx=400, Ny=400, Nz=60, dx=1500, dy=1500, dz=300, z_start=100, vertical_coord_type="z",
+                              SOR_parameter=1.9, max_iteration_times=10, iteration_tolerance=0.05))
+    c = ((bench.NX + 1) / 2 - 1) * bench.DX
+    car.set_horizontal_location(c, c)
+    car.set_data(bench.DX, bench.DX, step["z3d"], hgt=step["hgt"], T=step["vars3d"]["T"])
+    lev = oracle.interplevel(step["vars3d"]["T"], step["z3d"], car.z)
+    got_lev = interplevel(step["vars3d"]["T"], step["z3d"], car.z)
+    assert got_lev.shape == lev.shape == (60, bench.NY, bench.NX)
+    assert_same(np.asarray(got_lev), lev, "full-domain interplevel")
+    hgt_c = oracle.interp2D_fast(bench.DX, bench.DX, car.xTR, car.yTR, step["hgt"])
+    ref = oracle.interp2D_fast_layers(bench.DX, bench.DX, car.xTR, car.yTR, lev)
+    ref = np.where(car.z.reshape(-1, 1, 1) <= hgt_c[None], np.nan, ref)
+    assert_same(car.T, ref, "S2 Cartesian T")
+    assert 0.001 < np.isnan(ref).mean() < 0.3
+
+
 def test_S5_car_d_properties_and_slab():
     """80 x 2000 x 2000 (2.56 GB per field, 74 GB in flight): linear fields give exactly constant
     derivatives, and a y-slab is checked bit for bit against the numpy oracle."""
