@@ -13,6 +13,8 @@
 // the ascending target levels (O(nz+nlev)): for such a column the first bracket from the top is
 // the only bracket, so the result is identical.  Non-monotone columns and unsorted level lists
 // take the literal scan.  Only the bounding box of the horizontal targets is processed.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -159,8 +161,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // LM = level-major output (the layout wrf.interplevel returns: out[lev*o_lev + cy*o_y + cx], columns
 // contiguous): warps over levels, lanes over the tile's columns, bracket tables stored [lev][TC];
 // otherwise the dense level-fastest rows [column][nlev]: warps over columns, lanes over levels.
-template <typename T, bool INCLUSIVE, bool LM>
-__global__ void __launch_bounds__(256)
+// RB (level-major, 32-column tiles, <= 64 levels): the thread that brackets (column, level block) is
+// also the one that produces those outputs for every variable, so its brackets stay in REGISTERS --
+// no bracket tables in shared memory (5 -> 3 LSU operations per output, 15 KB less shared memory).
+template <typename T, bool INCLUSIVE, bool LM, bool RB>
+__global__ void __launch_bounds__(256, RB ? 4 : 5)   // RB: 64 registers (four resident CTAs); otherwise 48
 k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz, int64_t ny, int64_t nx,
                    int64_t y0, int64_t x0, int by, int bx, const double *__restrict__ levels, int nlev,
                    int levels_order, int direction, int round_f32, int TC, int off_w2, int off_lev,
@@ -233,14 +238,18 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
         // the levels ascend along the coordinate (the upper bound K = first row with v[K] > want
         // only moves forward); any other order searches again.  Non-monotone columns: the literal
         // scan.
+        constexpr int RBQ = 8;   // levels per thread in RB mode: 8 level blocks of <= 8 levels
+        int kpr[RB ? RBQ : 1];
+        double w2r[RB ? RBQ : 1];
+        const int per = (nlev + ngrp - 1) / ngrp;
+        const int l0 = g_own * per, l1 = min(l0 + per, nlev);
         if (j_own < tc) {
-            const int per = (nlev + ngrp - 1) / ngrp;
-            const int l0 = g_own * per, l1 = min(l0 + per, nlev);
             const bool is_mono = mono_s[j_own] != 0;
             int K = 0;
             double ww_prev = 0.0;
             bool have_prev = false;
-            for (int lev = l0; lev < l1; ++lev) {
+            auto do_level = [&](int q) {
+                const int lev = l0 + q;
                 const double want = lev_s[lev];
                 int kp = -1;
                 if (is_mono) {
@@ -278,9 +287,20 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
                     const double vlo = (double)vt[(kp - im) * pitch + j_own], vhi = (double)vt[(kp - ip) * pitch + j_own];
                     w2 = (want - vlo) / (vhi - vlo);
                 }
-                const int e = LM ? lev * TC + j_own : j_own * nlev + lev;
-                kps[e] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
-                w2s[e] = w2;
+                if (RB) {
+                    kpr[RB ? q : 0] = kp >= 0 ? kp : 255, w2r[RB ? q : 0] = w2;
+                } else {
+                    const int e = LM ? lev * TC + j_own : j_own * nlev + lev;
+                    kps[e] = kp >= 0 ? (unsigned char)kp : (unsigned char)255;
+                    w2s[e] = w2;
+                }
+            };
+            if (RB) {
+#pragma unroll
+                for (int q = 0; q < RBQ; ++q)
+                    if (l0 + q < l1) do_level(q);
+            } else {
+                for (int q = 0; l0 + q < l1; ++q) do_level(q);
             }
         }
         for (int v = 0; v < nvar; ++v) {
@@ -305,7 +325,23 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
                 }
                 return r;
             };
-            if (LM) {   // a level's columns are contiguous in the output: lanes over columns
+            if (RB) {   // brackets from registers: the thread's own (column, level block)
+                double *__restrict__ o = ptrs.out[v] + outoff[j_own < tc ? j_own : 0];
+#pragma unroll
+                for (int q = 0; q < RBQ; ++q) {
+                    const int lev = l0 + q;
+                    if (j_own < tc && lev < l1) {
+                        double r = nan_f64();
+                        if (kpr[q] != 255) {
+                            const double w2 = w2r[q];
+                            const double w1 = 1.0 - w2;
+                            r = w1 * (double)ft[(kpr[q] - im) * pitch + j_own] + w2 * (double)ft[(kpr[q] - ip) * pitch + j_own];
+                            if (round_f32) r = (double)(float)r;
+                        }
+                        __stcs(o + lev * o_lev, r);
+                    }
+                }
+            } else if (LM) {   // a level's columns are contiguous in the output: lanes over columns
                 double *__restrict__ o = ptrs.out[v];
                 for (int lev = warp; lev < nlev; lev += nwarps)
                     for (int j = lane; j < tc; j += 32) __stcs(o + lev * o_lev + outoff[j], value(lev * TC + j, j));
@@ -515,37 +551,46 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
     if ((rows_lf || level_major) && nz <= 254) {
         const size_t eb = dtype == MT_F64 ? 8 : 4;
         struct Lay { size_t w2, lev, kp, mono, col, total; };
+        bool regb = false;   // register brackets: no tables
         auto layout = [&](int tc) {
             Lay L;
             size_t b = 2 * (size_t)nz * (tc + 1) * eb;
             L.w2 = (b + 15) & ~size_t(15);
-            L.lev = L.w2 + (size_t)tc * nlev * 8;
+            L.lev = L.w2 + (regb ? 0 : (size_t)tc * nlev * 8);
             L.kp = L.lev + (size_t)nlev * 8;
-            L.mono = L.kp + (size_t)tc * nlev;
+            L.mono = L.kp + (regb ? 0 : (size_t)tc * nlev);
             L.col = (L.mono + tc + 7) & ~size_t(7);
             L.total = L.col + 2 * (size_t)tc * 8;
             return L;
         };
         int TC = 64;
         while (TC > 8 && layout(TC).total > 56 * 1024) TC >>= 1;   // >= 4 CTAs per SM
+        static const bool no_regb = getenv("MT_IL_NO_REGB") && getenv("MT_IL_NO_REGB")[0] == '1';   // A/B runs
+        if (level_major && nlev <= 64 && !no_regb) {
+            regb = true;
+            if (layout(32).total <= 56 * 1024) TC = 32;
+            else regb = false;
+        }
         const Lay L = layout(TC);
         if (L.total <= 200 * 1024) {
             const int64_t ntiles = ((int64_t)by * bx + TC - 1) / TC;
             const int ctas = (int)(220 * 1024 / L.total);
-            const unsigned grid_t = mt::grid_for(ntiles, 1, ctas < 1 ? 1 : (ctas > 8 ? 8 : ctas));
+            // resident CTAs per SM: by shared memory, and 4 by registers (launch bounds) in the register-bracket mode
+            const unsigned grid_t = mt::grid_for(ntiles, 1, ctas < 1 ? 1 : (ctas > (regb ? 4 : 8) ? (regb ? 4 : 8) : ctas));
             mt::ProfScope prof("k_interplevel_tile", stream);
-#define ILT_LAUNCH2(T, INC, LMV)                                                                            \
+#define ILT_LAUNCH2(T, INC, LMV, RBV)                                                                       \
     do {                                                                                                    \
-        MT_CUDA(cudaFuncSetAttribute(k_interplevel_tile<T, INC, LMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        MT_CUDA(cudaFuncSetAttribute(k_interplevel_tile<T, INC, LMV, RBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)L.total));                                                        \
-        k_interplevel_tile<T, INC, LMV><<<grid_t, 256, L.total, s>>>(                                       \
+        k_interplevel_tile<T, INC, LMV, RBV><<<grid_t, 256, L.total, s>>>(                                  \
             p, nvar, vert, (int)nz, ny, nx, y0, x0, by, bx, levels, (int)nlev, levels_order, direction, rf,  \
             TC, (int)L.w2, (int)L.lev, (int)L.kp, (int)L.mono, (int)L.col, o_lev, o_y);                     \
     } while (0)
 #define ILT_LAUNCH(T, INC)                      \
     do {                                        \
-        if (level_major) ILT_LAUNCH2(T, INC, true); \
-        else ILT_LAUNCH2(T, INC, false);        \
+        if (regb) ILT_LAUNCH2(T, INC, true, true);           \
+        else if (level_major) ILT_LAUNCH2(T, INC, true, false); \
+        else ILT_LAUNCH2(T, INC, false, false);              \
     } while (0)
             if (dtype == MT_F64) {
                 if (flags & MT_IL_INCLUSIVE) ILT_LAUNCH(double, true);
