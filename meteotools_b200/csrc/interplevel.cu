@@ -169,10 +169,12 @@ __global__ void __launch_bounds__(256, RB ? 4 : 5)   // RB: 64 registers (four r
 k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz, int64_t ny, int64_t nx,
                    int64_t y0, int64_t x0, int by, int bx, const double *__restrict__ levels, int nlev,
                    int levels_order, int direction, int round_f32, int TC, int off_w2, int off_lev,
-                   int off_kp, int off_mono, int off_col, int64_t o_lev, int64_t o_y)
+                   int off_kp, int off_mono, int off_col, int64_t o_lev, int64_t o_y, int vec2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int pitch = TC + 1;
+    // level-major modes read a tile row with lanes over its columns: dense rows (pitch TC) are conflict-free
+    // whatever rows the lanes' brackets point to, and 16-byte aligned for the paired copies
+    const int pitch = LM ? TC : TC + 1;
     T *tiles = reinterpret_cast<T *>(smem_raw);                                  // [2][nz][pitch]
     double *w2s = reinterpret_cast<double *>(smem_raw + off_w2);                 // [TC][nlev]
     double *lev_s = reinterpret_cast<double *>(smem_raw + off_lev);              // [nlev]
@@ -211,9 +213,20 @@ k_interplevel_tile(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz,
         auto prefetch = [&](int t) {
             const T *src = reinterpret_cast<const T *>(t == 0 ? vert : ptrs.field[t - 1]);
             T *dst = tiles + (t & 1) * tile_elems;
-            for (int e = tid; e < nz * TC; e += nthr) {
-                const int k = e >> tc_shift, j = e & (TC - 1);
-                if (j < tc) cp_async_elem(dst + k * pitch + j, src + (int64_t)k * plane + coloff[j]);
+            if (LM && vec2) {   // two columns per copy (16 bytes): the host checked that pairs are aligned and never straddle a row
+                for (int e = tid; e < nz * (TC >> 1); e += nthr) {
+                    const int k = e >> (tc_shift - 1), j = (e & ((TC >> 1) - 1)) << 1;
+                    if (j < tc) {
+                        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + k * pitch + j);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (int64_t)k * plane + coloff[j])
+                                     : "memory");
+                    }
+                }
+            } else {
+                for (int e = tid; e < nz * TC; e += nthr) {
+                    const int k = e >> tc_shift, j = e & (TC - 1);
+                    if (j < tc) cp_async_elem(dst + k * pitch + j, src + (int64_t)k * plane + coloff[j]);
+                }
             }
             cp_async_commit();
         };
@@ -572,6 +585,11 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
             else regb = false;
         }
         const Lay L = layout(TC);
+        // 16-byte tile copies (level-major modes, float64): every even box column must sit on a 16-byte
+        // boundary of its array and have its right neighbour in the same box row
+        int vec2 = level_major && dtype == MT_F64 && x0 % 2 == 0 && nx % 2 == 0 && bx % 2 == 0 && TC >= 2 &&
+                   (uintptr_t)vert % 16 == 0;
+        for (int v = 0; v < nvar && vec2; ++v) vec2 = (uintptr_t)fields[v] % 16 == 0;
         if (L.total <= 200 * 1024) {
             const int64_t ntiles = ((int64_t)by * bx + TC - 1) / TC;
             const int ctas = (int)(220 * 1024 / L.total);
@@ -584,7 +602,7 @@ int mt_interplevel(const void *const *fields, int nvar, const void *vert, int dt
                                      (int)L.total));                                                        \
         k_interplevel_tile<T, INC, LMV, RBV><<<grid_t, 256, L.total, s>>>(                                  \
             p, nvar, vert, (int)nz, ny, nx, y0, x0, by, bx, levels, (int)nlev, levels_order, direction, rf,  \
-            TC, (int)L.w2, (int)L.lev, (int)L.kp, (int)L.mono, (int)L.col, o_lev, o_y);                     \
+            TC, (int)L.w2, (int)L.lev, (int)L.kp, (int)L.mono, (int)L.col, o_lev, o_y, vec2);               \
     } while (0)
 #define ILT_LAUNCH(T, INC)                      \
     do {                                        \
