@@ -131,20 +131,27 @@ k_interplevel(ILPtrs ptrs, int nvar, const void *__restrict__ vert, int nz, int6
     }
 }
 
-// ------------------------------------------------------------------ tiled variant (hot path, F1)
-// Used when the output is the dense level-fastest box array [by][bx][nlev] that mt_setdata feeds
-// to the gather.  A CTA owns TC consecutive box columns and streams nvar+1 source tiles
-// ([nz][TC]: the coordinate, then every variable) through a DOUBLE-BUFFERED shared-memory ring
-// filled with cp.async (LDGSTS: no register staging, the next tile lands while the current one
-// is consumed):
-//   tile 0 (coordinate): one thread per column checks monotonicity; all threads then bracket
-//      every (column, level) pair by binary search in shared memory (monotone columns: the
-//      unique / topmost bracket, identical to the scan from the top; other columns: the literal
-//      scan) and keep kp (1 byte) and w2 (8 bytes) per pair in shared memory;
-//   tile v+1 (variable v): all threads produce the TC*nlev outputs in level-fastest order, i.e.
-//      one contiguous, fully coalesced segment of TC*nlev doubles.
-// Every HBM byte is touched once (ncu: dram bytes == algorithmic bytes); rows are padded to TC+1
-// elements so that the per-lane varying level index does not collide on shared-memory banks.
+// ------------------------------------------------------------------ tiled variant
+// Serves the two dense output layouts: the level-fastest box rows [by][bx][nlev] that mt_setdata
+// feeds to the gather, and the level-major array (nlev, ny, nx) that wrf.interplevel returns.
+// A CTA owns TC consecutive box columns and streams nvar+1 source tiles ([nz][TC]: the coordinate,
+// then every variable) through a DOUBLE-BUFFERED shared-memory ring filled with cp.async (LDGSTS:
+// no register staging, the next tile lands while the current one is consumed; 16-byte copies of two
+// columns in the level-major modes when the alignment allows):
+//   tile 0 (coordinate): every thread owns one (column, block of consecutive levels): the blocks of a
+//      column check its monotonicity together, then each thread brackets its levels -- one binary
+//      search, then the bracket walks forward while the levels ascend along the coordinate (monotone
+//      columns: the unique / topmost bracket, identical to the scan from the top; other columns: the
+//      literal scan).  kp (1 byte) and w2 (8 bytes) per pair go to shared-memory tables, or -- level-major,
+//      32-column tiles, <= 64 levels -- stay in the registers of the thread, which then also produces
+//      exactly those outputs for every variable;
+//   tile v+1 (variable v): the TC*nlev outputs, as one contiguous segment of TC*nlev doubles
+//      (level-fastest rows: warps over columns, lanes over levels) or as nlev segments of TC
+//      contiguous doubles (level-major: lanes over columns).
+// Every HBM byte is touched once (ncu: dram bytes == algorithmic bytes).  Tile rows are padded to
+// TC+1 elements in the rows mode (lanes vary the level, i.e. the tile row: no bank collisions) and
+// dense in the level-major modes (lanes vary the column: conflict-free whatever rows they point to).
+// ncu (full domain, 4 variables): LSU data pipe 71 %, issue slots 68 %, DRAM 41 % -- LSU / issue bound.
 template <typename T>
 __device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gmem_src)
 {
