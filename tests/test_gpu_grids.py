@@ -579,3 +579,29 @@ def test_cyl_prelude_abi(nt, nr, with_hgt):
             assert int(ticket.item()) == 0
     assert lib.mt_cyl_prelude(D.ptr_array(src), D.ptr_array(out), 5, ny, nx, D.ptr(ix), D.ptr(w), nt, nr, -1, z_start, dz,
                               None, None, D.stream()) != 0
+
+
+@pytest.mark.parametrize("nz,ny,nx,nlev,dt_", [(12, 9, 14, 70, np.float64), (12, 9, 13, 70, np.float64),
+                                               (30, 33, 40, 64, np.float64), (30, 33, 41, 5, np.float64),
+                                               (7, 20, 36, 33, np.float32), (40, 64, 64, 96, np.float64)])
+def test_interplevel_level_major_modes(nz, ny, nx, nlev, dt_):
+    """interpolation.interplevel (level-major result) through every mode of the tile kernel: register
+    brackets (<= 64 levels) and shared-memory tables (more), 16-byte tile copies (even nx) and 8-byte
+    ones (odd nx), float32 sources, pressure (decreasing) coordinate with descending levels -- bit for
+    bit against the oracle."""
+    from meteotools_b200.interpolation import interplevel
+    rng = np.random.default_rng(nz * 100 + nx)
+    hgt = 600.0 * rng.random((ny, nx))
+    k = np.arange(nz).reshape(-1, 1, 1)
+    z3d = hgt[None] + (15000.0 - hgt[None]) * (k / (nz - 1)) ** 1.3
+    fld = (rng.standard_normal((nz, ny, nx)) * 3 + 0.002 * z3d).astype(dt_)
+    levels = np.linspace(50.0, 16000.0, nlev)
+    got = interplevel(fld, z3d.astype(dt_), levels)
+    ref = oracle.interplevel(fld, z3d.astype(dt_), levels)
+    assert got.shape == (nlev, ny, nx) and got.dtype == ref.dtype
+    assert_same(np.asarray(got), ref, f"interplevel z {(nz, ny, nx, nlev)}")
+    assert np.isnan(ref).any() and not np.isnan(ref).all()
+    p3d = (1e5 * np.exp(-z3d / 8000.0)).astype(dt_)
+    plev = np.linspace(99000.0, 12000.0, nlev)
+    assert_same(np.asarray(interplevel(fld, p3d, plev)), oracle.interplevel(fld, p3d, plev),
+                f"interplevel p {(nz, ny, nx, nlev)}")
