@@ -78,6 +78,7 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
         if vertical_interp_order not in (1, 2, 3):   # the reference leaves `tmp` undefined (:100-112)
             raise NameError(f"vertical_interp_order must be 1, 2 or 3, got {vertical_interp_order}")
         cur3d = []
+        self.__dict__.pop('_masked_in_setdata', None)   # names masked inside this call's transpose only
         for varname, var in vardict.items():
             if len(var.shape) == 3:
                 self.varlist3D.append(varname)
