@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MT_ABI_VERSION 1
+#define MT_ABI_VERSION 2
 
 /* status codes */
 #define MT_OK 0
@@ -317,6 +317,10 @@ typedef struct {
        arrays then hold nz = (z_hi-z_lo) + halo_lo + halo_hi levels. */
     int64_t halo_lo, halo_hi;    /* number of halo levels below / above (0 or 1)            */
     int is_bottom, is_top;       /* shard touches the global first / last level              */
+    /* (ABI 2) restrict the stencil stage of mt_cyl_d / mt_car_d to the owned levels [sub_lo, sub_hi)
+       (indices into the owned block; both 0 = all of it): a level shard first runs the levels that need
+       no halo while the halo planes travel, then its boundary levels (pipeline.LevelShardDyn). */
+    int64_t sub_lo, sub_hi;
 } mt_grid_t;
 
 typedef struct { /* inputs: thermaldynamic_calculation.py:7-133 on a grid holding T,p,qv(,qc,qr) */
@@ -335,6 +339,11 @@ typedef struct {
     const double *u, *v, *w, *p, *T, *Th /* may be NULL: computed from T,p */, *qv;
     const double *q[6];  /* qc,qr,qi,qs,qg,qh ; NULL-terminated prefix semantics as the reference */
     const double *f;     /* (nt,nr) Coriolis */
+    /* (ABI 2, mt_cyl_d only) the caller's radial / tangential wind.  When both are set they ARE the
+       horizontal wind of the call -- nothing is recomputed from u, v, exactly as the reference's calc_*
+       methods use self.vr / self.vt once they exist (cylindrical_grid.py:290-508) -- and u, v are needed
+       for wind_speed only; out->vr / out->vt must then be NULL. */
+    const double *vr, *vt;
 } mt_dyn_in_t;
 typedef struct { /* cylindrical_grid.py:264-508 */
     double *vr, *vt, *wind_speed, *kinetic_energy, *Tv, *rho, *density_factor, *Th, *Th_rho;
@@ -344,11 +353,22 @@ typedef struct { /* cylindrical_grid.py:264-508 */
     uint8_t *strain_region;
     double *aam; /* absolute angular momentum vt*r + 0.5*f*r**2 (:290-297) */
 } mt_cyl_d_out_t;
-/* stages: bit 0 = stage A (point-wise fields), bit 1 = stage B (stencils); 3 = both.  A level-
- * sharded run calls A, exchanges one halo level of vr/vt/w/Th_rho (v/w/Th_rho for car_d), then B. */
+/* stages: bit 0 = stage A (point-wise fields), bit 1 = stage B (stencils); 3 = both (the library then
+ * decides which kernel produces the wind-derived point-wise fields).
+ *   MT_STAGE_B alone reads vr / vt (cyl), Th_rho and rho from the OUTPUT buffers of an earlier stage-A
+ *   call (or vr / vt from in->vr / in->vt).
+ *   MT_STAGE_WIND_IN_B moves the wind-derived point-wise outputs (vr, vt, wind_speed, kinetic_energy,
+ *   coriolis_force, centrifugal_force, aam) from stage A to stage B, where the TMA stencil kernel has
+ *   u, v, w staged in shared memory anyway.  A level-sharded run exchanges one halo level of the INPUTS
+ *   u, v, w (v, w for car_d), calls MT_STAGE_A | MT_STAGE_WIND_IN_B (thermodynamic point-wise fields),
+ *   exchanges one halo level of Th_rho, then calls MT_STAGE_B | MT_STAGE_WIND_IN_B -- first for the
+ *   levels that need no halo (mt_grid_t.sub_lo / sub_hi), while the planes travel (mt_halo_exchange).
+ * Stage B runs as a TMA plane pipeline (csrc/diag_tma.cu) for arrays whose contiguous axis has an even
+ * length (16-byte aligned rows), otherwise as register-marching kernels; same results bit for bit. */
 #define MT_STAGE_A 1
 #define MT_STAGE_B 2
 #define MT_STAGE_ALL 3
+#define MT_STAGE_WIND_IN_B 4
 int mt_cyl_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_cyl_d_out_t *out, int stages,
              mt_stream_t stream);
 

@@ -37,7 +37,8 @@ def tma_tile(dtype):
     tw, al = (MT_TMA_TILE_W_F32, 4) if dtype == MT_F32 else (MT_TMA_TILE_W_F64, 2)
     return tw, MT_TMA_TILE_H, al, MT_TMA_MAX_TARGETS
 MT_LAYOUT_ZTR, MT_LAYOUT_TRZ = 0, 1
-MT_STAGE_A, MT_STAGE_B, MT_STAGE_ALL = 1, 2, 3
+MT_STAGE_A, MT_STAGE_B, MT_STAGE_ALL, MT_STAGE_WIND_IN_B = 1, 2, 3, 4
+MT_ABI_VERSION = 2
 FD_KINDS = {"FD2": 0, "FD4": 1, "FD2_front": 2, "FD2_back": 3, "FD2_2": 4, "FD2_2_front": 5,
             "FD2_2_back": 6}
 OPS = {name: i for i, name in enumerate(
@@ -49,7 +50,8 @@ class mt_grid_t(ct.Structure):
     _fields_ = [("nz", c_i64), ("nt", c_i64), ("nr", c_i64), ("layout", c_int),
                 ("dz", c_dbl), ("dt", c_dbl), ("dr", c_dbl),
                 ("r", c_vp), ("sin_t", c_vp), ("cos_t", c_vp),
-                ("halo_lo", c_i64), ("halo_hi", c_i64), ("is_bottom", c_int), ("is_top", c_int)]
+                ("halo_lo", c_i64), ("halo_hi", c_i64), ("is_bottom", c_int), ("is_top", c_int),
+                ("sub_lo", c_i64), ("sub_hi", c_i64)]
 
 
 def _ptr_struct(name, fields):
@@ -76,7 +78,7 @@ mt_car_d_out_t = _ptr_struct("mt_car_d_out_t", CAR_D_OUT)
 
 class mt_dyn_in_t(ct.Structure):
     _fields_ = [(f, c_vp) for f in ("u", "v", "w", "p", "T", "Th", "qv")] + \
-               [("q", c_vp * 6), ("f", c_vp)]
+               [("q", c_vp * 6), ("f", c_vp), ("vr", c_vp), ("vt", c_vp)]
 
 
 _SIGS = {

@@ -14,56 +14,19 @@
 // Every expression keeps the reference's order of evaluation (bit-exact for pure arithmetic).
 #include <type_traits>
 
-#include "fd.cuh"
-#include "thermo.cuh"
+#include "diag.cuh"
 
 namespace {
 
 using mt::nan_f64;
 using mt::inf_f64;
-
-template <int LAYOUT>
-struct Lay {
-    int nz, nt, nr;
-    int64_t sz, st, sr;
-    __host__ __device__ Lay(int nz_, int nt_, int nr_) : nz(nz_), nt(nt_), nr(nr_)
-    {
-        if (LAYOUT == MT_LAYOUT_ZTR) {
-            sr = 1, st = nr, sz = (int64_t)nt * nr;
-        } else {
-            sz = 1, sr = nz, st = (int64_t)nr * nz;
-        }
-    }
-    __device__ __forceinline__ void decode(int64_t m, int &iz, int &it, int &ir) const
-    {
-        if (LAYOUT == MT_LAYOUT_ZTR) {
-            ir = (int)(m % nr);
-            const int64_t q = m / nr;
-            it = (int)(q % nt);
-            iz = (int)(q / nt);
-        } else {
-            iz = (int)(m % nz);
-            const int64_t q = m / nz;
-            ir = (int)(q % nr);
-            it = (int)(q / nr);
-        }
-    }
-};
-
-struct GridP {
-    double dz, dt, dr;
-    const double *r, *sin_t, *cos_t;
-    int own_lo, own_hi;  // owned local level range [own_lo, own_hi)
-    bool bottom, top;
-};
-
-struct StageAOut {
-    double *vr, *vt, *wind_speed, *kinetic_energy, *Tv, *rho, *density_factor, *Th, *Th_rho,
-        *coriolis_force, *centrifugal_force, *aam;
-};
+using namespace mt::dg;
 
 // ------------------------------------------------------------------------------- stage A
-template <int LAYOUT, bool CYL>
+// WIND: how the horizontal wind reaches the point-wise outputs (diag.cuh): WIND_NONE -- no wind output is
+// requested from this launch (the TMA stencil kernel produces them): u, v are not read; WIND_UV -- (u, v),
+// rotated on a cylindrical grid; WIND_GIVEN -- the caller's (vr, vt), used as they are.
+template <int LAYOUT, bool CYL, int WIND>
 __global__ void __launch_bounds__(256)
 k_stage_a(Lay<LAYOUT> L, GridP g, mt_dyn_in_t in, mt::th::Hydro hyd, StageAOut o)
 {
@@ -72,20 +35,25 @@ k_stage_a(Lay<LAYOUT> L, GridP g, mt_dyn_in_t in, mt::th::Hydro hyd, StageAOut o
          m += (int64_t)gridDim.x * blockDim.x) {
         int iz, it, ir;
         L.decode(m, iz, it, ir);
-        const double u = __ldg(in.u + m), v = __ldg(in.v + m);
         double vr = 0, vt = 0;
-        if (CYL) {
-            const double s = __ldg(g.sin_t + it), c = __ldg(g.cos_t + it);
-            vr = v * s + u * c;  // cylindrical_grid.py:267
-            vt = v * c - u * s;  // :268
-            if (o.vr) o.vr[m] = vr;
-            if (o.vt) o.vt[m] = vt;
-        }
-        if (o.wind_speed) __stcs(o.wind_speed + m, sqrt(u * u + v * v));  // (u**2+v**2)**0.5
-        if (o.kinetic_energy && in.w) {
-            const double w = __ldg(in.w + m);
-            const double ke = CYL ? (vr * vr + vt * vt + w * w) / 2 : (u * u + v * v + w * w) / 2;
-            __stcs(o.kinetic_energy + m, ke);
+        if (WIND != WIND_NONE) {
+            double u = 0, v = 0;
+            if (WIND == WIND_UV || o.wind_speed) u = __ldg(in.u + m), v = __ldg(in.v + m);
+            if (CYL && WIND == WIND_UV) {
+                const double s = __ldg(g.sin_t + it), c = __ldg(g.cos_t + it);
+                vr = v * s + u * c;  // cylindrical_grid.py:267
+                vt = v * c - u * s;  // :268
+                if (o.vr) o.vr[m] = vr;
+                if (o.vt) o.vt[m] = vt;
+            } else if (CYL) {
+                vr = __ldg(in.vr + m), vt = __ldg(in.vt + m);
+            }
+            if (o.wind_speed) __stcs(o.wind_speed + m, sqrt(u * u + v * v));  // (u**2+v**2)**0.5
+            if (o.kinetic_energy && in.w) {
+                const double w = __ldg(in.w + m);
+                const double ke = CYL ? (vr * vr + vt * vt + w * w) / 2 : (u * u + v * v + w * w) / 2;
+                __stcs(o.kinetic_energy + m, ke);
+            }
         }
         const bool need_thermo = o.Tv || o.rho || o.density_factor || o.Th || o.Th_rho;
         if (need_thermo) {
@@ -110,7 +78,7 @@ k_stage_a(Lay<LAYOUT> L, GridP g, mt_dyn_in_t in, mt::th::Hydro hyd, StageAOut o
                 if (o.Th_rho) o.Th_rho[m] = Th * df;  // :453
             }
         }
-        if (CYL && (o.coriolis_force || o.centrifugal_force || o.aam)) {
+        if (CYL && WIND != WIND_NONE && (o.coriolis_force || o.centrifugal_force || o.aam)) {
             const double rr = __ldg(g.r + ir);
             if (o.coriolis_force) __stcs(o.coriolis_force + m, __ldg(in.f + (int64_t)it * L.nr + ir) * vt);
             if (o.centrifugal_force) __stcs(o.centrifugal_force + m, vt * vt / rr);
@@ -125,16 +93,6 @@ k_stage_a(Lay<LAYOUT> L, GridP g, mt_dyn_in_t in, mt::th::Hydro hyd, StageAOut o
 #define MT_STAGEB_MINB 8   // resident CTAs per SM the interior kernel is compiled for: 64 registers (a few
                            // spilled words) beat 80 registers at 6 CTAs -- the kernel is load-latency bound
 #endif
-struct StageBIn {
-    const double *a, *b, *w, *thr, *p, *rho, *f;  // cyl: a=vr, b=vt ; car: a=u, b=v
-};
-struct StageBOut {
-    double *radial_PG_force, *agradient_force;
-    double *zeta_r, *zeta_t, *zeta_z, *abs_zeta_z, *div_hori, *div, *PV;
-    double *shear_deform, *stretch_deform, *filamentation_time;
-    uint8_t *strain_region;
-};
-
 // Stage B marches along the SLOWEST memory axis (z for "ZTR", theta for "TRZ"): one thread per
 // position of the (contiguous) plane keeps the previous / current / next plane values of the four
 // differentiated fields in registers, so every plane is read from HBM once even when a plane is
@@ -165,7 +123,7 @@ __device__ __forceinline__ double dmarch(const Roll &r, int i, int n, bool first
 //                neighbour loads of a point together (the generic body issues them in small groups
 //                between run-time branches and pays the L2 latency once per group).
 template <int LAYOUT, bool CYL, bool SHELL, bool FULL>
-__global__ void __launch_bounds__(128, SHELL ? 4 : MT_STAGEB_MINB)
+__global__ void __launch_bounds__(128, SHELL ? 6 : MT_STAGEB_MINB)
 k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
 {
     constexpr bool ZTR = LAYOUT == MT_LAYOUT_ZTR;
@@ -191,6 +149,19 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
         s_hi = min(m_hi, s_lo + seg_len);
         if (s_lo >= s_hi) return;
     } else {
+        int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        int iz, it, ir;
+        if (seg_len == 2) {
+            // only the two END PLANES of the march axis (the TMA kernel of csrc/diag_tma.cu produces every
+            // other point, the edges of the planes included): whole contiguous planes, coalesced
+            const int nf = (first ? 1 : 0) + (last ? 1 : 0);
+            if (q >= (int64_t)nf * plane) return;
+            const int f = (int)(q / plane);
+            const int64_t rem = q - (int64_t)f * plane;
+            const int m_end = (f == 0 && first) ? (ZTR ? g.own_lo : 0) : (ZTR ? g.own_hi - 1 : n0 - 1);
+            const int j1 = (int)(rem / n2), j2 = (int)(rem - (int64_t)j1 * n2);
+            iz = ZTR ? m_end : j2, it = ZTR ? j1 : m_end, ir = ZTR ? j2 : j1;
+        } else {
         // compact enumeration of the outermost shell of the owned block: the global z faces, the two
         // theta faces of the remaining levels, the two r faces of what is left -- one thread per
         // shell point (the first version launched a thread per GRID point and let 95 % of them
@@ -199,13 +170,11 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
         const int nzin = max(zin_hi - zin_lo, 0);
         const int64_t nA = (int64_t)((g.bottom ? 1 : 0) + (g.top ? 1 : 0)) * nt * nr;
         const int64_t nB = 2LL * nzin * nr, nC = 2LL * nzin * (nt - 2);
-        int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        int iz, it, ir;
         if (q < nA) {
             const int f = (int)(q / ((int64_t)nt * nr));
             const int64_t rem = q - (int64_t)f * nt * nr;
             it = (int)(rem / nr), ir = (int)(rem - (int64_t)it * nr);
-            iz = (f == 0 && g.bottom) ? 0 : nz - 1;
+            iz = (f == 0 && g.bottom) ? g.own_lo : g.own_hi - 1;
         } else if ((q -= nA) < nB) {
             const int f = (int)(q / ((int64_t)nzin * nr));
             const int64_t rem = q - (int64_t)f * nzin * nr;
@@ -222,6 +191,7 @@ k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
             ir = f ? nr - 1 : 0;
         } else {
             return;
+        }
         }
         s_lo = ZTR ? iz : it, s_hi = s_lo + 1;
         i1 = ZTR ? it : ir, i2 = ZTR ? ir : iz;
@@ -442,6 +412,13 @@ bool check_grid(const mt_grid_t *g, bool cyl)
         mt::set_error("bad halo description");
         return false;
     }
+    const int64_t owned = g->nz - g->halo_lo - g->halo_hi;
+    if (g->sub_lo < 0 || g->sub_hi < 0 || g->sub_hi > owned || (g->sub_hi != 0 && g->sub_lo >= g->sub_hi) ||
+        (g->sub_hi == 0 && g->sub_lo != 0)) {
+        mt::set_error("bad level sub-range [%lld, %lld) of %lld owned levels", (long long)g->sub_lo,
+                      (long long)g->sub_hi, (long long)owned);
+        return false;
+    }
     return true;
 }
 
@@ -450,10 +427,14 @@ GridP grid_params(const mt_grid_t *g)
     GridP p;
     p.dz = g->dz, p.dt = g->dt, p.dr = g->dr;
     p.r = g->r, p.sin_t = g->sin_t, p.cos_t = g->cos_t;
-    p.own_lo = (int)g->halo_lo;
-    p.own_hi = (int)(g->nz - g->halo_hi);
-    p.bottom = g->is_bottom != 0;
-    p.top = g->is_top != 0;
+    p.halo_lo = (int)g->halo_lo, p.halo_hi = (int)g->halo_hi;
+    const int64_t owned = g->nz - g->halo_lo - g->halo_hi;
+    const int64_t lo = g->sub_hi ? g->sub_lo : 0, hi = g->sub_hi ? g->sub_hi : owned;
+    p.own_lo = (int)(g->halo_lo + lo);
+    p.own_hi = (int)(g->halo_lo + hi);
+    // a sub-range that does not start / end at the shard's own end has ordinary (centred) levels there
+    p.bottom = g->is_bottom != 0 && lo == 0;
+    p.top = g->is_top != 0 && hi == owned;
     return p;
 }
 
@@ -468,26 +449,91 @@ mt::th::Hydro hydro_of(const mt_dyn_in_t *in)
 }
 
 template <bool CYL>
-int run_sets(const mt_grid_t *g, const mt_dyn_in_t *in, const StageAOut &a, const StageBIn &bi,
-             const StageBOut &bo, int stages, bool need_a, bool need_b, cudaStream_t s)
+int launch_stage_a(const mt_grid_t *g, const GridP &p, const mt_dyn_in_t *in, const StageAOut &a, int wind,
+                   cudaStream_t s)
 {
+    const bool any = a.vr || a.vt || a.wind_speed || a.kinetic_energy || a.Tv || a.rho || a.density_factor || a.Th ||
+                     a.Th_rho || a.coriolis_force || a.centrifugal_force || a.aam;
+    if (!any) return MT_OK;
     const int64_t total = g->nz * g->nt * g->nr;
     const unsigned grid = mt::grid_for(total, 256, 8);
-    GridP p = grid_params(g);
     mt::th::Hydro hyd = hydro_of(in);
-    if ((stages & 1) && need_a) {
-        mt::ProfScope prof(CYL ? "k_stage_a_cyl" : "k_stage_a_car", (mt_stream_t)s);
-        if (g->layout == MT_LAYOUT_ZTR)
-            k_stage_a<MT_LAYOUT_ZTR, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_ZTR>((int)g->nz, (int)g->nt, (int)g->nr), p, *in, hyd, a);
-        else
-            k_stage_a<MT_LAYOUT_TRZ, CYL><<<grid, 256, 0, s>>>(Lay<MT_LAYOUT_TRZ>((int)g->nz, (int)g->nt, (int)g->nr), p, *in, hyd, a);
-        MT_LAUNCH_CHECK();
+    mt::ProfScope prof(CYL ? "k_stage_a_cyl" : "k_stage_a_car", (mt_stream_t)s);
+#define SA_LAUNCH(LAYOUT_, WIND_)                                                                           \
+    k_stage_a<LAYOUT_, CYL, WIND_><<<grid, 256, 0, s>>>(Lay<LAYOUT_>((int)g->nz, (int)g->nt, (int)g->nr), p, *in, hyd, a)
+#define SA_DISPATCH(LAYOUT_)                                       \
+    do {                                                           \
+        if (wind == WIND_NONE) SA_LAUNCH(LAYOUT_, WIND_NONE);      \
+        else if (wind == WIND_UV) SA_LAUNCH(LAYOUT_, WIND_UV);     \
+        else SA_LAUNCH(LAYOUT_, WIND_GIVEN);                       \
+    } while (0)
+    if (g->layout == MT_LAYOUT_ZTR) SA_DISPATCH(MT_LAYOUT_ZTR);
+    else SA_DISPATCH(MT_LAYOUT_TRZ);
+#undef SA_DISPATCH
+#undef SA_LAUNCH
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
+
+// `a`: every point-wise output requested (wind-derived and thermodynamic); `wind`: where the horizontal
+// wind comes from (WIND_UV: in->u, in->v; WIND_GIVEN: bi.a, bi.b are the caller's vr, vt).
+// Work split (include/meteotools_b200.h, MT_STAGE_*): the wind-derived point-wise outputs belong to
+// stage A unless MT_STAGE_WIND_IN_B is set -- or both stages run in this call and the TMA stencil kernel
+// can take them: it has u, v, w staged in shared memory anyway.
+template <bool CYL>
+int run_sets(const mt_grid_t *g, const mt_dyn_in_t *in, const StageAOut &a, const StageBIn &bi,
+             const StageBOut &bo, int stages, int wind, bool need_b, cudaStream_t s)
+{
+    GridP p = grid_params(g);
+    StageAOut thermo = a, windo = a;   // the two halves of the point-wise outputs
+    thermo.vr = thermo.vt = thermo.wind_speed = thermo.kinetic_energy = nullptr;
+    thermo.coriolis_force = thermo.centrifugal_force = thermo.aam = nullptr;
+    windo.Tv = windo.rho = windo.density_factor = windo.Th = windo.Th_rho = nullptr;
+    const bool any_wind = windo.vr || windo.vt || windo.wind_speed || windo.kinetic_energy ||
+                          windo.coriolis_force || windo.centrifugal_force || windo.aam;
+    const bool tma_ok = need_b && stencil_tma_supported(g);
+    // the TMA kernel rotates (u, v) itself; a caller-given (vr, vt) pair needs no wind pass in it
+    const bool tma_wind = tma_ok && wind == WIND_UV;
+    const bool wind_in_b = (stages & MT_STAGE_WIND_IN_B) || ((stages & MT_STAGE_ALL) == MT_STAGE_ALL && tma_wind);
+    int rc = MT_OK;
+    if (stages & MT_STAGE_A) {
+        rc = launch_stage_a<CYL>(g, p, in, wind_in_b ? thermo : a, (wind_in_b || !any_wind) ? WIND_NONE : wind, s);
+        if (rc != MT_OK) return rc;
     }
-    if ((stages & 2) && need_b) {
-        mt::ProfScope prof(CYL ? "k_stage_b_cyl" : "k_stage_b_car", (mt_stream_t)s);
+    if (!(stages & MT_STAGE_B)) return MT_OK;
+    bool wind_done = !(wind_in_b && any_wind);
+    if (need_b) {
         const bool ztr = g->layout == MT_LAYOUT_ZTR;
+        // the whole set requested -> the straight-line instantiations (MT_STAGEB_GENERIC=1: A/B runs)
+        static const bool force_generic = getenv("MT_STAGEB_GENERIC") && getenv("MT_STAGEB_GENERIC")[0] == '1';
+        const bool full = !force_generic && bi.a && bi.b && bi.w && bi.thr && bi.rho && bi.f && bo.zeta_r &&
+                          bo.zeta_t && bo.zeta_z && bo.abs_zeta_z && bo.div_hori && bo.div && bo.PV &&
+                          bo.shear_deform && bo.stretch_deform && bo.filamentation_time &&
+                          (!CYL || (bi.p && bo.radial_PG_force && bo.agradient_force && bo.strain_region));
+        bool interior_done = false;
+        if (tma_ok) {
+            WindOut wo{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            const bool fold = wind_in_b && any_wind && tma_wind;
+            if (fold)
+                wo = WindOut{windo.vr, windo.vt, windo.wind_speed, in->w ? windo.kinetic_energy : nullptr,
+                             windo.coriolis_force, windo.centrifugal_force, windo.aam};
+            const bool from_uv = tma_wind && (wind_in_b || !CYL);
+            rc = stencil_tma<CYL>(g, p, bi, (CYL && from_uv) ? in->u : nullptr, (CYL && from_uv) ? in->v : nullptr, wo,
+                                  bo, full, s);
+            if (rc == MT_OK) {
+                interior_done = true;
+                if (fold) wind_done = true;
+            } else if (rc != MT_ENOSUP) {
+                return rc;
+            }
+        }
+        if (!wind_done) {   // the marching kernels read vr / vt from global memory
+            rc = launch_stage_a<CYL>(g, p, in, windo, wind, s);
+            if (rc != MT_OK) return rc;
+            wind_done = true;
+        }
         const int64_t plane = ztr ? g->nt * g->nr : g->nr * g->nz;
-        const int64_t n_march = ztr ? (g->nz - g->halo_lo - g->halo_hi) : g->nt;
+        const int64_t n_march = ztr ? (p.own_hi - p.own_lo) : g->nt;
         // enough segments of the march axis for ~2 full waves of 128-thread CTAs
         int64_t want_threads = (int64_t)mt::sm_count() * 2048 * 2;
         int64_t nseg = (want_threads + plane - 1) / plane;
@@ -496,29 +542,36 @@ int run_sets(const mt_grid_t *g, const mt_dyn_in_t *in, const StageAOut &a, cons
         const int seg_len = (int)((n_march + nseg - 1) / nseg);
         dim3 gridb((unsigned)((plane + 127) / 128), (unsigned)((n_march + seg_len - 1) / seg_len));
         // shell launch: one thread per point of the outermost shell of the owned block
-        const int64_t own = g->nz - g->halo_lo - g->halo_hi;
-        const int64_t nzin = own - (g->is_bottom ? 1 : 0) - (g->is_top ? 1 : 0);
-        const int64_t n_shell = ((g->is_bottom ? 1 : 0) + (g->is_top ? 1 : 0)) * g->nt * g->nr +
+        const int64_t own = p.own_hi - p.own_lo;
+        const int64_t nzin = own - (p.bottom ? 1 : 0) - (p.top ? 1 : 0);
+        const int64_t n_shell = ((p.bottom ? 1 : 0) + (p.top ? 1 : 0)) * g->nt * g->nr +
                                 2 * (nzin > 0 ? nzin : 0) * (g->nr + g->nt - 2);
-        dim3 grids((unsigned)((n_shell + 127) / 128 > 0 ? (n_shell + 127) / 128 : 1));
-        // the whole set requested -> the straight-line instantiation (MT_STAGEB_GENERIC=1: A/B runs)
-        static const bool force_generic = getenv("MT_STAGEB_GENERIC") && getenv("MT_STAGEB_GENERIC")[0] == '1';
-        const bool full = !force_generic && bi.a && bi.b && bi.w && bi.thr && bi.rho && bi.f && bo.zeta_r &&
-                          bo.zeta_t && bo.zeta_z && bo.abs_zeta_z && bo.div_hori && bo.div && bo.PV &&
-                          bo.shear_deform && bo.stretch_deform && bo.filamentation_time &&
-                          (!CYL || (bi.p && bo.radial_PG_force && bo.agradient_force && bo.strain_region));
-#define SB_LAUNCH(LAYOUT_)                                                                         \
-    do {                                                                                           \
-        Lay<LAYOUT_> lay((int)g->nz, (int)g->nt, (int)g->nr);                                      \
-        if (full) k_stage_b<LAYOUT_, CYL, false, true><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len); \
-        else k_stage_b<LAYOUT_, CYL, false, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);  \
-        MT_LAUNCH_CHECK();                                                                         \
-        k_stage_b<LAYOUT_, CYL, true, false><<<grids, 128, 0, s>>>(lay, p, bi, bo, 1);             \
+        // after the TMA kernel only the two end planes of the march axis are left (mode 2 of the shell kernel)
+        const int64_t n_ends = ((ztr ? (p.bottom ? 1 : 0) + (p.top ? 1 : 0) : 2)) * plane;
+        const int64_t n_sh = interior_done ? n_ends : n_shell;
+        const int shell_mode = interior_done ? 2 : 1;
+        dim3 grids((unsigned)((n_sh + 127) / 128 > 0 ? (n_sh + 127) / 128 : 1));
+#define SB_LAUNCH(LAYOUT_)                                                                             \
+    do {                                                                                               \
+        Lay<LAYOUT_> lay((int)g->nz, (int)g->nt, (int)g->nr);                                          \
+        if (!interior_done) {                                                                          \
+            mt::ProfScope prof(CYL ? "k_stage_b_cyl" : "k_stage_b_car", (mt_stream_t)s);               \
+            if (full) k_stage_b<LAYOUT_, CYL, false, true><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len); \
+            else k_stage_b<LAYOUT_, CYL, false, false><<<gridb, 128, 0, s>>>(lay, p, bi, bo, seg_len);  \
+            MT_LAUNCH_CHECK();                                                                         \
+        }                                                                                              \
+        mt::ProfScope prof(CYL ? "k_stage_b_shell_cyl" : "k_stage_b_shell_car", (mt_stream_t)s);       \
+        if (full) k_stage_b<LAYOUT_, CYL, true, true><<<grids, 128, 0, s>>>(lay, p, bi, bo, shell_mode);   \
+        else k_stage_b<LAYOUT_, CYL, true, false><<<grids, 128, 0, s>>>(lay, p, bi, bo, shell_mode);     \
+        MT_LAUNCH_CHECK();                                                                             \
     } while (0)
         if (ztr) SB_LAUNCH(MT_LAYOUT_ZTR);
         else SB_LAUNCH(MT_LAYOUT_TRZ);
 #undef SB_LAUNCH
-        MT_LAUNCH_CHECK();
+    }
+    if (!wind_done) {   // MT_STAGE_WIND_IN_B without any stencil output
+        rc = launch_stage_a<CYL>(g, p, in, windo, wind, s);
+        if (rc != MT_OK) return rc;
     }
     return MT_OK;
 }
@@ -531,37 +584,55 @@ int mt_cyl_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_cyl_d_out_t *ou
              mt_stream_t stream)
 {
     if (!check_grid(g, true)) return MT_EINVAL;
-    MT_REQUIRE(in && out && in->u && in->v, "mt_cyl_d: u and v are required");
+    MT_REQUIRE(in && out, "mt_cyl_d: null argument");
+    MT_REQUIRE((stages & MT_STAGE_ALL) != 0 && (stages & ~(MT_STAGE_ALL | MT_STAGE_WIND_IN_B)) == 0,
+               "mt_cyl_d: bad stages %d", stages);
     const mt_cyl_d_out_t &o = *out;
-    const bool z_needed = o.zeta_r || o.zeta_t || o.div || o.PV;
-    MT_REQUIRE(!z_needed || (g->nz - g->halo_lo - g->halo_hi >= 1 &&
-                             g->nz >= 3),
-               "mt_cyl_d: z-derivatives need at least 3 local levels");
-    const bool b_uses_w = o.zeta_r || o.zeta_t || o.div || o.PV;
-    MT_REQUIRE(!b_uses_w || in->w, "mt_cyl_d: w is required for the requested outputs");
-    const bool need_b = o.radial_PG_force || o.agradient_force || o.zeta_r || o.zeta_t || o.zeta_z ||
-                        o.abs_zeta_z || o.div_hori || o.div || o.PV || o.shear_deform ||
-                        o.stretch_deform || o.filamentation_time || o.strain_region;
+    const bool given = in->vr && in->vt;   // the caller's vr / vt are used as they are
+    MT_REQUIRE(!(in->vr || in->vt) || given, "mt_cyl_d: vr and vt must be given together");
+    MT_REQUIRE(!given || (!o.vr && !o.vt), "mt_cyl_d: vr / vt are inputs of this call, they cannot be outputs too");
+    const bool have_uv = in->u && in->v;
     const bool need_ab = o.zeta_r || o.zeta_t || o.zeta_z || o.abs_zeta_z || o.div_hori || o.div || o.PV ||
                          o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
-    MT_REQUIRE(!((stages & MT_STAGE_B) && need_ab) || (o.vr && o.vt),
-               "mt_cyl_d: stencil outputs need the vr and vt buffers");
-    MT_REQUIRE(!((stages & MT_STAGE_B) && o.agradient_force) || o.vt, "mt_cyl_d: agradient_force needs vt");
+    const bool need_b = need_ab || o.radial_PG_force || o.agradient_force;
+    const bool wind_pw = o.vr || o.vt || o.kinetic_energy || o.coriolis_force || o.centrifugal_force || o.aam;
+    const bool b_only = (stages & MT_STAGE_ALL) == MT_STAGE_B && !(stages & MT_STAGE_WIND_IN_B);
+    // stage B alone reads the horizontal wind from the vr / vt buffers of an earlier stage-A call
+    const double *vr_src = given ? in->vr : o.vr, *vt_src = given ? in->vt : o.vt;
+    MT_REQUIRE(!o.wind_speed || have_uv, "mt_cyl_d: wind_speed needs u and v");
+    MT_REQUIRE(!wind_pw || given || have_uv, "mt_cyl_d: u and v (or vr and vt) are required");
+    MT_REQUIRE(!((stages & MT_STAGE_B) && need_ab) || (vr_src && vt_src),
+               "mt_cyl_d: stencil outputs need vr and vt (inputs, or output buffers filled from u, v)");
+    MT_REQUIRE(!((stages & MT_STAGE_B) && need_ab) || given || b_only || have_uv,
+               "mt_cyl_d: u and v (or vr and vt) are required");
+    MT_REQUIRE(!((stages & MT_STAGE_B) && o.agradient_force) || vt_src, "mt_cyl_d: agradient_force needs vt");
+    const bool z_needed = o.zeta_r || o.zeta_t || o.div || o.PV;
+    MT_REQUIRE(!z_needed || (g->nz - g->halo_lo - g->halo_hi >= 1 && g->nz >= 3),
+               "mt_cyl_d: z-derivatives need at least 3 local levels");
+    MT_REQUIRE(!z_needed || in->w, "mt_cyl_d: w is required for the requested outputs");
     MT_REQUIRE(!(o.PV) || (o.Th_rho && o.rho && in->f), "mt_cyl_d: PV needs Th_rho, rho buffers and f");
     MT_REQUIRE(!(o.radial_PG_force || o.agradient_force) || (o.rho && in->p),
                "mt_cyl_d: the pressure-gradient force needs p and the rho buffer");
     MT_REQUIRE(!(o.abs_zeta_z || o.agradient_force || o.coriolis_force || o.aam) || in->f, "mt_cyl_d: f is required");
     const bool thermo = o.Tv || o.rho || o.density_factor || o.Th || o.Th_rho;
-    MT_REQUIRE(!thermo || in->qv, "mt_cyl_d: qv is required for Tv/rho/density_factor/Th_rho");
-    MT_REQUIRE(!(o.Tv || o.rho) || (in->T && in->p), "mt_cyl_d: Tv/rho need T and p");
-    MT_REQUIRE(!(o.Th || o.Th_rho) || in->Th || (in->T && in->p), "mt_cyl_d: Th needs Th or (T, p)");
+    const bool thermo_now = thermo && (stages & MT_STAGE_A);
+    MT_REQUIRE(!thermo_now || in->qv, "mt_cyl_d: qv is required for Tv/rho/density_factor/Th_rho");
+    MT_REQUIRE(!(thermo_now && (o.Tv || o.rho)) || (in->T && in->p), "mt_cyl_d: Tv/rho need T and p");
+    MT_REQUIRE(!(thermo_now && (o.Th || o.Th_rho)) || in->Th || (in->T && in->p), "mt_cyl_d: Th needs Th or (T, p)");
     StageAOut a{o.vr, o.vt, o.wind_speed, o.kinetic_energy, o.Tv, o.rho, o.density_factor, o.Th,
                 o.Th_rho, o.coriolis_force, o.centrifugal_force, o.aam};
-    StageBIn bi{o.vr, o.vt, in->w, o.Th_rho, in->p, o.rho, in->f};
+    StageBIn bi{vr_src, vt_src, in->w, o.Th_rho, in->p, o.rho, in->f};
     StageBOut bo{o.radial_PG_force, o.agradient_force, o.zeta_r, o.zeta_t, o.zeta_z, o.abs_zeta_z,
                  o.div_hori, o.div, o.PV, o.shear_deform, o.stretch_deform, o.filamentation_time,
                  o.strain_region};
-    return run_sets<true>(g, in, a, bi, bo, stages, true, need_b, (cudaStream_t)stream);
+    // WIND_GIVEN also describes stage B alone on the vr / vt buffers of an earlier call: nothing is rotated
+    const int wind = (given || b_only) ? WIND_GIVEN : WIND_UV;
+    mt_dyn_in_t in2 = *in;
+    if (wind == WIND_GIVEN) in2.vr = vr_src, in2.vt = vt_src;
+    if (b_only)   // the point-wise outputs of an earlier stage-A call are inputs here
+        a = StageAOut{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, nullptr};
+    return run_sets<true>(g, &in2, a, bi, bo, stages, wind, need_b, (cudaStream_t)stream);
 }
 
 int mt_car_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_car_d_out_t *out, int stages,
@@ -569,24 +640,28 @@ int mt_car_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_car_d_out_t *ou
 {
     if (!check_grid(g, false)) return MT_EINVAL;
     MT_REQUIRE(in && out && in->u && in->v, "mt_car_d: u and v are required");
+    MT_REQUIRE((stages & MT_STAGE_ALL) != 0 && (stages & ~(MT_STAGE_ALL | MT_STAGE_WIND_IN_B)) == 0,
+               "mt_car_d: bad stages %d", stages);
     const mt_car_d_out_t &o = *out;
     const bool b_uses_w = o.zeta_r || o.zeta_t || o.div || o.PV;
     MT_REQUIRE(!b_uses_w || (in->w && g->nz >= 3), "mt_car_d: w and >= 3 local levels are required");
     MT_REQUIRE(!(o.PV) || (o.Th_rho && o.rho && in->f), "mt_car_d: PV needs Th_rho, rho buffers and f");
     MT_REQUIRE(!(o.abs_zeta_z) || in->f, "mt_car_d: f is required");
     const bool thermo = o.Tv || o.rho || o.density_factor || o.Th || o.Th_rho;
-    MT_REQUIRE(!thermo || in->qv, "mt_car_d: qv is required for Tv/rho/density_factor/Th_rho");
-    MT_REQUIRE(!(o.Tv || o.rho) || (in->T && in->p), "mt_car_d: Tv/rho need T and p");
-    MT_REQUIRE(!(o.Th || o.Th_rho) || in->Th || (in->T && in->p), "mt_car_d: Th needs Th or (T, p)");
-    const bool need_a = o.wind_speed || o.kinetic_energy || thermo;
+    const bool thermo_now = thermo && (stages & MT_STAGE_A);
+    MT_REQUIRE(!thermo_now || in->qv, "mt_car_d: qv is required for Tv/rho/density_factor/Th_rho");
+    MT_REQUIRE(!(thermo_now && (o.Tv || o.rho)) || (in->T && in->p), "mt_car_d: Tv/rho need T and p");
+    MT_REQUIRE(!(thermo_now && (o.Th || o.Th_rho)) || in->Th || (in->T && in->p), "mt_car_d: Th needs Th or (T, p)");
     const bool need_b = o.zeta_r || o.zeta_t || o.zeta_z || o.abs_zeta_z || o.div_hori || o.div || o.PV ||
                         o.shear_deform || o.stretch_deform || o.filamentation_time;
+    const bool b_only = (stages & MT_STAGE_ALL) == MT_STAGE_B && !(stages & MT_STAGE_WIND_IN_B);
     StageAOut a{nullptr, nullptr, o.wind_speed, o.kinetic_energy, o.Tv, o.rho, o.density_factor, o.Th,
                 o.Th_rho, nullptr, nullptr, nullptr};
+    if (b_only) a.wind_speed = a.kinetic_energy = nullptr;
     StageBIn bi{in->u, in->v, in->w, o.Th_rho, in->p, o.rho, in->f};
     StageBOut bo{nullptr, nullptr, o.zeta_r, o.zeta_t, o.zeta_z, o.abs_zeta_z, o.div_hori, o.div, o.PV,
                  o.shear_deform, o.stretch_deform, o.filamentation_time, nullptr};
-    return run_sets<false>(g, in, a, bi, bo, stages, need_a, need_b, (cudaStream_t)stream);
+    return run_sets<false>(g, in, a, bi, bo, stages, WIND_UV, need_b, (cudaStream_t)stream);
 }
 
 int mt_azimuthal_mean(const double *var, const mt_grid_t *g, double *sym, double *asy,

@@ -12,9 +12,11 @@ namespace mt {
 // q = RN(q0 + r*rd)  is the correctly rounded a/d (Markstein's correction step -- the tail of the
 // IEEE division sequence without the ~15 instructions that build the reciprocal).  Verified bit for
 // bit against a/d on 352 000 (a, d) pairs with exact rational arithmetic (profiles/experiments_r01.md)
-// and by every bit-exact FD / cyl_d / car_d parity test.  Quotients that are huge, infinite or close
-// to the subnormal range, and divisors that are not normal numbers (r[0] = 0!), take the IEEE
-// division; NaN flows through the fast path as NaN (terrain-masked lanes stay branch-free).
+// and by every bit-exact FD / cyl_d / car_d parity test.  Three FP64 instructions + an INTEGER test of
+// q0's exponent (the FP64 pipe is the scarce one): quotients that are huge, infinite, zero or close to
+// the subnormal range, and divisors that are not normal numbers (r[0] = 0!), leave the fast path --
+// a zero dividend returns q0 = +-0 (the sign IEEE gives), everything else takes the IEEE division;
+// NaN flows through the fast path as NaN (terrain-masked lanes stay branch-free).
 struct CDiv {
     double d, rd;
     bool plain;
@@ -29,8 +31,12 @@ struct CDiv {
         const double q0 = a * rd;
         const double r = fma(-q0, d, a);
         double q = fma(r, rd, q0);
-        const double aq = fabs(q0);
-        if (aq >= 1e300 || (aq < 1e-290 && aq != 0.0)) q = a / d;
+        // biased exponent of q0 in [60, 2020]  <=>  2^-963 <= |q0| < 2^998: the residual is exact
+        const unsigned e = ((unsigned)__double2hiint(q0) >> 20) & 0x7ffu;
+        if (e - 60u > 1960u) {
+            if (a == 0.0) q = q0;            // +-0 / d
+            else if (q0 == q0) q = a / d;    // tiny, huge, infinite; NaN keeps the fast path's NaN
+        }
         return q;
     }
 };

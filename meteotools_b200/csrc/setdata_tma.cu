@@ -23,14 +23,11 @@
 //             order of fastcompute.f90:100-102, one 16-byte streaming store per lane.
 // Consumers never read global memory; they only wait on mbarriers and store results.
 // Arithmetic and its order are identical to k_interplevel_tile + k_gather2d_lf (bit-exact tests).
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -66,39 +63,7 @@ struct __align__(16) Meta {   // one staged target (two 16-byte words; a third w
 };
 static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    const uint32_t a = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-        : "memory");
-}
+using namespace mt::tma;   // smem_u32, mbar_*, load_3d (csrc/tma.cuh)
 #ifdef MT_TMA_TIMING
 // phase clocks of consumer warp 0 (debug builds only: scratch/tma_timing.py)
 __device__ unsigned long long g_tma_timing[8];
@@ -141,7 +106,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     // an odd level count is handled as pairs too: the last level is its own partner (the second
     // half of that pair is computed and never stored)
@@ -234,7 +199,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                         s_item4[n & 3] = it;
                     }
                     mbar_expect_tx(full + q_slot, (uint32_t)(NC * nz * (int)sizeof(T)));
-                    tma_load_3d(smem + (size_t)q_slot * stage_bytes, &P.maps[t], full + q_slot, it.x - org_x,
+                    load_3d(smem + (size_t)q_slot * stage_bytes, &P.maps[t], full + q_slot, it.x - org_x,
                                 it.y - org_y, 0);
                 }
                 if (++q_slot == stages) q_slot = 0, q_par ^= 1u;
@@ -497,19 +462,6 @@ __global__ void k_fill_flagged2(OutPtrs ptrs, int nvar, const int4 *__restrict__
 }
 
 // ---- host side: tensor maps (cached per source buffer) ---------------------------------------
-PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
-{
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-    }();
-    return fn;
-}
-
 struct MapKey {
     const void *ptr;
     int64_t nz, ny, nx, pitch;

@@ -18,6 +18,8 @@ from .thermaldynamic_calculation import calc_thermaldynamic
 
 class cartesian_grid(gridsystem, calc_thermaldynamic):
     _layout = _lib.MT_LAYOUT_ZTR
+    _derived_caches = {'hinterp_target_xxloc': ('_plan', '_fused_items'),
+                       'hinterp_target_yyloc': ('_plan', '_fused_items')}
 
     def init_grid(self):  # :17-25
         self.meta_convert_to_float('dx', 'dy', 'dz', 'z_start', 'SOR_parameter', 'iteration_tolerance')
@@ -139,8 +141,11 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
     def _run_car_d(self, outputs, stages=_lib.MT_STAGE_ALL, existing=()):
         lib = _lib.load()
         din = _lib.mt_dyn_in_t()
+        keep = []   # broadcast temporaries of non-field attributes stay alive until the launch
         for k in ("u", "v", "w", "p", "T", "Th", "qv", "f"):
-            setattr(din, k, self.device(k).data_ptr() if self._has(k) else None)
+            if self._has(k):
+                keep.append(self.device(k, ndim=2 if k == "f" else 3))
+                setattr(din, k, keep[-1].data_ptr())
         hyd = self._hydro_names()
         if not hyd and ('density_factor' in outputs or 'Th_rho' in outputs):
             print('Warning: no liquid / solid hydrometeor mixing ratio set; Th_rho will equal Th_v')

@@ -33,6 +33,9 @@ _HYDRO_SETS = (("qc", "qr", "qi", "qs", "qg", "qh"), ("qc", "qr", "qi", "qs", "q
 
 class cylindrical_grid(gridsystem, calc_thermaldynamic):
     _layout = _lib.MT_LAYOUT_TRZ
+    # the stencil plan / work items follow the targets, the sin / cos / r tables follow the axes
+    _derived_caches = {'xTR': ('_plan', '_fused_items'), 'yTR': ('_plan', '_fused_items'),
+                       'theta': ('_grid_cache',), 'r': ('_grid_cache',)}
 
     def init_grid(self):  # :19-25
         self.meta_convert_to_float('dr', 'dtheta', 'dz', 'dt', 'z_start', 'r_start', 'theta_start')
@@ -381,13 +384,26 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         return ()
 
     def _run_cyl_d(self, outputs, stages=_lib.MT_STAGE_ALL, existing=()):
-        """One ``mt_cyl_d`` call producing `outputs`; `existing` names are stage-A fields that are
-        already on the grid and only read (stage B)."""
+        """One ``mt_cyl_d`` call producing `outputs`.  `existing`: point-wise fields of earlier calls
+        (Th_rho, rho) that a stage-B-only call reads from the grid.
+
+        When the grid already holds ``vr`` / ``vt`` and the call does not (re)compute them, they are
+        handed in as INPUTS (``mt_dyn_in_t.vr / .vt``) and used as they are -- exactly what the
+        reference's methods do with ``self.vr`` / ``self.vt`` (user-assigned or storm-relative winds
+        included); u and v are then not needed at all."""
         lib = _lib.load()
         g = self._grid_struct()
         din = _lib.mt_dyn_in_t()
+        keep = []   # broadcast temporaries of non-field attributes (a scalar f, ...) stay alive until the launch
         for k in ("u", "v", "w", "p", "T", "Th", "qv", "f"):
-            setattr(din, k, self.device(k).data_ptr() if self._has(k) else None)
+            if self._has(k):
+                keep.append(self.device(k, ndim=2 if k == "f" else 3))
+                setattr(din, k, keep[-1].data_ptr())
+        if 'vr' not in outputs and 'vt' not in outputs:
+            for k in ("vr", "vt"):
+                if self._has(k):
+                    keep.append(self.device(k))
+                    setattr(din, k, keep[-1].data_ptr())
         hyd = self._hydro_names()
         if not hyd and ('density_factor' in outputs or 'Th_rho' in outputs):
             print('Warning: no liquid / solid hydrometeor mixing ratio set; Th_rho will equal Th_v')
@@ -399,10 +415,25 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             bufs[k] = self._new(dtype=D.torch().uint8 if k == 'strain_region' else None)
             setattr(dout, k, bufs[k].data_ptr())
         for k in existing:
-            setattr(dout, k, self.device(k).data_ptr())
+            keep.append(self.device(k))
+            setattr(dout, k, keep[-1].data_ptr())
         _lib.check(lib.mt_cyl_d(g, din, dout, stages, D.stream()), 'mt_cyl_d')
         for k, b in bufs.items():
             self._put(k, b)
+
+    def _stencil(self, outputs, existing=()):
+        """Stencil outputs from the grid's vr / vt (stage B alone) or, when the grid does not hold them
+        yet, from u, v in ONE fused call that also leaves vr / vt on the grid -- the reference's
+        ``if 'vr' not in dir(self): self.calc_vr_vt()`` followed by the method body."""
+        if self._has('vr', 'vt'):
+            self._run_cyl_d(outputs, _lib.MT_STAGE_B, existing=existing)
+        elif existing:   # inputs of stage B that are fields of the grid: two calls
+            self.calc_vr_vt()
+            self._run_cyl_d(outputs, _lib.MT_STAGE_B, existing=existing)
+        elif self._has('u', 'v'):
+            self._run_cyl_d(['vr', 'vt'] + list(outputs), _lib.MT_STAGE_ALL)
+        else:
+            raise AttributeError('u and v must be set first')
 
     def calc_diagnostics(self, outputs=None):
         """The whole cyl_d diagnostic set (test_cyl_dynamics.py:148-227) in two HBM passes."""
@@ -459,8 +490,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             raise AttributeError('f must be set first')
         if not self._has('vt') or not self._has('vr'):
             self.calc_vr_vt()
-        # vt is recomputed from u, v by stage A (same expression, same bits)
-        self._run_cyl_d(['aam', 'vr', 'vt'], _lib.MT_STAGE_A)
+        self._run_cyl_d(['aam'], _lib.MT_STAGE_A)   # from the grid's vt, as it is
 
     def calc_agradient_force(self):  # :335-348
         if not self._has('vt'):
@@ -469,8 +499,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             self.calc_rho()
         if self._has('p', 'f'):
             self._run_cyl_d(['coriolis_force', 'centrifugal_force'], _lib.MT_STAGE_A)
-            self._run_cyl_d(['radial_PG_force', 'agradient_force'], _lib.MT_STAGE_B,
-                            existing=('vr', 'vt', 'rho') if self._has('vr') else ('vt', 'rho'))
+            self._run_cyl_d(['radial_PG_force', 'agradient_force'], _lib.MT_STAGE_B, existing=('rho',))
         else:
             raise AttributeError('p and f must be set first')
 
@@ -525,30 +554,27 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             self.calc_vr_vt()
 
     def calc_vorticity_3D(self):  # :383-394
-        self._need_vr_vt()
-        if self._has('w'):
-            self._run_cyl_d(['zeta_r', 'zeta_t', 'zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
-        else:
+        if not self._has('w'):
+            self._need_vr_vt()
             raise AttributeError('w must be set first')
+        self._stencil(['zeta_r', 'zeta_t', 'zeta_z'])
 
     def calc_abs_vorticity_3D(self):  # :396-402
         if not self._has('zeta_z'):
             self.calc_vorticity_3D()
         if self._has('f'):
-            self._run_cyl_d(['abs_zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+            self._stencil(['abs_zeta_z'])
         else:
             raise AttributeError('f must be set first')
 
     def calc_divergence_hori(self):  # :404-409
-        self._need_vr_vt()
-        self._run_cyl_d(['div_hori'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        self._stencil(['div_hori'])
 
     def calc_divergence(self):  # :412-421
-        self._need_vr_vt()
-        if self._has('w'):
-            self._run_cyl_d(['div'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
-        else:
+        if not self._has('w'):
+            self._need_vr_vt()
             raise AttributeError('w must be set first')
+        self._stencil(['div'])
 
     def calc_density_factor(self):  # :423-447
         if not self._has('qv'):
@@ -568,30 +594,28 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             self.calc_abs_vorticity_3D()
         if not self._has('rho'):
             self.calc_rho()
-        self._run_cyl_d(['PV'], _lib.MT_STAGE_B, existing=('vr', 'vt', 'Th_rho', 'rho'))
+        self._stencil(['PV'], existing=('Th_rho', 'rho'))
 
     def calc_vorticity_z(self):  # :473-477
-        self._need_vr_vt()
-        self._run_cyl_d(['zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        self._stencil(['zeta_z'])
 
     def calc_abs_vorticity_z(self):  # :479-485
         if not self._has('zeta_z'):
             self.calc_vorticity_z()
         if self._has('f'):
-            self._run_cyl_d(['abs_zeta_z'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+            self._stencil(['abs_zeta_z'])
         else:
             raise AttributeError('f must be set first')
 
     def calc_deformation(self):  # :487-493
-        self._need_vr_vt()
-        self._run_cyl_d(['shear_deform', 'stretch_deform'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        self._stencil(['shear_deform', 'stretch_deform'])
 
     def calc_filamentation(self):  # :495-508
         if not self._has('shear_deform') or not self._has('stretch_deform'):
             self.calc_deformation()
         if not self._has('zeta_z'):
             self.calc_vorticity_z()
-        self._run_cyl_d(['filamentation_time', 'strain_region'], _lib.MT_STAGE_B, existing=('vr', 'vt'))
+        self._stencil(['filamentation_time', 'strain_region'])
 
     # ------------------------------------------------------- azimuthal statistics (a13, 8f-1)
     def _azimuthal(self, varname, want_axisym):

@@ -96,8 +96,14 @@ class gridsystem:
         s3 = self._grid_shape3()
         return tuple(shape) == s3 or tuple(shape) == s3[1:]
 
+    #: attribute name -> cached objects (in ``__dict__``) that are derived from it and must be rebuilt
+    #: when the user assigns it directly, as the reference permits (``cyl.xTR = ...``)
+    _derived_caches = {}
+
     def __setattr__(self, name, value):
         fields = self.__dict__.get("_fields")
+        for cache in self._derived_caches.get(name, ()):
+            self.__dict__.pop(cache, None)
         if fields is not None and not name.startswith("_"):
             is_np = isinstance(value, np.ndarray) and value.dtype.kind == "f"
             is_t = D.is_tensor(value) and value.is_floating_point()
@@ -150,10 +156,30 @@ class gridsystem:
             return D.permute3(t, (nt, nr, nz), (nr, 1, nt * nr))
         return t
 
-    def device(self, name):
+    def device(self, name, ndim=3):
         """CUDA tensor of a field in the canonical layout ((Nt,Nr,Nz) memory order for TRZ grids,
-        (Nz,Nt,Nr) for ZTR grids; (Nt,Nr) for 2-D fields), uploading it if it is host-only."""
-        f = self._fields[name]
+        (Nz,Nt,Nr) for ZTR grids; (Nt,Nr) for 2-D fields), uploading it if it is host-only.
+
+        An attribute that is not a stored field -- a scalar (``cyl.f = 5e-5``), an integer array, a
+        1-D profile -- is broadcast to the grid shape (``ndim`` = 3: (Nz,Nt,Nr), 2: (Nt,Nr)) as
+        float64, the way the reference's NumPy expressions broadcast it (``self.f*self.vt``)."""
+        f = self._fields.get(name)
+        if f is None:
+            if name not in self.__dict__:
+                raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+            val = np.asarray(self.__dict__[name])
+            shape = self._grid_shape3() if ndim == 3 else self._grid_shape3()[1:]
+            if val.dtype.kind not in "fiub":
+                raise TypeError(f"attribute {name!r} ({val.dtype}) is not numeric: expected an array "
+                                f"broadcastable to {shape}")
+            try:
+                b = np.broadcast_to(val, shape)
+            except ValueError:
+                raise TypeError(f"attribute {name!r} of shape {val.shape} cannot be broadcast to the grid "
+                                f"shape {shape}") from None
+            return self._canonical(D.to_device(np.ascontiguousarray(b, dtype=np.float64)))
+        if f.ndim == 3 and ndim == 2:
+            raise TypeError(f"field {name!r} is 3-D where a 2-D (Ntheta, Nr) / (Ny, Nx) field is expected")
         if f.dev is None:
             f.dev = self._canonical(D.to_device(f.host))
         return f.dev

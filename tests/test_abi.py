@@ -35,7 +35,7 @@ def test_header_symbols_exported(built):
     from meteotools_b200 import _lib
     assert set(_lib.EXPORTED_SYMBOLS) == set(names), set(_lib.EXPORTED_SYMBOLS) ^ set(names)
     L = _lib.load()
-    assert L.mt_abi_version() == 1 and L.mt_launch_count() == 0
+    assert L.mt_abi_version() == 2 and L.mt_launch_count() == 0
 
 
 def test_library_is_sm100a_only(built):
