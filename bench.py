@@ -297,6 +297,57 @@ def bind_near_gpu(local_rank):
     return 0
 
 
+def link_probe(h2d_bytes, d2h_bytes, barrier, reps=10):
+    """ms for moving exactly one step's bytes over the host link with nothing else going on: one
+    cudaMemcpyAsync per direction, pinned buffers, two streams, both directions at once."""
+    import torch
+    hs = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    hd = torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
+    ds = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    dd = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    ts = []
+    for i in range(reps + 2):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            ds.copy_(hs, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hd.copy_(dd, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+        if i >= 2:
+            ts.append((time.perf_counter() - t0) * 1e3)
+    del hs, hd, ds, dd
+    torch.cuda.empty_cache()
+    return float(np.median(ts))
+
+
+def placement(local_rank, cpus_bound):
+    """Where this rank's GPU and host threads sit: PCI bus id, the GPU's NUMA node (sysfs), the CPUs the
+    process may run on."""
+    info = {"local_rank": local_rank, "cpus_bound_near_gpu": cpus_bound,
+            "cpus_allowed": len(os.sched_getaffinity(0))}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        addr = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        info["pci"] = addr
+        with open(f"/sys/bus/pci/devices/{addr}/numa_node") as fh:
+            info["gpu_numa_node"] = int(fh.read().strip())
+    except Exception as e:   # not every VM exposes it
+        info["gpu_numa_node"] = None
+        info["note"] = str(e)[:80]
+    try:
+        with open("/sys/devices/system/node/online") as fh:
+            info["numa_nodes_online"] = fh.read().strip()
+    except OSError:
+        pass
+    return info
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -307,6 +358,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--streams", type=int, default=2, help="time steps in flight in the device-resident leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary rows (S3 / S5 / FD2 / interplevel / level shards)")
+    ap.add_argument("--min-timed-s", type=float, default=1.0, help="repeat the timed block of K steps until this much GPU time")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -362,18 +415,31 @@ def main():
     run_steps(args.warmup * nslots)
     barrier()
     launches0 = lib.mt_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    torch.cuda.synchronize()
-    launches = lib.mt_launch_count() - launches0
-    ms = e0.elapsed_time(e1) / args.steps
-    barrier()
+    # The timed block is EXACTLY K steps between barrier + synchronize on both sides; the block is repeated
+    # until >= --min-timed-s of GPU time has been measured (sustained behaviour, >= 10 clock samples under
+    # load) and the MEDIAN block is reported (every block is listed in `timed_blocks_ms`).
+    blocks = []
+    while True:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        blocks.append(e0.elapsed_time(e1))
+        barrier()
+        done = torch.tensor([1.0 if (sum(blocks) >= args.min_timed_s * 1e3 or len(blocks) >= 400) else 0.0],
+                            device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(done, op=dist.ReduceOp.MIN)   # every rank runs the same number of blocks
+        if done.item() == 1.0:
+            break
+    launches = (lib.mt_launch_count() - launches0) // len(blocks)
+    blk = torch.tensor(blocks, device="cuda", dtype=torch.float64)
     if world > 1:
-        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+        dist.all_reduce(blk, op=dist.ReduceOp.MAX)        # per block: the slowest rank
+    blocks = [float(x) for x in blk.tolist()]
+    ms = float(np.median(blocks)) / args.steps
     value = world * NPTS / (ms * 1e-3)
 
     # ---------------- roofline: per-launch CUDA events over the same steps ----------------------
@@ -466,13 +532,55 @@ def main():
     e2e32io_s = (time.perf_counter() - t0) / n_stream
     assert r["Th_e"].dtype == np.float32
     del ts32io, step32
-    if world > 1:
-        te = torch.tensor([e2e_s, e2e_single_s, e2e32_s, e2e32io_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_single_s, e2e32_s, e2e32io_s = (float(x) for x in te.tolist())
     y0, y1, x0, x1 = cyl._target_box(NX, NY, DX, DX)
     h2d = (len(NAMES3D) + 1) * NZ * (y1 - y0) * (x1 - x0) * 8 + 2 * NY * NX * 8
     d2h = len(td_names) * NPTS * 8
+    # (e) everything the reference's set_data + calc_* leave on the grid: the 12 interpolated fields too
+    all_names = td_names + [n for n in NAMES3D if n not in td_names]
+    ts_all = TimeStepStream(cyl, (NZ, NY, NX), DX, DX, NAMES3D, names2d=("f",), hgt=True, outputs=all_names,
+                            slots=int(os.environ.get("MT_E2E_SLOTS", 3)))
+    for _ in ts_all.process([step] * 3):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    for _, r in ts_all.process([step] * n_stream):
+        pass
+    torch.cuda.synchronize()
+    e2e_all_s = (time.perf_counter() - t0) / n_stream
+    assert r["u"].shape == (CYL["Nz"], CYL["Ntheta"], CYL["Nr"])
+    d2h_all = len(all_names) * NPTS * 8
+    del ts_all, r
+    torch.cuda.empty_cache()
+    # (f) what the host<->device link alone gives for exactly these bytes, all ranks at once
+    link_ms = link_probe(h2d, d2h, barrier)
+    link_all_ms = link_probe(h2d, d2h_all, barrier)
+    if world > 1:
+        te = torch.tensor([e2e_s, e2e_single_s, e2e32_s, e2e32io_s, e2e_all_s, link_ms, link_all_ms], device="cuda",
+                          dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s, e2e_single_s, e2e32_s, e2e32io_s, e2e_all_s, link_ms, link_all_ms = (float(x) for x in te.tolist())
+    place = placement(local, near)
+    if world > 1:
+        places = [None] * world
+        dist.all_gather_object(places, place)
+    else:
+        places = [place]
+    # ---------------- secondary rows (SURVEY 8d S3 / S5 / FD2 / interplevel; level shards at N > 1) ----------
+    secondary = []
+    if not args.no_secondary:
+        import bench_rows
+        if world == 1:
+            secondary = bench_rows.secondary_single_gpu(reps=10)
+        else:
+            unsharded = None
+            if rank == 0:   # the strong-scaling reference: the same S5 on one GPU
+                r5 = bench_rows.bench_dyn("car", bench_rows.CAR_S5, 5, "S5 car_d, 17 outputs, (80,2000,2000), one GPU (rank 0)")
+                unsharded = r5["ms"]
+                secondary.append(r5)
+            barrier()
+            sh = bench_rows.sharded_car_d(rank, world, dist, reps=10, unsharded_ms=unsharded)
+            if sh is not None:
+                secondary.append(sh)
 
     if rank == 0:
         out = {
@@ -480,8 +588,23 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(),
             "clocks": clk, "gpu_launches": int(launches), "steps_in_flight": nslots, "cpus_bound_near_gpu": near,
+            "timed_reps": len(blocks), "timed_region_s": sum(blocks) * 1e-3,
+            "timed_blocks_ms": {"median": float(np.median(blocks)), "min": float(np.min(blocks)),
+                                "max": float(np.max(blocks)), "steps_per_block": args.steps},
             "e2e": {"value": world * NPTS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": n_stream,
+                    "link_floor_ms": link_ms, "frac_of_link": link_ms / (e2e_s * 1e3),
+                    "link_probe": "one cudaMemcpyAsync of h2d_bytes_per_step (pinned -> device) and one of "
+                                  "d2h_bytes_per_step (device -> pinned) on two streams at once, all ranks together; "
+                                  "median of 10",
+                    "placement": places,
+                    "all_fields": {"value": world * NPTS / e2e_all_s, "ms_per_step": e2e_all_s * 1e3,
+                                   "d2h_bytes_per_step": int(d2h_all), "link_floor_ms": link_all_ms,
+                                   "frac_of_link": link_all_ms / (e2e_all_s * 1e3),
+                                   "note": "the 13 cyl_td outputs AND the 12 interpolated set_data fields downloaded: "
+                                           "everything the reference's set_data + calc_* leave on the grid as host "
+                                           "arrays (the headline downloads the 13 outputs; the others stay on the "
+                                           "device until read: 52 MB each)"},
                     "path": "pipeline.TimeStepStream.process (pinned host arrays in -> pinned host arrays out, "
                             "three slots: D2H of step k overlaps H2D of step k+1; the link alone takes 13.9 ms for these bytes, "
                             "scratch/pcie_probe.py)",
@@ -498,7 +621,7 @@ def main():
                                            "note": "float32 sources and results rounded to float32 on the device "
                                                    "(the precision of the reference's netCDF cache): half the "
                                                    "bytes both ways; NOT the headline, which keeps float64 results"}},
-            "roofline": roof, "tc_iterations": tc_iters,
+            "roofline": roof, "tc_iterations": tc_iters, "secondary": secondary,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(step, os.cpu_count() or 1)

@@ -380,6 +380,27 @@ typedef struct { /* cartesian_grid.py:232-364 */
 int mt_car_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_car_d_out_t *out, int stages,
              mt_stream_t stream);
 
+/* ---- multi-GPU: one-level vertical halo exchange over NCCL (csrc/halo.cu) -----------------
+ * Vertical levels couple only through FD2(., dz, axis=0) (grids/cartesian_grid.py:250-251,275,321,
+ * grids/cylindrical_grid.py:388-389,419,466): a rank that owns a contiguous block of levels of a
+ * MT_LAYOUT_ZTR array needs ONE plane of each z-differentiated field from each neighbour.
+ * The library never links against NCCL: it binds at run time to the libnccl.so.2 already loaded in the
+ * process (torch.distributed's), or to `path` (mt_nccl_load; NULL = only look for a loaded copy).
+ * Communicator: rank 0 calls mt_nccl_unique_id(128-byte buffer), the bytes reach the other ranks by any
+ * means (torch.distributed broadcast), every rank calls mt_nccl_comm_init.
+ * mt_halo_exchange: fields[f] are (nz_local, ny, nx) C-order device arrays whose owned levels are
+ * [halo_lo, nz_local - halo_hi); for each field, in ONE NCCL group on `stream`: level halo_lo is sent to
+ * rank_lo and level 0 received from it (when halo_lo = 1), level nz_local-1-halo_hi is sent to rank_hi
+ * and level nz_local-1 received from it (when halo_hi = 1).  Asynchronous on `stream`: run it on a side
+ * stream while mt_car_d / mt_cyl_d work on the levels that need no halo (mt_grid_t.sub_lo / sub_hi). */
+int mt_nccl_load(const char *path);
+int mt_nccl_version(void); /* NCCL_VERSION_CODE of the bound library, 0 when none */
+int mt_nccl_unique_id(void *id128);
+int mt_nccl_comm_init(void **comm, int nranks, int rank, const void *id128);
+int mt_nccl_comm_destroy(void *comm);
+int mt_halo_exchange(void *comm, double *const *fields, int nfields, int64_t plane_elems, int64_t nz_local,
+                     int halo_lo, int halo_hi, int rank_lo, int rank_hi, mt_stream_t stream);
+
 /* ---- azimuthal statistics (a13; cylindrical_grid.py:214-235) -------------------------------
  * sym[z,r] = nanmean over theta, asy = var - sym (asy may be NULL). */
 int mt_azimuthal_mean(const double *var, const mt_grid_t *g, double *sym, double *asy,

@@ -146,6 +146,12 @@ _SIGS = {
                          c_int, c_vp]),
     "mt_car_d": (c_int, [ct.POINTER(mt_grid_t), ct.POINTER(mt_dyn_in_t), ct.POINTER(mt_car_d_out_t),
                          c_int, c_vp]),
+    "mt_nccl_load": (c_int, [ct.c_char_p]),
+    "mt_nccl_version": (c_int, []),
+    "mt_nccl_unique_id": (c_int, [c_vp]),
+    "mt_nccl_comm_init": (c_int, [ct.POINTER(c_vp), c_int, c_int, c_vp]),
+    "mt_nccl_comm_destroy": (c_int, [c_vp]),
+    "mt_halo_exchange": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "mt_azimuthal_mean": (c_int, [c_vp, ct.POINTER(mt_grid_t), c_vp, c_vp, c_vp]),
     "mt_cast_f32_f64": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mt_cast_f64_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),

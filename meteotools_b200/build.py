@@ -27,7 +27,7 @@ path_of_meteotools = os.path.dirname(os.path.abspath(__file__))
 platform_name = platform.system()
 
 SOURCES = ["api.cu", "interp.cu", "legacy.cu", "interplevel.cu", "fd.cu", "thermo.cu", "diag.cu",
-           "util.cu", "setdata_tma.cu", "reduce.cu", "spline.cu", "diag_tma.cu"]
+           "util.cu", "setdata_tma.cu", "reduce.cu", "spline.cu", "diag_tma.cu", "halo.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -88,7 +88,7 @@ class task:
         self.ptxas_log = "".join(r[1] for r in results)
         newest = max(os.path.getmtime(o) for o in objs)
         if force or not os.path.exists(self.output) or os.path.getmtime(self.output) < newest:
-            cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", self.output] + objs
+            cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", self.output] + objs + ["-ldl"]
             proc = subprocess.run(cmd, capture_output=True, text=True)
             if proc.returncode != 0:
                 raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")

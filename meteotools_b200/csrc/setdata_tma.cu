@@ -64,6 +64,16 @@ struct __align__(16) Meta {   // one staged target (two 16-byte words; a third w
 static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
 
 using namespace mt::tma;   // smem_u32, mbar_*, load_3d (csrc/tma.cuh)
+// store of the 16-byte result pairs (A/B builds with -DMT_TMA_STORE_KIND=n: scratch/build_variant.sh)
+#if !defined(MT_TMA_STORE_KIND) || MT_TMA_STORE_KIND == 0
+#define MT_TMA_ST(ptr, val) __stcs(ptr, val)
+#elif MT_TMA_STORE_KIND == 1
+#define MT_TMA_ST(ptr, val) (*(ptr) = (val))
+#elif MT_TMA_STORE_KIND == 2
+#define MT_TMA_ST(ptr, val) __stcg(ptr, val)
+#else
+#define MT_TMA_ST(ptr, val) __stwt(ptr, val)
+#endif
 #ifdef MT_TMA_TIMING
 // phase clocks of consumer warp 0 (debug builds only: scratch/tma_timing.py)
 __device__ unsigned long long g_tma_timing[8];
@@ -420,8 +430,8 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                         if (ter1 > l + 1) r1.y = nan_f64();
                     }
                     if (EXACT || wide) {
-                        __stcs(reinterpret_cast<double2 *>(o0 + l), r0);
-                        if (two) __stcs(reinterpret_cast<double2 *>(o1 + l), r1);
+                        MT_TMA_ST(reinterpret_cast<double2 *>(o0 + l), r0);
+                        if (two) MT_TMA_ST(reinterpret_cast<double2 *>(o1 + l), r1);
                     } else {   // odd level count / odd row pitch: rows are only 8-byte aligned
                         __stcs(o0 + l, r0.x);
                         if (l + 1 < nlev) __stcs(o0 + l + 1, r0.y);

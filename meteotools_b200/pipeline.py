@@ -244,9 +244,64 @@ class CylStepPipeline:
                 self.g._put(k, v, nd)
 
 
+class HaloComm:
+    """The library's own NCCL communicator for the level-shard halo exchange (csrc/halo.cu,
+    ``mt_halo_exchange``): rank 0 creates the NCCL unique id, ``torch.distributed`` carries its 128 bytes
+    to the other ranks, every rank joins.  The library binds to the NCCL copy torch already loaded.
+
+        comm = HaloComm(rank, world)            # torch.distributed must be initialised (any backend)
+        comm.exchange([v, w], hlo, hhi, stream) # asynchronous on `stream`
+    """
+
+    def __init__(self, rank, world, dist=None):
+        import ctypes as ct
+        import torch.distributed as dist_mod
+        t = D.require_cuda()
+        dist = dist or dist_mod
+        self.lib, self.rank, self.world = _lib.load(), rank, world
+        path = None
+        try:   # only needed when no NCCL is resident yet (torch loads it with torch.cuda / distributed)
+            import os
+            import nvidia.nccl as _n
+            cand = os.path.join(list(_n.__path__)[0], "lib", "libnccl.so.2")
+            path = cand.encode() if os.path.exists(cand) else None
+        except Exception:
+            pass
+        _lib.check(self.lib.mt_nccl_load(path), "mt_nccl_load")
+        idbuf = ct.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(self.lib.mt_nccl_unique_id(idbuf), "mt_nccl_unique_id")
+        backend = dist.get_backend()
+        carrier = t.frombuffer(bytearray(idbuf.raw), dtype=t.uint8).clone()
+        if backend == "nccl":
+            carrier = carrier.cuda()
+        dist.broadcast(carrier, src=0)
+        raw = bytes(carrier.cpu().numpy().tobytes())
+        self.comm = ct.c_void_p()
+        _lib.check(self.lib.mt_nccl_comm_init(ct.byref(self.comm), world, rank, raw), "mt_nccl_comm_init")
+
+    def exchange(self, tensors, halo_lo, halo_hi, stream=None):
+        """One halo level of every (nz_local, ny, nx) C-order tensor, asynchronous on `stream`."""
+        if not (halo_lo or halo_hi) or not tensors:
+            return
+        first = tensors[0]
+        plane = int(first.shape[1]) * int(first.shape[2])
+        for x in tensors:
+            assert x.is_contiguous() and x.shape == first.shape and x.dtype == first.dtype
+        s = stream.cuda_stream if stream is not None else D.stream()
+        _lib.check(self.lib.mt_halo_exchange(self.comm, D.ptr_array(tensors), len(tensors), plane,
+                                             int(first.shape[0]), int(halo_lo), int(halo_hi),
+                                             self.rank - 1 if halo_lo else -1, self.rank + 1 if halo_hi else -1, s),
+                   "mt_halo_exchange")
+
+    def close(self):
+        if self.comm:
+            _lib.check(self.lib.mt_nccl_comm_destroy(self.comm), "mt_nccl_comm_destroy")
+            self.comm = None
+
+
 class LevelShardDyn:
-    """cyl_d / car_d of ONE time step on ONE level shard: ``stage_a()``, then the caller
-    exchanges one halo level of ``halo_fields`` with the neighbouring shards, then ``stage_b()``.
+    """cyl_d / car_d of ONE time step on ONE level shard.
 
     kind      "car" or "cyl"
     local     dict name -> CUDA tensor (nz_own, nt, nr) C-order ("ZTR") with the shard's OWNED levels
@@ -255,12 +310,22 @@ class LevelShardDyn:
     spacings  (dz, dt, dr)  i.e. (dz, dy, dx) or (dz, dtheta, dr)
     shard     (lo, hi, halo_lo, halo_hi) from ``level_shard``
     tables    cyl only: dict(r=, sin_t=, cos_t=) CUDA tensors
-    The one-sided FD2 formulas are used only at the global first / last level; everywhere else
-    stage B differentiates across the halo levels.
+
+    Only FD2(., dz, axis=0) couples levels: one halo plane of the z-differentiated INPUTS
+    (``halo_inputs``: v, w -- and u on a cylindrical grid, whose rotation mixes u and v) and of the derived
+    theta_rho (``halo_derived``) is needed from each neighbour; the one-sided formulas are used only at
+    the global first / last level.  ``run(comm)`` overlaps the exchange with the work that does not need it:
+
+        side stream:  exchange(halo_inputs) ........ [wait stage A] exchange(theta_rho)
+        main stream:  stage A (thermodynamic point-wise fields) -> stage B on the levels that need no halo
+                      -> [wait side] stage B on the one or two boundary levels
+
+    ``stage_a`` / ``stage_b`` / ``halo_fields`` remain for callers that exchange by other means.
     """
 
     def __init__(self, kind, local, f2d, spacings, shard, nz_global, outputs, tables=None):
         t = D.require_cuda()
+        self.t = t
         self.lib, self.kind, self.outputs = _lib.load(), kind, list(outputs)
         lo, hi, hlo, hhi = shard
         self.hlo, self.hhi, self.nz_own = hlo, hhi, hi - lo
@@ -300,28 +365,86 @@ class LevelShardDyn:
             setattr(dout, k, self.outs[k].data_ptr())
         self._g, self._din, self._dout = g, din, dout
         self._call = self.lib.mt_cyl_d if kind == "cyl" else self.lib.mt_car_d
-        # the z-differentiated fields: one halo level of each is exchanged between the stages
-        self.halo_fields = [self.outs["Th_rho"], self.fields["w"]] + \
-            ([self.outs["vr"], self.outs["vt"]] if kind == "cyl" else [self.fields["v"]])
+        # the z-differentiated fields: inputs first (they can travel at once), theta_rho after stage A
+        self.halo_inputs = [self.fields["w"], self.fields["v"]] + ([self.fields["u"]] if kind == "cyl" else [])
+        self.halo_derived = [self.outs["Th_rho"]]
+        self.halo_fields = self.halo_inputs + self.halo_derived
+        self._side = None
+
+    def _stage(self, stages, sub=(0, 0)):
+        self._g.sub_lo, self._g.sub_hi = sub
+        _lib.check(self._call(self._g, self._din, self._dout, stages, D.stream()), f"stages {stages}")
+        self._g.sub_lo, self._g.sub_hi = 0, 0
 
     def stage_a(self):
-        _lib.check(self._call(self._g, self._din, self._dout, _lib.MT_STAGE_A, D.stream()), "stage A")
+        """Thermodynamic point-wise fields of all local levels (Tv, rho, density factor, theta, theta_rho)."""
+        self._stage(_lib.MT_STAGE_A | _lib.MT_STAGE_WIND_IN_B)
 
-    def stage_b(self):
-        _lib.check(self._call(self._g, self._din, self._dout, _lib.MT_STAGE_B, D.stream()), "stage B")
+    def stage_b(self, sub=(0, 0)):
+        """Stencil outputs + the wind-derived point-wise outputs of the owned levels [sub[0], sub[1])
+        (indices into the owned block; (0, 0) = all of it)."""
+        self._stage(_lib.MT_STAGE_B | _lib.MT_STAGE_WIND_IN_B, sub)
+
+    def interior(self):
+        """Owned levels whose z-stencil stays inside the shard: they need no halo plane."""
+        return (1 if self.hlo else 0, self.nz_own - (1 if self.hhi else 0))
+
+    def stage_b_split(self):
+        """stage_b() as run() issues it: interior levels first, then the boundary levels."""
+        a, b = self.interior()
+        if b > a:
+            self.stage_b((a, b))
+        if self.hlo:
+            self.stage_b((0, 1))
+        if self.hhi and (self.nz_own > 1 or not self.hlo):
+            self.stage_b((self.nz_own - 1, self.nz_own))
+
+    def run(self, comm=None):
+        """The whole set with the halo exchange overlapped (see the class docstring).  `comm`: a HaloComm,
+        or None for a single shard."""
+        t = self.t
+        if comm is None or not (self.hlo or self.hhi):
+            self.stage_a()
+            self.stage_b()
+            return
+        main = t.cuda.current_stream()
+        if self._side is None:
+            self._side = t.cuda.Stream()
+        side = self._side
+        side.wait_stream(main)                      # the inputs are ready
+        comm.exchange(self.halo_inputs, self.hlo, self.hhi, side)
+        self.stage_a()
+        ev_a = t.cuda.Event()
+        ev_a.record(main)
+        side.wait_event(ev_a)                       # theta_rho of the boundary levels exists
+        comm.exchange(self.halo_derived, self.hlo, self.hhi, side)
+        ev_h = t.cuda.Event()
+        ev_h.record(side)
+        a, b = self.interior()
+        if b > a:
+            self.stage_b((a, b))                    # overlaps the planes in flight
+        main.wait_event(ev_h)
+        if self.hlo:
+            self.stage_b((0, 1))
+        if self.hhi and (self.nz_own > 1 or not self.hlo):
+            self.stage_b((self.nz_own - 1, self.nz_own))
 
     def result(self):
         return {k: self.outs[k][self.hlo:self.hlo + self.nz_own] for k in self.outputs}
 
 
 def dyn_level_sharded(kind, local, f2d, spacings, shard, nz_global, outputs, rank, world, tables=None,
-                      dist=None):
-    """Distributed form of ``LevelShardDyn``: stage A, NCCL halo exchange with rank+-1, stage B."""
+                      dist=None, comm=None):
+    """Distributed form of ``LevelShardDyn``.  With a ``HaloComm`` the exchange runs through the library's
+    NCCL communicator, overlapped with the interior levels; without one (CPU tests with gloo, or a caller
+    that has no NCCL) the planes travel through ``torch.distributed`` point-to-point calls."""
     job = LevelShardDyn(kind, local, f2d, spacings, shard, nz_global, outputs, tables)
+    if comm is not None or world == 1:
+        job.run(comm if world > 1 else None)
+        return job.result()
     job.stage_a()
-    if world > 1:
-        D.torch().cuda.current_stream().synchronize()
-        halo_exchange_levels(job.halo_fields, shard[2], shard[3], rank, world, dist)
+    D.torch().cuda.current_stream().synchronize()
+    halo_exchange_levels(job.halo_fields, shard[2], shard[3], rank, world, dist)
     job.stage_b()
     return job.result()
 

@@ -122,6 +122,29 @@ __global__ void k_rowmarch(Ptrs P, int nz, int ny, int nx, int ys)
     }
 }
 
+// the store pattern of k_setdata_tma: rows of 60 doubles, one warp per row, 30 lanes x 16 bytes, 12 streams.
+// pitch 60 (dense rows: 480-byte rows start at multiples of 32 bytes) or 64 (padded); `perm`: rows visited in
+// a scattered order (as the source-tile bucketing does) instead of sequentially
+__global__ void k_rows(Ptrs P, long long nrows, int pitch, int perm)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < nrows; i += nwarp) {
+        long long row = i;
+        if (perm) row = (i * 7919LL) % nrows;   // nrows is not a multiple of 7919
+        if (lane < 30)
+            for (int k = 0; k < P.nw; ++k)
+                __stcs(reinterpret_cast<double2 *>(P.w[k] + row * pitch) + lane, make_double2((double)k, (double)lane));
+    }
+}
+// the same bytes written as aligned 512-byte chunks (what an aligned-group store order would issue)
+__global__ void k_chunks512(Ptrs P, long long n)
+{
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2; i < n; i += (long long)gridDim.x * blockDim.x * 2)
+        for (int k = 0; k < P.nw; ++k) __stcs(reinterpret_cast<double2 *>(P.w[k] + i), make_double2((double)k, 1.0));
+}
+
 int main(int argc, char **argv)
 {
     const int nz = argc > 1 ? atoi(argv[1]) : 80, ny = argc > 2 ? atoi(argv[2]) : 1000, nx = argc > 3 ? atoi(argv[3]) : 1000;
@@ -150,6 +173,19 @@ int main(int argc, char **argv)
         printf("%-34s %2dr %2dw  %8.3f ms  %7.1f GB/s\n", name, nr, nw, ms, (nr + nw) * n * 8.0 / ms / 1e6);
         fflush(stdout);
     };
+    if (argc > 8) {   // setdata store pattern
+        const long long nrows = n / 64;
+        for (int perm = 0; perm < 2; ++perm) {
+            char nm[64];
+            snprintf(nm, sizeof nm, "rows of 60, pitch 60, perm %d", perm);
+            run(nm, 0, 12, [&](Ptrs P) { k_rows<<<sms * 8, 256>>>(P, nrows, 60, perm); });
+            snprintf(nm, sizeof nm, "rows of 60, pitch 64, perm %d", perm);
+            run(nm, 0, 12, [&](Ptrs P) { k_rows<<<sms * 8, 256>>>(P, nrows, 64, perm); });
+        }
+        run("aligned 512-byte chunks", 0, 12, [&](Ptrs P) { k_chunks512<<<sms * 8, 256>>>(P, nrows * 60); });
+        printf("(rows variants move nrows*60*8*12 bytes: scale GB/s by 60/64 = 0.9375 against the printed value)\n");
+        return 0;
+    }
     const bool quick = argc > 4;
     auto set_kind = [&](int k) { CK(cudaMemcpyToSymbol(g_store_kind, &k, sizeof(int))); };
     const int combos[][2] = {{5, 12}, {0, 12}, {9, 5}, {5, 0}};

@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from meteotools_b200 import _lib
+if os.environ.get('MT_LIB'):
+    _lib.LIB_PATH = os.environ['MT_LIB']   # A/B builds (scratch/build_variant.sh)
 from meteotools_b200.pipeline import CylStepPipeline
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 step = bench.make_step(0, pinned=False)
