@@ -588,8 +588,16 @@ int mt_cyl_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_cyl_d_out_t *ou
     MT_REQUIRE((stages & MT_STAGE_ALL) != 0 && (stages & ~(MT_STAGE_ALL | MT_STAGE_WIND_IN_B)) == 0,
                "mt_cyl_d: bad stages %d", stages);
     const mt_cyl_d_out_t &o = *out;
-    const bool given = in->vr && in->vt;   // the caller's vr / vt are used as they are
-    MT_REQUIRE(!(in->vr || in->vt) || given, "mt_cyl_d: vr and vt must be given together");
+    // the caller's vr / vt are used as they are; one of them alone is enough when no requested output reads
+    // the other (calc_agradient_force needs vt only, cylindrical_grid.py:335-348)
+    const bool given = in->vr || in->vt;
+    const bool reads_vr = o.zeta_t || o.zeta_z || o.abs_zeta_z || o.div_hori || o.div || o.PV || o.shear_deform ||
+                          o.stretch_deform || o.filamentation_time || o.strain_region || o.kinetic_energy;
+    const bool reads_vt = o.zeta_r || o.zeta_z || o.abs_zeta_z || o.div_hori || o.div || o.PV || o.shear_deform ||
+                          o.stretch_deform || o.filamentation_time || o.strain_region || o.kinetic_energy ||
+                          o.coriolis_force || o.centrifugal_force || o.agradient_force || o.aam;
+    MT_REQUIRE(!given || ((!reads_vr || in->vr) && (!reads_vt || in->vt)),
+               "mt_cyl_d: the requested outputs read both vr and vt, only one was given");
     MT_REQUIRE(!given || (!o.vr && !o.vt), "mt_cyl_d: vr / vt are inputs of this call, they cannot be outputs too");
     const bool have_uv = in->u && in->v;
     const bool need_ab = o.zeta_r || o.zeta_t || o.zeta_z || o.abs_zeta_z || o.div_hori || o.div || o.PV ||
@@ -598,7 +606,8 @@ int mt_cyl_d(const mt_grid_t *g, const mt_dyn_in_t *in, const mt_cyl_d_out_t *ou
     const bool wind_pw = o.vr || o.vt || o.kinetic_energy || o.coriolis_force || o.centrifugal_force || o.aam;
     const bool b_only = (stages & MT_STAGE_ALL) == MT_STAGE_B && !(stages & MT_STAGE_WIND_IN_B);
     // stage B alone reads the horizontal wind from the vr / vt buffers of an earlier stage-A call
-    const double *vr_src = given ? in->vr : o.vr, *vt_src = given ? in->vt : o.vt;
+    // (a component no output reads is still loaded by the kernels: it may alias the other one)
+    const double *vr_src = given ? (in->vr ? in->vr : in->vt) : o.vr, *vt_src = given ? (in->vt ? in->vt : in->vr) : o.vt;
     MT_REQUIRE(!o.wind_speed || have_uv, "mt_cyl_d: wind_speed needs u and v");
     MT_REQUIRE(!wind_pw || given || have_uv, "mt_cyl_d: u and v (or vr and vt) are required");
     MT_REQUIRE(!((stages & MT_STAGE_B) && need_ab) || (vr_src && vt_src),

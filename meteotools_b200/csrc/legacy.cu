@@ -24,23 +24,17 @@ int mt_interp1d_nonequal_layers(const double *, const double *, int64_t, int64_t
 
 namespace {
 
-// Grow-only device arena + stream, one per process, serialised by a mutex (the reference never
-// calls these concurrently; SURVEY 8b "threading").
+// Grow-only device arena + stream, one per DEVICE (a process that alternates between GPUs keeps one arena
+// on each: nothing is dropped or leaked on a switch), serialised by one mutex (the reference never calls
+// these concurrently; SURVEY 8b "threading").
 struct Arena {
-    std::mutex mu;
-    int device = -1;
     char *base = nullptr;
     size_t cap = 0, used = 0;
     cudaStream_t stream = nullptr;
 
     cudaError_t reset(size_t need)
     {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        if (dev != device) {  // device switched: drop the old arena lazily
-            base = nullptr, cap = 0, stream = nullptr, device = dev;
-        }
+        cudaError_t e;
         if (!stream && (e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess)
             return e;
         if (need > cap) {
@@ -61,7 +55,25 @@ struct Arena {
         return reinterpret_cast<double *>(p);
     }
 };
-Arena g_arena;
+constexpr int MAX_DEVICES = 64;
+std::mutex g_mu;
+Arena g_arenas[MAX_DEVICES];
+
+// the arena of the CURRENT device (nullptr + error text when the device cannot be determined)
+Arena *current_arena()
+{
+    int dev = 0;
+    const cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        mt::cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+        return nullptr;
+    }
+    if (dev < 0 || dev >= MAX_DEVICES) {
+        mt::set_error("device index %d out of range", dev);
+        return nullptr;
+    }
+    return &g_arenas[dev];
+}
 
 inline size_t pad(size_t n_doubles) { return (n_doubles * sizeof(double) + 255) & ~size_t(255); }
 
@@ -81,27 +93,40 @@ void fail(const char *name, double *out, size_t n_out)
         }                                                                    \
     } while (0)
 
+// One input of a call: a dense host array of n doubles, or (rows > 0) a 2-D window of a larger host array --
+// `rows` rows of `n` contiguous doubles each, `pitch` doubles apart -- that lands densely on the device.
 struct In {
     const double *host;
     size_t n;
+    size_t rows = 0, pitch = 0;
+    size_t total() const { return rows ? rows * n : n; }
 };
 
 // Generic driver: upload `nin` arrays, run `launch(dev_in[], dev_out, stream)`, download.
 template <class Launch>
 void run(const char *name, const In *ins, int nin, double *out_h, size_t n_out, Launch launch)
 {
-    std::lock_guard<std::mutex> lock(g_arena.mu);
+    std::lock_guard<std::mutex> lock(g_mu);
+    Arena *arena = current_arena();
+    if (!arena) {
+        fail(name, out_h, n_out);
+        return;
+    }
     size_t need = pad(n_out);
-    for (int i = 0; i < nin; ++i) need += pad(ins[i].n);
-    L_CUDA(g_arena.reset(need));
-    cudaStream_t s = g_arena.stream;
+    for (int i = 0; i < nin; ++i) need += pad(ins[i].total());
+    L_CUDA(arena->reset(need));
+    cudaStream_t s = arena->stream;
     const double *dev_in[8];
     for (int i = 0; i < nin; ++i) {
-        double *d = g_arena.take(ins[i].n);
-        L_CUDA(cudaMemcpyAsync(d, ins[i].host, ins[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
+        double *d = arena->take(ins[i].total());
+        if (ins[i].rows)
+            L_CUDA(cudaMemcpy2DAsync(d, ins[i].n * sizeof(double), ins[i].host, ins[i].pitch * sizeof(double),
+                                     ins[i].n * sizeof(double), ins[i].rows, cudaMemcpyHostToDevice, s));
+        else
+            L_CUDA(cudaMemcpyAsync(d, ins[i].host, ins[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
         dev_in[i] = d;
     }
-    double *dev_out = g_arena.take(n_out);
+    double *dev_out = arena->take(n_out);
     if (launch(dev_in, dev_out, (mt_stream_t)s) != MT_OK) {
         cudaStreamSynchronize(s);
         fail(name, out_h, n_out);
@@ -111,6 +136,37 @@ void run(const char *name, const In *ins, int nin, double *out_h, size_t n_out, 
     L_CUDA(cudaStreamSynchronize(s));
 }
 
+// Bounding box [x0, x1) x [y0, y1) of the source columns the bilinear stencils of all targets touch
+// (fastcompute.f90:80-93: x0 = int(x/dx), x1 <= x0 + 1).  The 2-D routines then upload ONLY that window of
+// the source (cart -> cyl of a 1000 x 1000 WRF field touches 9 % of it: 43 MB instead of 480 MB of pageable
+// host memory per call).  `whole` when the window would not pay, or when a target lies outside the array (the
+// kernel clamps such indices into the FULL array, which must then be resident).
+struct Box {
+    int x0, x1, y0, y1;
+    bool whole;
+};
+Box target_box(const double *x, const double *y, int n, double dx, double dy, int lenx, int leny)
+{
+    Box b{0, lenx, 0, leny, true};
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    int valid = 0;
+    for (int i = 0; i < n; ++i) {
+        const double xi = x[i], yi = y[i];
+        if (!(xi == xi) || !(yi == yi) || xi == MT_SENTINEL || yi == MT_SENTINEL) continue;   // NaN / sentinel targets
+        const double tx = xi / dx, ty = yi / dy;
+        xmin = tx < xmin ? tx : xmin, xmax = tx > xmax ? tx : xmax;
+        ymin = ty < ymin ? ty : ymin, ymax = ty > ymax ? ty : ymax;
+        ++valid;
+    }
+    if (!valid || xmin < 0 || ymin < 0 || xmax > lenx - 1 || ymax > leny - 1) return b;
+    b.x0 = (int)xmin, b.y0 = (int)ymin;
+    b.x1 = (int)xmax + 2 < lenx ? (int)xmax + 2 : lenx;
+    b.y1 = (int)ymax + 2 < leny ? (int)ymax + 2 : leny;
+    b.whole = (double)(b.x1 - b.x0) * (b.y1 - b.y0) > 0.6 * (double)lenx * leny;
+    if (b.whole) b = Box{0, lenx, 0, leny, true};
+    return b;
+}
+
 }  // namespace
 
 extern "C" {
@@ -118,13 +174,7 @@ extern "C" {
 void interp2D_fast(int lenx, int leny, double dx, double dy, int N, const double *xNewLoc,
                    const double *yNewLoc, const double *xyData, double *RThetaData)
 {
-    if (N <= 0) return;
-    In ins[3] = {{xyData, (size_t)lenx * leny}, {xNewLoc, (size_t)N}, {yNewLoc, (size_t)N}};
-    run("interp2D_fast", ins, 3, RThetaData, (size_t)N,
-        [&](const double **d, double *o, mt_stream_t s) {
-            // xyData(leny,lenx): y contiguous
-            return mt_interp2d_layers(d[0], 1, leny, lenx, 0, 1, leny, dx, dy, d[1], d[2], N, o, 0, 1, s);
-        });
+    interp2D_fast_layers(lenx, leny, 1, dx, dy, N, xNewLoc, yNewLoc, xyData, RThetaData);
 }
 
 void interp2D_fast_layers(int lenx, int leny, int layers, double dx, double dy, int N,
@@ -132,13 +182,22 @@ void interp2D_fast_layers(int lenx, int leny, int layers, double dx, double dy, 
                           double *RThetaData)
 {
     if (N <= 0 || layers <= 0) return;
-    In ins[3] = {{xyData, (size_t)layers * lenx * leny}, {xNewLoc, (size_t)N}, {yNewLoc, (size_t)N}};
-    run("interp2D_fast_layers", ins, 3, RThetaData, (size_t)layers * N,
-        [&](const double **d, double *o, mt_stream_t s) {
-            // xyData(layers,leny,lenx) / RThetaData(layers,N): layer index contiguous
-            return mt_interp2d_layers(d[0], layers, leny, lenx, 1, layers, (int64_t)layers * leny, dx,
-                                      dy, d[1], d[2], N, o, 1, layers, s);
-        });
+    // xyData(layers,leny,lenx) / RThetaData(layers,N): layer index contiguous, x slowest.  Only the window of
+    // the source under the targets travels: rows = x, each row the y-range of that x, `layers` per column.
+    const Box b = target_box(xNewLoc, yNewLoc, N, dx, dy, lenx, leny);
+    const int64_t by = b.y1 - b.y0, bx = b.x1 - b.x0;
+    In src{xyData + ((int64_t)b.y0 + (int64_t)leny * b.x0) * layers, (size_t)(by * layers), (size_t)bx,
+           (size_t)leny * layers};
+    if (b.whole) src = In{xyData, (size_t)layers * lenx * leny};
+    In ins[3] = {src, {xNewLoc, (size_t)N}, {yNewLoc, (size_t)N}};
+    const char *name = layers == 1 ? "interp2D_fast" : "interp2D_fast_layers";
+    run(name, ins, 3, RThetaData, (size_t)layers * N, [&](const double **d, double *o, mt_stream_t s) {
+        // the window is addressed with FULL-array indices: element (l, y, x) of the dense window sits at
+        // l + layers*((y - y0) + by*(x - x0)), i.e. at the virtual base  d[0] - layers*(y0 + by*x0)
+        const double *base = d[0] - (int64_t)layers * ((int64_t)b.y0 + by * b.x0);
+        return mt_interp2d_layers(base, layers, leny, lenx, 1, layers, (int64_t)layers * by, dx, dy, d[1], d[2], N,
+                                  o, 1, layers, s);
+    });
 }
 
 void interp3D_fast(int lenx, int leny, int lenz, double dx, double dy, double dz, int N,

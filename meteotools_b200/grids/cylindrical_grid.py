@@ -673,6 +673,34 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         self.wspd_max_RMW = self.sym_wind_speed[np.arange(self.Nz), max_wind_r_idx]
         self.vt_max_RMW = self.sym_vt[np.arange(self.Nz), max_wind_r_idx]
 
+    def find_rmw_and_speed10(self):  # :317-331, as written there
+        if not self._has('sym_vt10'):
+            if not self._has('vt10'):
+                self.calc_vr_vt10()
+            self.calc_axisymmetric_asymmetric('vt10')
+        if not self._has('sym_wind_speed10'):
+            if not self._has('wind_speed10'):
+                self.calc_wind_speed10()
+            self.calc_axisymmetric_asymmetric('wind_speed10')
+        # sym_wind_speed10 is 1-D (Nr,): the reference's axis=1 raises numpy's AxisError here too
+        max_wind_r_idx = np.nanargmax(self.sym_wind_speed10, axis=1)
+        self.RMW10 = self.r[max_wind_r_idx]
+        self.wspd_max_RMW10 = self.sym_wind_speed10[max_wind_r_idx]
+        self.vt_max_RMW10 = self.sym_vt[max_wind_r_idx]       # (sic) sym_vt, not sym_vt10
+
+    def rotate_to_shear_direction(self, varname, direction, unit='rad'):  # :237-262
+        """``shear_relative_<var>``: the variable rolled along theta by int(direction / dtheta) points
+        (3-D (z, theta, r): axis 1; 2-D (theta, r) and 1-D (theta): axis 0)."""
+        if unit == 'deg':
+            direction = np.deg2rad(direction)
+        rotate_idx = int(direction / self.dtheta)
+        print(rotate_idx)
+        var = np.asarray(getattr(self, varname))
+        if var.ndim == 3:
+            setattr(self, f'shear_relative_{varname}', np.roll(var, rotate_idx, axis=1))
+        elif var.ndim in (1, 2):
+            setattr(self, f'shear_relative_{varname}', np.roll(var, rotate_idx, axis=0))
+
     # ------------------------------------------------------------ range averages (8f-1)
     def _wsum3(self, varname, axis, w, mode, denom):
         """mt_axis_wsum over one logical axis (0: z, 1: theta, 2: r) of a 3-D field in the grid's

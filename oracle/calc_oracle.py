@@ -240,12 +240,17 @@ def cyl_d_set(f, grid):
     ``f``; ``grid`` = dict(r, theta, dr, dtheta, dz).  Returns a dict of outputs."""
     r, th = grid["r"], grid["theta"].reshape(1, -1, 1)
     dr, dth, dz = grid["dr"], grid["dtheta"], grid["dz"]
-    u, v, w, p, T, fc = f["u"], f["v"], f["w"], f["p"], f["T"], f["f"]
+    w, p, T, fc = f["w"], f["p"], f["T"], f["f"]
+    u, v = f.get("u"), f.get("v")
     o = {}
-    o["vr"] = v * np.sin(th) + u * np.cos(th)                      # :266-268
-    o["vt"] = v * np.cos(th) - u * np.sin(th)
+    if "vr" in f and "vt" in f:      # every method uses self.vr / self.vt as they are once they exist (:290-508)
+        o["vr"], o["vt"] = f["vr"], f["vt"]
+    else:
+        o["vr"] = v * np.sin(th) + u * np.cos(th)                  # :266-268
+        o["vt"] = v * np.cos(th) - u * np.sin(th)
     vr, vt = o["vr"], o["vt"]
-    o["wind_speed"] = (u ** 2 + v ** 2) ** 0.5                     # :356
+    if u is not None and v is not None:
+        o["wind_speed"] = (u ** 2 + v ** 2) ** 0.5                 # :356
     o["Tv"] = Tv_from_qv(T, f["qv"])                               # calc_rho -> calc_Tv
     o["rho"] = rho(p, o["Tv"])
     o["coriolis_force"] = fc * vt                                  # :341-347

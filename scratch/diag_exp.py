@@ -13,6 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from meteotools_b200 import _device as D, _lib  # noqa: E402
 
+if os.environ.get('MT_LIB'):
+    _lib.LIB_PATH = os.environ['MT_LIB']   # A/B builds (scratch/build_variant.sh)
 lib = _lib.load()
 PEAK = 6536.0
 

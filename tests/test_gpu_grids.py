@@ -605,3 +605,115 @@ def test_interplevel_level_major_modes(nz, ny, nx, nlev, dt_):
     plev = np.linspace(99000.0, 12000.0, nlev)
     assert_same(np.asarray(interplevel(fld, p3d, plev)), oracle.interplevel(fld, p3d, plev),
                 f"interplevel p {(nz, ny, nx, nlev)}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The reference's methods use self.vr / self.vt AS THEY ARE once they exist (cylindrical_grid.py:290-508): a
+# grid that holds only vr, vt (user-assigned, storm-relative ...) needs no u, v; a modified vt must be honoured.
+def _vrvt_case(seed=5, nz=8, nt=12, nr=10):
+    rng = np.random.default_rng(seed)
+    st = dict(Nr=nr, Ntheta=nt, Nz=nz, dr=1000, dtheta=2 * np.pi / nt, dz=250, z_start=100, r_start=0,
+              theta_start=0, vertical_coord_type="z", dt=300)
+    shp = (nz, nt, nr)
+    zz = (np.arange(nz) * 250.0 + 100.0).reshape(-1, 1, 1)
+    f = {k: 10 * rng.standard_normal(shp) for k in ("vr", "vt", "w")}
+    f["p"] = 1e5 * np.exp(-zz / 8000.0) + rng.standard_normal(shp)
+    f["T"] = 300 - 6.5e-3 * zz + rng.standard_normal(shp)
+    f["qv"] = 1e-3 + 1e-3 * np.abs(rng.standard_normal(shp))
+    f["qc"] = 1e-4 * np.abs(rng.standard_normal(shp))
+    f["qr"] = 1e-4 * np.abs(rng.standard_normal(shp))
+    return st, f
+
+
+VRVT_METHODS = ("calc_aam", "calc_agradient_force", "calc_kinetic_energy", "calc_vorticity_3D",
+                "calc_abs_vorticity_3D", "calc_divergence_hori", "calc_divergence",
+                "calc_density_potential_temperature", "calc_PV", "calc_deformation", "calc_filamentation")
+VRVT_EXACT = ["coriolis_force", "centrifugal_force", "radial_PG_force", "agradient_force", "kinetic_energy",
+              "zeta_r", "zeta_t", "zeta_z", "abs_zeta_z", "div_hori", "div", "shear_deform", "stretch_deform",
+              "strain_region"]
+
+
+@pytest.mark.parametrize("f_kind", ["field", "scalar"])
+def test_cyl_methods_use_the_grids_vr_vt_without_u_v(f_kind):
+    from meteotools_b200.grids import cylindrical_grid
+    st, f = _vrvt_case()
+    cyl = cylindrical_grid(dict(st))
+    for k, v in f.items():
+        setattr(cyl, k, v.copy())
+    if f_kind == "scalar":      # a scalar Coriolis parameter broadcasts, as in the reference's self.f*self.vt
+        cyl.f = 5e-5
+        fc = 5e-5
+    else:
+        fc = 5e-5 + 1e-7 * np.arange(st["Ntheta"] * st["Nr"], dtype=np.float64).reshape(st["Ntheta"], st["Nr"])
+        cyl.f = fc
+    for m in VRVT_METHODS:
+        getattr(cyl, m)()
+    assert not cyl._has("u") and not cyl._has("v")
+    with np.errstate(all="ignore"):
+        ref = co.cyl_d_set(dict(f, f=fc), dict(r=cyl.r, theta=cyl.theta, dr=cyl.dr, dtheta=cyl.dtheta, dz=cyl.dz))
+    for k in VRVT_EXACT:
+        assert_same(getattr(cyl, k), ref[k], f"{k} from the grid's vr / vt ({f_kind} f)")
+    r = cyl.r.reshape(1, 1, -1)
+    assert_same(cyl.aam, f["vt"] * r + 0.5 * fc * r ** 2, "aam")
+    assert_same(cyl.vt, f["vt"], "vt untouched")
+    assert_close(cyl.PV, ref["PV"], 1e-10, "PV", nonfinite="class", floor=1e-3)
+    with pytest.raises(AttributeError):
+        cyl.calc_wind_speed()       # needs u, v (cylindrical_grid.py:354-358)
+
+
+def test_cyl_modified_vt_is_honoured():
+    """u, v present AND a user-modified vt: the reference differentiates self.vt, not a recomputed one."""
+    from meteotools_b200.grids import cylindrical_grid
+    st, f = _vrvt_case(seed=6)
+    rng = np.random.default_rng(7)
+    cyl = cylindrical_grid(dict(st))
+    u, v = 10 * rng.standard_normal(f["w"].shape), 10 * rng.standard_normal(f["w"].shape)
+    cyl.u, cyl.v, cyl.w, cyl.f = u, v, f["w"].copy(), 5e-5
+    cyl.calc_vr_vt()
+    vt_rel = np.array(cyl.vt) - 5.0          # storm-relative tangential wind
+    cyl.vt = vt_rel
+    cyl.calc_vorticity_3D()
+    cyl.calc_aam()
+    th = cyl.theta.reshape(1, -1, 1)
+    vr = v * np.sin(th) + u * np.cos(th)
+    with np.errstate(all="ignore"):
+        zeta_r = co.FD2(f["w"], cyl.dtheta, 1) / cyl.r - co.FD2(vt_rel, cyl.dz, 0)
+        zeta_z = co.FD2(vt_rel * cyl.r, cyl.dr, 2) / cyl.r - co.FD2(vr, cyl.dtheta, 1) / cyl.r
+    assert_same(cyl.zeta_r, zeta_r, "zeta_r from the modified vt")
+    assert_same(cyl.zeta_z, zeta_z, "zeta_z from the modified vt")
+    assert_same(cyl.vt, vt_rel, "vt untouched by calc_aam")
+    r = cyl.r.reshape(1, 1, -1)
+    assert_same(cyl.aam, vt_rel * r + 0.5 * 5e-5 * r ** 2, "aam")
+
+
+def test_cyl_stale_plan_is_dropped_when_targets_are_assigned():
+    """cyl.xTR / yTR may be assigned directly (the reference permits it): the cached stencil plan follows."""
+    from meteotools_b200.grids import cylindrical_grid
+    rng = np.random.default_rng(3)
+    st = dict(Nr=12, Ntheta=16, Nz=6, dr=2000, dtheta=2 * np.pi / 16, dz=500, z_start=100, r_start=0,
+              theta_start=0, vertical_coord_type="z", dt=300)
+    nz, ny, nx, dx = 8, 40, 40, 2000.0
+    z3d = np.broadcast_to((np.arange(nz) * 600.0).reshape(-1, 1, 1), (nz, ny, nx)).copy()
+    fld = rng.standard_normal((nz, ny, nx))
+    cyl = cylindrical_grid(dict(st))
+    cyl.set_horizontal_location(39000.0, 39000.0)
+    cyl.set_data.__wrapped__(cyl, dx, dx, z3d, u=fld)
+    x2, y2 = np.array(cyl.xTR) + 3000.0, np.array(cyl.yTR) - 1000.0
+    cyl.xTR, cyl.yTR = x2, y2                # direct assignment
+    cyl.set_data.__wrapped__(cyl, dx, dx, z3d, u=fld)
+    lev = oracle.interplevel(fld, z3d, cyl.z)
+    assert_same(cyl.u, oracle.interp2D_fast_layers(dx, dx, x2, y2, lev), "u after re-targeting")
+
+
+def test_cyl_rotate_and_rmw10_follow_the_reference():
+    from meteotools_b200.grids import cylindrical_grid
+    st, f = _vrvt_case(seed=8)
+    cyl = cylindrical_grid(dict(st))
+    cyl.vt = f["vt"].copy()
+    cyl.rotate_to_shear_direction("vt", 95.0, unit="deg")
+    idx = int(np.deg2rad(95.0) / cyl.dtheta)
+    assert_same(cyl.shear_relative_vt, np.roll(f["vt"], idx, axis=1), "shear_relative_vt")
+    cyl.u10 = f["vt"][0].copy()
+    cyl.v10 = f["vr"][0].copy()
+    with pytest.raises(np.exceptions.AxisError):     # the reference's nanargmax(axis=1) on a 1-D array
+        cyl.find_rmw_and_speed10()
