@@ -190,8 +190,9 @@ int mt_setdata(const void *const *fields, int nvar, const void *vert, int dtype,
  * (nitems x 4 int32: tile_x, tile_y in full-source indices, start into `order`, count <= 128);
  * a target belongs to the tile that contains its (x0, y0) corner, tiles are tile_w x tile_h cells
  * (16x4 or 16x2).  `nflagged` = number of NaN / sentinel targets (they only get the fill value).
- * `counter`: one int32 of device scratch (work-item counter).  fields/vert describe the uploaded
- * region exactly as in mt_setdata. */
+ * `counter`: TWO int32 of device scratch, zero before the first launch ([0]: work-item counter, [1]: the
+ * status word of mt_setdata_tma, see there).  fields/vert describe the uploaded region exactly as in
+ * mt_setdata. */
 int mt_setdata_fused(const void *const *fields, int nvar, const void *vert, int dtype, int64_t nz,
                      int64_t ny, int64_t nx, int64_t org_y, int64_t org_x, const double *levels,
                      int64_t nlev, int direction, const int32_t *plan_ix, const double *plan_w,
@@ -208,8 +209,11 @@ int mt_setdata_fused(const void *const *fields, int nvar, const void *vert, int 
  *   - tiles are MT_TMA_TILE_W_F64 x MT_TMA_TILE_H source cells for float64 sources and
  *     MT_TMA_TILE_W_F32 x MT_TMA_TILE_H for float32 sources (the 16-column box covers the tile's
  *     tile_w + 1 columns), and every item's tile_x - org_x must be a multiple of 2 (float64) / 4
- *     (float32) -- a PRECONDITION on `items` that the library cannot check without reading them
- *     back (a violation ends in cudaErrorIllegalInstruction).
+ *     (float32).  The kernel checks every item it draws: one that breaks this rule (the TMA unit would
+ *     raise a sticky cudaErrorIllegalInstruction), or whose start / count do not fit `order` / exceed
+ *     MT_TMA_MAX_TARGETS, is skipped -- its targets are not written -- and recorded in counter[1];
+ *     mt_setdata_tma_status(counter, stream) synchronises, returns MT_EINVAL if anything was recorded
+ *     and clears the record.  Call it once after the first launch with a new `items` array.
  * `direction` must be 0 or 1 (decided by the caller from column (0,0) of the full coordinate
  * array).  mt_setdata_tma_supported() tells whether a shape can take this path (otherwise use
  * mt_setdata: same results, two kernels).
@@ -227,6 +231,7 @@ int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dt
                    const double *plan_w, int64_t n, const int32_t *order, const int32_t *items,
                    int64_t nitems, int64_t nflagged, const int32_t *hgt_idx, double *const *out,
                    int64_t o_n, int flags, int32_t *counter, mt_stream_t stream);
+int mt_setdata_tma_status(int32_t *counter, mt_stream_t stream);
 
 /* mt_upload_box with a padded device row pitch (elements): dev is (nz, y1-y0, dev_row_pitch). */
 int mt_upload_box_pitched(const void *host, int elem_bytes, int64_t nz, int64_t ny, int64_t nx,
@@ -445,6 +450,13 @@ int mt_smooth_pass(const double *v0, const double *cur, double *out, int64_t n0,
 /* ---- staging helpers used by the host-facing wrappers -----------------------------------------
  * out[i] = in[i] as double (f32 -> f64 upcast on the device; exact). */
 int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream);
+/* Map-factor scaling of the ingest (wrfout_grid.correct_map_scale, grids/wrfout_grid.py:48-55:
+ * ua *= MAPFAC_MX, va *= MAPFAC_MY, u10 / v10 likewise): box[k][j][i] *= fac[(org_y + j)*fac_pitch + org_x + i]
+ * IN PLACE on a staged source box (nz, by, row_pitch) whose [0][0] column is column (org_y, org_x) of the full
+ * grid the (., fac_pitch) factor array covers.  NumPy's arithmetic per dtype pair: float32 *= float32 is a
+ * float product, every other pairing the double product cast back to the box's type. */
+int mt_scale_box_2d(void *box, int dtype, int64_t nz, int64_t by, int64_t bx, int64_t row_pitch, const void *fac,
+                    int fac_dtype, int64_t fac_pitch, int64_t org_y, int64_t org_x, mt_stream_t stream);
 /* float64 -> float32, round to nearest (what the reference's netCDF cache stores: 'f4',
  * grids/grid_general.py:119-129): for results that leave the device as float32. */
 int mt_cast_f64_f32(const double *in, float *out, int64_t n, mt_stream_t stream);

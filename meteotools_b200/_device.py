@@ -88,6 +88,23 @@ def cast_f64(x):
     return out
 
 
+def scale_box(box, fac, org_y, org_x, width):
+    """box (nz, by, pitch) *= fac[org_y:org_y+by, org_x:org_x+width] in place (mt_scale_box_2d): the map-factor
+    scaling of wrfout_grid.correct_map_scale on a staged source box, in the box's own dtype."""
+    t = torch()
+    if not is_tensor(fac):   # keep a float32 factor float32: float32 *= float32 is a float product in NumPy
+        fac = np.asarray(fac)
+        fac = np.ascontiguousarray(fac, dtype=fac.dtype if fac.dtype in (np.float32, np.float64) else np.float64)
+        fac = _from_numpy(fac).cuda()
+    else:
+        fac = fac.contiguous() if fac.dtype in (t.float32, t.float64) else fac.to(t.float64).contiguous()
+    nz, by, pitch = (int(v) for v in box.shape)
+    code = lambda x: _lib.MT_F32 if x.dtype == t.float32 else _lib.MT_F64  # noqa: E731
+    _lib.check(_lib.load().mt_scale_box_2d(ptr(box), code(box), nz, by, int(width), pitch, ptr(fac), code(fac),
+                                           int(fac.shape[-1]), int(org_y), int(org_x), stream()), "mt_scale_box_2d")
+    return box
+
+
 def to_host(x):
     """Device tensor -> NumPy array backed by PINNED host memory (torch's caching host allocator
     recycles the blocks, so repeated downloads run at PCIe speed without re-pinning)."""

@@ -130,6 +130,7 @@ _SIGS = {
     "mt_nansum_weighted": (c_int, [c_vp, c_vp, ct.POINTER(mt_grid_t), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mt_smooth_pass": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_vp]),
     "mt_setdata_tma_supported": (c_int, [c_int, c_i64, c_i64, c_i64]),
+    "mt_setdata_tma_status": (c_int, [c_vp, c_vp]),
     "mt_setdata_tma": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
                                c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_int,
                                c_vp, c_vp]),
@@ -153,6 +154,7 @@ _SIGS = {
     "mt_nccl_comm_destroy": (c_int, [c_vp]),
     "mt_halo_exchange": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "mt_azimuthal_mean": (c_int, [c_vp, ct.POINTER(mt_grid_t), c_vp, c_vp, c_vp]),
+    "mt_scale_box_2d": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_i64, c_i64, c_vp]),
     "mt_cast_f32_f64": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mt_cast_f64_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mt_cyl_prelude": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_dbl,

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, int LP, int stages,
               int stage_bytes, int org_x, int org_y, const double *__restrict__ levels, int decreasing,
               const int4 *__restrict__ pix, const double2 *__restrict__ pw,
-              const int32_t *__restrict__ order, const int4 *__restrict__ items, int nitems,
+              const int32_t *__restrict__ order, const int4 *__restrict__ items, int nitems, int n_order,
               int *__restrict__ counter, const int32_t *__restrict__ hgt_idx, int64_t o_n, int off_lev,
               int lev_bytes, int off_meta, int off_misc)
 {
@@ -146,6 +146,21 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                     nid = __shfl_sync(0xffffffffu, nid, 0);
                     if (nid < nitems) nit = items[nid];
                     else nit = make_int4(0, 0, 0, 0);
+                    if (nid < nitems) {
+                        // `items` comes from the caller.  A tile origin that is not 16-byte aligned makes the
+                        // TMA unit raise cudaErrorIllegalInstruction (sticky: the context is lost), a bad
+                        // start / count reads beyond `order`: such an item is made harmless here -- origin
+                        // rounded down, no targets -- and reported through the status word counter[1]
+                        // (mt_setdata_tma_status -> MT_EINVAL).
+                        constexpr int ALIGN = 16 / (int)sizeof(T);
+                        const int rel = nit.x - org_x;
+                        const int mis = ((rel % ALIGN) + ALIGN) % ALIGN;
+                        const bool bad = mis != 0 || nit.w < 0 || nit.w > MAXT || nit.z < 0 || nit.z > n_order - nit.w;
+                        if (bad) {
+                            if (lane == 0) atomicOr(counter + 1, 1);
+                            nit.x -= mis, nit.w = 0, nit.z = 0;
+                        }
+                    }
                     break;
                 case 2:
 #pragma unroll
@@ -639,7 +654,8 @@ int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int 
                                      (int)L.total));                                                               \
         k_setdata_tma<T, INC, RND, PPV, EX><<<grid, NTHREADS, L.total, s>>>(                                           \
             P, nvar, (int)nz, (int)nlev, L.LP, L.stages, L.stage_bytes, (int)org_x, (int)org_y, levels, direction, \
-            pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, counter, hgt_idx, o_n, L.off_lev,  \
+            pix, pw, order, reinterpret_cast<const int4 *>(items), (int)nitems, (int)(n - nflagged), counter,  \
+            hgt_idx, o_n, L.off_lev,                                                                               \
             L.lev_bytes, L.off_meta, L.off_misc);                                                                  \
     } while (0)
 #define ST_DISPATCH2(T, INC, RND)                      \
@@ -683,6 +699,20 @@ int mt_setdata_tma(const void *const *fields, int nvar, const void *vert, int dt
     return setdata_tma_impl(fields, nvar, vert, dtype, nz, ny, nx, row_pitch, org_y, org_x, levels, nlev, direction,
                             plan_ix, plan_w, n, order, items, nitems, nflagged, hgt_idx, out, o_n, flags, counter,
                             stream);
+}
+
+int mt_setdata_tma_status(int32_t *counter, mt_stream_t stream)
+{
+    MT_REQUIRE(counter, "mt_setdata_tma_status: null counter");
+    int32_t st = 0;
+    MT_CUDA(cudaMemcpyAsync(&st, counter + 1, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (st == 0) return MT_OK;
+    MT_CUDA(cudaMemsetAsync(counter + 1, 0, sizeof(st), (cudaStream_t)stream));
+    mt::set_error("mt_setdata_tma: `items` held entries that break the contract (tile_x - org_x not a multiple of "
+                  "16 bytes, count outside 0..%d, or start + count beyond the `order` array); their targets were "
+                  "NOT written", MAXT);
+    return MT_EINVAL;
 }
 
 #ifdef MT_TMA_TIMING

@@ -109,9 +109,52 @@ k_rows_to_levels(RowsToLevels P, int nvar, int64_t n, int nlev, const double *__
         }
     }
 }
+// wrfout_grid.correct_map_scale (grids/wrfout_grid.py:48-55): ua *= MAPFAC_MX ... -- a (z, y, x) field times
+// a (y, x) factor IN PLACE, in NumPy's arithmetic for the two dtypes: float32 *= float32 is a float
+// product, every other pairing is the double product cast back to the field's type.
+template <typename TF, typename TM>
+__global__ void __launch_bounds__(256)
+k_scale_box_2d(TF *__restrict__ box, int64_t nz, int by, int bx, int64_t pitch, const TM *__restrict__ fac,
+               int64_t fac_pitch, int64_t org_y, int64_t org_x)
+{
+    const int64_t total = nz * by * (int64_t)bx;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % bx);
+        const int64_t q = e / bx;
+        const int j = (int)(q % by);
+        const int64_t k = q / by;
+        TF *ptr = box + (k * by + j) * pitch + i;
+        const TM m = __ldg(fac + (org_y + j) * fac_pitch + org_x + i);
+        if (sizeof(TF) == 4 && sizeof(TM) == 4) *ptr = (TF)((float)*ptr * (float)m);
+        else *ptr = (TF)((double)*ptr * (double)m);
+    }
+}
 }  // namespace
 
 extern "C" {
+
+int mt_scale_box_2d(void *box, int dtype, int64_t nz, int64_t by, int64_t bx, int64_t row_pitch, const void *fac,
+                    int fac_dtype, int64_t fac_pitch, int64_t org_y, int64_t org_x, mt_stream_t stream)
+{
+    MT_REQUIRE(box && fac && nz >= 1 && by >= 1 && bx >= 1 && row_pitch >= bx && fac_pitch >= 1 && org_y >= 0 &&
+                   org_x >= 0 && by < 2147483647LL && bx < 2147483647LL,
+               "mt_scale_box_2d: bad arguments");
+    MT_REQUIRE((dtype == MT_F64 || dtype == MT_F32) && (fac_dtype == MT_F64 || fac_dtype == MT_F32),
+               "mt_scale_box_2d: bad dtype");
+    const unsigned grid = mt::grid_for(nz * by * bx, 256, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    mt::ProfScope prof("k_scale_box_2d", stream);
+#define SC_LAUNCH(TF, TM)                                                                                        \
+    k_scale_box_2d<TF, TM><<<grid, 256, 0, s>>>((TF *)box, nz, (int)by, (int)bx, row_pitch, (const TM *)fac, fac_pitch, \
+                                                org_y, org_x)
+    if (dtype == MT_F32 && fac_dtype == MT_F32) SC_LAUNCH(float, float);
+    else if (dtype == MT_F32) SC_LAUNCH(float, double);
+    else if (fac_dtype == MT_F32) SC_LAUNCH(double, float);
+    else SC_LAUNCH(double, double);
+#undef SC_LAUNCH
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+}
 
 int mt_cast_f32_f64(const float *in, double *out, int64_t n, mt_stream_t stream)
 {

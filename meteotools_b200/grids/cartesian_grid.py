@@ -75,8 +75,11 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
     _fused_items_for = cylindrical_grid._fused_items_for
 
     @timer
-    def set_data(self, src_dx, src_dy, src_vertical, vertical_interp_order=1, inclusive=False, **vardict):
-        """Interpolate source fields onto this grid (:76-125); terrain: z <= hgt -> NaN (:127-136)."""
+    def set_data(self, src_dx, src_dy, src_vertical, vertical_interp_order=1, inclusive=False, map_factors=None,
+                 **vardict):
+        """Interpolate source fields onto this grid (:76-125); terrain: z <= hgt -> NaN (:127-136).
+        ``map_factors``: see ``cylindrical_grid.set_data`` (wrfout_grid.correct_map_scale on the device)."""
+        map_factors = dict(map_factors or {})
         if vertical_interp_order not in (1, 2, 3):   # the reference leaves `tmp` undefined (:100-112)
             raise NameError(f"vertical_interp_order must be 1, 2 or 3, got {vertical_interp_order}")
         cur3d = []
@@ -86,11 +89,11 @@ class cartesian_grid(gridsystem, calc_thermaldynamic):
                 self.varlist3D.append(varname)
                 cur3d.append(varname)
             elif len(var.shape) == 2:
-                self._put(varname, self._interp2d_var(src_dx, src_dy, var), ndim=2)
+                self._put(varname, self._interp2d_var(src_dx, src_dy, var, map_factors.get(varname)), ndim=2)
                 self.varlist2D.append(varname)
         if cur3d:
             self._setdata3d(src_dx, src_dy, src_vertical, [vardict[n] for n in cur3d], cur3d, None, inclusive,
-                            spline_order=vertical_interp_order)
+                            spline_order=vertical_interp_order, map_factors=map_factors)
         if 'hgt' in self.varlist2D:
             self.set_terrain()
             self.terrain_mask_vars(skip=self.__dict__.pop('_masked_in_setdata', ()))

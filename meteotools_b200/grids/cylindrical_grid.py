@@ -34,7 +34,7 @@ _HYDRO_SETS = (("qc", "qr", "qi", "qs", "qg", "qh"), ("qc", "qr", "qi", "qs", "q
 class cylindrical_grid(gridsystem, calc_thermaldynamic):
     _layout = _lib.MT_LAYOUT_TRZ
     # the stencil plan / work items follow the targets, the sin / cos / r tables follow the axes
-    _derived_caches = {'xTR': ('_plan', '_fused_items'), 'yTR': ('_plan', '_fused_items'),
+    _derived_caches = {'xTR': ('_plan', '_fused_items', '_items_checked'), 'yTR': ('_plan', '_fused_items', '_items_checked'),
                        'theta': ('_grid_cache',), 'r': ('_grid_cache',)}
 
     def init_grid(self):  # :19-25
@@ -94,11 +94,14 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
     def _targets_dev(self):
         return self.device('xTR'), self.device('yTR')
 
-    def _interp2d_var(self, dx, dy, var):
+    def _interp2d_var(self, dx, dy, var, map_factor=None):
         """2-D variable -> (theta, r) device tensor (interp2D_fast, :104-105)."""
         var = np.asarray(var) if not D.is_tensor(var) else var
         ny, nx = var.shape
         self._target_box(nx, ny, dx, dy)
+        if map_factor is not None:   # u10 *= MAPFAC_MX in the field's own dtype, on a device copy
+            raw = D.torch().from_numpy(np.ascontiguousarray(var)).cuda() if not D.is_tensor(var) else var.clone()
+            var = D.scale_box(raw.reshape(1, ny, nx), map_factor, 0, 0, nx).reshape(ny, nx)
         src = D.to_device(var)
         xd, yd = self._targets_dev()
         out = self._new(2)
@@ -108,11 +111,17 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         return out
 
     @timer
-    def set_data(self, wrf_dx, wrf_dy, wrf_vertical, ver_interp_order=1, inclusive=False, **vardict):
+    def set_data(self, wrf_dx, wrf_dy, wrf_vertical, ver_interp_order=1, inclusive=False, map_factors=None,
+                 **vardict):
         """Interpolate source fields (z, y, x) / (y, x) onto this grid (:95-137).
 
         ``inclusive``: bracket test of the vertical interpolation, see include/meteotools_b200.h
-        (MT_IL_INCLUSIVE); default = the strict test of wrf-python's DINTERP3DZ."""
+        (MT_IL_INCLUSIVE); default = the strict test of wrf-python's DINTERP3DZ.
+        ``map_factors``: dict name -> (ny, nx) factor, e.g. ``dict(u=MAPFAC_MX, v=MAPFAC_MY, u10=MAPFAC_MX,
+        v10=MAPFAC_MY)``: the source field is multiplied by it on the device while it is staged --
+        ``wrfout_grid.correct_map_scale`` (grids/wrfout_grid.py:48-55) without a pass over the host arrays,
+        in NumPy's arithmetic for the two dtypes."""
+        map_factors = dict(map_factors or {})
         if ver_interp_order not in (1, 2):   # the reference leaves `tmp` undefined -> NameError (:110-127)
             raise NameError(f"ver_interp_order must be 1 (linear) or 2 (quadratic spline), got {ver_interp_order}")
         self.varlist3D, self.varlist2D = [], []
@@ -120,7 +129,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             if len(var.shape) == 3:
                 self.varlist3D.append(varname)
             elif len(var.shape) == 2:
-                self._put(varname, self._interp2d_var(wrf_dx, wrf_dy, var), ndim=2)
+                self._put(varname, self._interp2d_var(wrf_dx, wrf_dy, var, map_factors.get(varname)), ndim=2)
                 self.varlist2D.append(varname)
         hgt_idx = None
         if 'hgt' in self.varlist2D:
@@ -128,9 +137,10 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             hgt_idx = self._hgt_idx_dev
         if self.varlist3D:
             self._setdata3d(wrf_dx, wrf_dy, wrf_vertical, [vardict[n] for n in self.varlist3D],
-                            self.varlist3D, hgt_idx, inclusive, spline_order=ver_interp_order)
+                            self.varlist3D, hgt_idx, inclusive, spline_order=ver_interp_order,
+                            map_factors=map_factors)
 
-    def _setdata3d(self, dx, dy, vert, sources, names, hgt_idx, inclusive, spline_order=1):
+    def _setdata3d(self, dx, dy, vert, sources, names, hgt_idx, inclusive, spline_order=1, map_factors=None):
         """3-D variables: one ``mt_setdata`` per batch of <= 16 variables.  Host arrays are
         uploaded box-only with one strided DMA each (``mt_upload_box``); CUDA tensors are used in
         place (full array, no copy).  ``spline_order`` 2 / 3: the vertical stage is the per-column
@@ -163,19 +173,23 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         else:        # region = the box, rows padded to D.box_pitch (never read)
             sny, snx, oy, ox = y1 - y0, D.box_pitch(x1 - x0), y0, x0
 
-        def stage(a, want32):
+        def stage(a, want32, fac=None):
+            """Source -> device array the kernels read; `fac`: (ny, nx) map factor applied to the raw
+            staged data in ITS dtype, before any widening (wrfout_grid.correct_map_scale)."""
             if on_dev and in_place:
-                a = a.contiguous()
-                return a if (is_f32(a) and want32) else D.cast_f64(a)
-            if on_dev:
-                b = D.upload_box(a, y0, y1, x0, x1)
-                return b if (is_f32(a) and want32) else D.cast_f64(b)
-            a = np.asarray(a)
-            if a.dtype == np.float32 and not want32:
-                return D.cast_f64(D.upload_box(a, y0, y1, x0, x1))
-            if a.dtype not in (np.float32, np.float64):
-                a = a.astype(np.float64)
-            return D.upload_box(a, y0, y1, x0, x1)
+                raw, org, width = a.contiguous(), (0, 0), nx
+                if fac is not None:
+                    raw = raw.clone()          # never modify the caller's array
+            elif on_dev:
+                raw, org, width = D.upload_box(a, y0, y1, x0, x1), (y0, x0), x1 - x0
+            else:
+                a = np.asarray(a)
+                if a.dtype not in (np.float32, np.float64):
+                    a = a.astype(np.float64)
+                raw, org, width = D.upload_box(a, y0, y1, x0, x1), (y0, x0), x1 - x0
+            if fac is not None:
+                D.scale_box(raw, fac, org[0], org[1], width)
+            return raw if (raw.dtype == t.float32 and want32) else D.cast_f64(raw)
         vert_cache = {}
         # float32 sources: wrf-python returns float32 (result rounded), reproduced by ROUND_F32;
         # they are uploaded as float32 (half the PCIe bytes) when the coordinate is float32 too.
@@ -193,7 +207,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                 flags = _lib.MT_IL_SPLINE2 if spline_order == 2 else _lib.MT_IL_SPLINE3
             for b0 in range(0, len(group), _lib.MT_MAX_VARS):
                 batch = group[b0:b0 + _lib.MT_MAX_VARS]
-                srcs = [stage(s, use32) for _, s in batch]
+                srcs = [stage(s, use32, (map_factors or {}).get(nm)) for nm, s in batch]
                 outs = [self._new() for _ in batch]
                 mode = os.environ.get("MT_SETDATA", "tma")   # tma (default) | split | fused
                 fits = nz <= 254 and spline_order == 1
@@ -212,6 +226,10 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
                                                   D.ptr(items_t), nitems, nflag, D.ptr(hgt_idx),
                                                   D.ptr_array(rows), self.Nz, flags, D.ptr(counter),
                                                   D.stream()), 'mt_setdata_tma')
+                    checked = self.__dict__.setdefault('_items_checked', set())
+                    if counter.data_ptr() not in checked:   # once per work-item list: the kernel's verdict on it
+                        _lib.check(lib.mt_setdata_tma_status(D.ptr(counter), D.stream()), 'mt_setdata_tma_status')
+                        checked.add(counter.data_ptr())
                     if not trz and self.Nz <= 96:
                         # (z, y, x) grid: one batched transpose for the whole batch, the Cartesian
                         # terrain mask applied on the way when the grid has a terrain height
@@ -271,6 +289,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
             plan = (ix, w, key)
             self.__dict__['_plan'] = plan
             self.__dict__.pop('_fused_items', None)
+            self.__dict__.pop('_items_checked', None)
         return plan
 
     def _fused_items_for(self, plan, tile_w=16, tile_h=4, max_targets=128, spatial=False, align=1, org_x=0):
@@ -346,7 +365,7 @@ class cylindrical_grid(gridsystem, calc_thermaldynamic):
         t = D.torch()
         res = (t.from_numpy(order).cuda(), t.from_numpy(np.ascontiguousarray(items)).cuda() if len(items) else
                t.zeros((1, 4), dtype=t.int32, device='cuda'), int(len(items)), nflagged,
-               t.zeros((1,), dtype=t.int32, device='cuda'))
+               t.zeros((2,), dtype=t.int32, device='cuda'))   # [work-item counter, status word]
         cache[key_] = res
         return res
 

@@ -111,7 +111,8 @@ class CylStepPipeline:
             self.f_order, self.f_items, self.f_nitems, self.f_nflag, _ = \
                 g._fused_items_for(self.plan, 16, self.tile_h)
         # the work-item counter is per pipeline: pipelines of one grid may run on different streams
-        self.f_counter = t.zeros((1,), dtype=t.int32, device="cuda")
+        self.f_counter = t.zeros((2,), dtype=t.int32, device="cuda")   # [work-item counter, status word]
+        self._items_checked = False
         # the 2-D part of the step (bilinear of the 2-D fields, terrain index + fix-up) is one launch
         self.f_ticket = t.zeros((1,), dtype=t.int32, device="cuda")
         self._keys2d = list(self.out2d)
@@ -201,6 +202,9 @@ class CylStepPipeline:
                                           D.ptr(self.f_items), self.f_nitems, self.f_nflag,
                                           D.ptr(self.hgt_idx), self._out_ptrs, g.Nz, self.flags,
                                           D.ptr(self.f_counter), s), "mt_setdata_tma")
+            if not self._items_checked:   # once per plan: the kernel's verdict on the work items it was given
+                _lib.check(lib.mt_setdata_tma_status(D.ptr(self.f_counter), s), "mt_setdata_tma_status")
+                self._items_checked = True
         elif self.mode == "fused":
             _lib.check(lib.mt_setdata_fused(self._src_ptrs, len(self.names3d), D.ptr(self._vert), self.mt_dtype,
                                             self.nz, sny, snx, oy, ox, D.ptr(self.levels), g.Nz, self.direction,

@@ -87,3 +87,55 @@ def assert_close(a, b, rtol=1e-10, what="", nonfinite="exact", floor=1e-6):
     if not (err <= tol).all():
         i = np.argmax(err / tol)
         raise AssertionError(f"{what}: max err/tol = {(err / tol)[i]:.3g} (a={a[fin][i]!r}, b={b[fin][i]!r})")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Parity report: what the tolerance classes above actually measured, per output field, at
+# the full sizes -- WITHOUT the floor.  The full-size GPU tests call parity_record(); at the end of the session
+# the records are written to gpurun_out/parity_r02.json (copied to profiles/ after a gpurun call).
+_PARITY = {}
+
+
+def parity_record(case, name, a, b, floor=1e-6):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype == bool or b.dtype == bool:
+        _PARITY.setdefault(case, {})[name] = dict(points=int(a.size), bit_mismatches=int(np.count_nonzero(a != b)))
+        return
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    fin = np.isfinite(b) & np.isfinite(a)
+    rec = dict(points=int(a.size), bit_mismatches=int(np.count_nonzero(~same)),
+               nan_masks_equal=bool(np.array_equal(np.isnan(a), np.isnan(b))),
+               inf_masks_and_signs_equal=bool(np.array_equal(np.isinf(a), np.isinf(b)) and
+                                              np.array_equal(a[np.isinf(b) & np.isinf(a)], b[np.isinf(b) & np.isinf(a)])),
+               finite_masks_equal=bool(np.array_equal(np.isfinite(a), np.isfinite(b))),
+               nan_points=int(np.isnan(b).sum()), inf_points=int(np.isinf(b).sum()))
+    if fin.any():
+        bb, err = np.abs(b[fin]), np.abs(a[fin] - b[fin])
+        nz = bb > 0
+        scale = floor * bb.max()
+        rel = np.zeros_like(err)
+        rel[nz] = err[nz] / bb[nz]
+        above = bb >= scale
+        rec.update(max_abs_err=float(err.max()), max_abs_value=float(bb.max()),
+                   max_rel_err_no_floor=float(rel.max()) if nz.any() else 0.0,
+                   max_rel_err_above_floor=float(rel[above].max()) if above.any() else 0.0,
+                   floor=floor, points_below_floor=int(np.count_nonzero(~above)),
+                   max_abs_err_below_floor_over_scale=float((err[~above] / scale).max()) if (~above).any() else 0.0,
+                   points_rel_err_gt_1e10=int(np.count_nonzero(rel > 1e-10)))
+    _PARITY.setdefault(case, {})[name] = rec
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY:
+        return
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_r02.json"), "w") as fh:
+            json.dump(dict(note="max_rel_err_no_floor: max |gpu - oracle| / |oracle| over finite non-zero oracle values, "
+                                "NO floor; bit_mismatches counts points that are not bit-identical (NaN == NaN)",
+                           cases=_PARITY), fh, indent=1)
+    except OSError:
+        pass

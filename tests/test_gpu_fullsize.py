@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import assert_close, assert_same
+from conftest import assert_close, assert_same, parity_record
 from oracle import calc_oracle as co
 
 pytestmark = pytest.mark.gpu
@@ -53,6 +53,9 @@ def test_S3_cyl_d_full_size():
     cyl.calc_diagnostics()
     with np.errstate(all="ignore"):
         ref = co.cyl_d_set(f, dict(r=cyl.r, theta=cyl.theta, dr=cyl.dr, dtheta=cyl.dtheta, dz=cyl.dz))
+    for k in EXACT + ["Th_rho", "filamentation_time"]:
+        parity_record("S3 cyl_d (60,360,300) vs numpy oracle", k, getattr(cyl, k), ref[k])
+    parity_record("S3 cyl_d (60,360,300) vs numpy oracle", "PV", cyl.PV, ref["PV"], floor=1e-3)
     for k in EXACT:
         assert_same(getattr(cyl, k), ref[k], f"S3 {k}")
     assert_close(cyl.Th_rho, ref["Th_rho"], 1e-10, "S3 Th_rho")
@@ -63,6 +66,8 @@ def test_S3_cyl_d_full_size():
     with np.errstate(all="ignore"):
         ref2 = co.cyl_d_set(dict(f, Th=np.asarray(cyl.Th)), dict(r=cyl.r, theta=cyl.theta, dr=cyl.dr,
                                                                dtheta=cyl.dtheta, dz=cyl.dz))
+    for k in ("Th_rho", "PV"):
+        parity_record("S3 cyl_d, oracle fed with the GPU's own Th (isolates pow's ulps)", k, getattr(cyl, k), ref2[k])
     assert_same(cyl.Th_rho, ref2["Th_rho"], "S3 Th_rho from the GPU's Th")
     assert_same(cyl.PV, ref2["PV"], "S3 PV from the GPU's Th")
 
@@ -76,6 +81,8 @@ def test_S4_cyl_td_one_step_full_size():
     cyl.calc_all_thermaldynamic()
     ref = co.cyl_td_set(f["T"], f["p"], f["qv"], f["qc"], f["qr"])
     assert int(cyl._tc_scratch[15].item()) == ref["_Tc_iters"]
+    for k in ("vapor", "Tv", "rho", "Th", "vapor_s", "qvs", "RH", "Td", "Th_es", "Th_v", "Tc", "Th_e", "moist_dTdz"):
+        parity_record("S4 cyl_td, one step (60,360,300) vs numpy oracle", k, getattr(cyl, k), ref[k])
     for k in ("vapor", "Tv", "rho"):
         assert_same(getattr(cyl, k), ref[k], f"S4 {k}")
     for k in ("Th", "vapor_s", "qvs", "RH", "Td", "Th_es", "Th_v", "Tc", "Th_e", "moist_dTdz"):
@@ -99,6 +106,7 @@ def test_S2_set_data_full_size():
     for k in names:
         lev = oracle.interplevel(step["vars3d"][k], step["z3d"], cyl.z)
         ref = co.cyl_terrain_mask(oracle.interp2D_fast_layers(bench.DX, bench.DX, cyl.xTR, cyl.yTR, lev), idx)
+        parity_record("S2 set_data 1000x1000x60 -> (60,360,300) vs CPU pipeline", k, getattr(cyl, k), ref)
         assert_same(getattr(cyl, k), ref, f"S2 {k}")
         assert 0.005 < np.isnan(ref).mean() < 0.2
 
@@ -155,6 +163,11 @@ def test_S5_car_d_properties_and_slab():
     sub["f"] = f2d[699:765].cpu().numpy()
     with np.errstate(all="ignore"):
         ref = co.car_d_set(sub, dict(dx=dx, dy=dy, dz=dz))
+    for k in ("zeta_r", "zeta_t", "zeta_z", "div", "shear_deform", "wind_speed", "rho", "Th_rho"):
+        parity_record("S5 car_d (80,2000,2000), y-slab of 64 rows vs numpy oracle", k, res[k][:, ys].cpu().numpy(),
+                      ref[k][:, 1:-1])
+    parity_record("S5 car_d (80,2000,2000), y-slab of 64 rows vs numpy oracle", "PV", res["PV"][:, ys].cpu().numpy(),
+                  ref["PV"][:, 1:-1], floor=1e-3)
     for k in ("zeta_r", "zeta_t", "zeta_z", "div", "shear_deform", "wind_speed", "rho"):
         assert_same(res[k][:, ys].cpu().numpy(), ref[k][:, 1:-1], f"S5 slab {k}")
     assert_close(res["PV"][:, ys].cpu().numpy(), ref["PV"][:, 1:-1], 1e-10, "S5 slab PV", floor=1e-3)

@@ -717,3 +717,33 @@ def test_cyl_rotate_and_rmw10_follow_the_reference():
     cyl.v10 = f["vr"][0].copy()
     with pytest.raises(np.exceptions.AxisError):     # the reference's nanargmax(axis=1) on a 1-D array
         cyl.find_rmw_and_speed10()
+
+
+@pytest.mark.parametrize("src_dtype,fac_dtype", [(np.float32, np.float32), (np.float64, np.float32),
+                                                  (np.float32, np.float64), (np.float64, np.float64)])
+def test_set_data_map_factors_match_correct_map_scale(src_dtype, fac_dtype):
+    """wrfout_grid.correct_map_scale (grids/wrfout_grid.py:48-55: ua *= MAPFAC_MX, u10 *= MAPFAC_MX)
+    folded into the staging of set_data; reference = the NumPy in-place products, then the CPU pipeline."""
+    from meteotools_b200.grids import cylindrical_grid
+    rng = np.random.default_rng(9)
+    st = dict(Nr=14, Ntheta=16, Nz=6, dr=2000, dtheta=2 * np.pi / 16, dz=500, z_start=100, r_start=0,
+              theta_start=0, vertical_coord_type="z", dt=300)
+    nz, ny, nx, dx = 8, 44, 46, 2000.0
+    z3d = np.broadcast_to((np.arange(nz) * 600.0).reshape(-1, 1, 1), (nz, ny, nx)).astype(src_dtype)
+    ua = (10 * rng.standard_normal((nz, ny, nx))).astype(src_dtype)
+    va = (10 * rng.standard_normal((nz, ny, nx))).astype(src_dtype)
+    u10 = (10 * rng.standard_normal((ny, nx))).astype(src_dtype)
+    mx = (1.0 + 0.05 * rng.random((ny, nx))).astype(fac_dtype)
+    my = (1.0 + 0.05 * rng.random((ny, nx))).astype(fac_dtype)
+    cyl = cylindrical_grid(dict(st))
+    cyl.set_horizontal_location(45000.0, 43000.0)
+    cyl.set_data.__wrapped__(cyl, dx, dx, z3d, u=ua, v=va, u10=u10, map_factors=dict(u=mx, v=my, u10=mx))
+    ua_s, va_s, u10_s = ua.copy(), va.copy(), u10.copy()
+    ua_s *= mx          # exactly what correct_map_scale does
+    va_s *= my
+    u10_s *= mx
+    for name, src in (("u", ua_s), ("v", va_s)):
+        lev = oracle.interplevel(src, z3d, cyl.z)
+        assert_same(getattr(cyl, name), oracle.interp2D_fast_layers(dx, dx, cyl.xTR, cyl.yTR, lev), f"scaled {name}")
+    assert_same(cyl.u10, oracle.interp2D_fast(dx, dx, cyl.xTR, cyl.yTR, u10_s), "scaled u10")
+    assert not np.array_equal(ua_s, ua)
