@@ -20,7 +20,9 @@ namespace mt {
 struct CDiv {
     double d, rd;
     bool plain;
-    __device__ __forceinline__ explicit CDiv(double d_) : d(d_), rd(1.0 / d_)
+    __device__ __forceinline__ explicit CDiv(double d_) : CDiv(d_, 1.0 / d_) {}
+    // rd_ = RN(1 / d_) computed by the caller (on the host: the same IEEE division)
+    __device__ __forceinline__ CDiv(double d_, double rd_) : d(d_), rd(rd_)
     {
         const unsigned h = (unsigned)__double2hiint(d_) & 0x7fffffffu;
         plain = h - 0x00100000u >= 0x7fe00000u;   // zero, denormal, inf, NaN
