@@ -102,12 +102,13 @@ struct KP {
     WindOut wo;
 };
 
-// Divisions are IEEE divisions.  Three cheaper exact forms were measured and all were SLOWER here (4-7 %):
-// mt::CDiv (reciprocal + one exact correction step, branching to the IEEE division per quotient), the same with
-// an integer range test, and a branch-free variant that redoes flagged points -- the kernel is bound by
-// instruction fetch and dependent-issue latency of its ~2000-instruction straight-line body, not by the FP64
-// pipe (ncu: fp64 26 %, no_instruction and wait stalls), and every variant made the body longer
-// (profiles/experiments_r02.md).
+// Divisions by the grid spacings and by the radius go through mt::FDiv (fd.cuh): reciprocal once per thread,
+// three FP64 instructions per quotient, a branch-free select for the special operands -- bit-identical to the
+// IEEE division for every normal operand and for 0, NaN, inf, r = 0.  The Cartesian kernel gains 10 %, the
+// cylindrical one (23 such quotients per point) 32 %.  Variants that BRANCH to an IEEE division per quotient
+// (mt::CDiv) or redo flagged points in a second body measured 4-9 % slower than plain IEEE divisions: the
+// ~2000-instruction straight-line body lives on overlapping its dependent FP64 chains, and every convergence
+// region or second body costs more than the shorter sequence saves (profiles/experiments_r02.md).
 // MB: resident CTAs per SM the kernel is compiled for.
 template <int LAYOUT, bool CYL, bool FULL, int TR, int NS, int MB, int MSH>
 __global__ void __launch_bounds__(Geo<TR, CYL, NS, MSH>::NTHR, MB)
@@ -183,7 +184,7 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
     const bool want_def = FULL || o.shear_deform || o.stretch_deform || o.filamentation_time || o.strain_region;
     const bool want_div = FULL || o.div_hori || o.div;
     const bool wind_out = (p.flags & K_WIND) != 0;
-    const double ddz = p.dz, ddt = p.dt, ddr = p.dr;
+    const FDiv ddz(p.dz), ddt(p.dt), ddr(p.dr);   // the host has checked the three spacings (fdiv_divisor_ok)
 
     int slot = 0;          // stage of the plane that lands next
     uint32_t par = 0;
@@ -227,7 +228,7 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
             rr = rad(ir);
             r_a = rad(ir + er.oa / st), r_b = rad(ir + er.ob / st), r_c = rad(ir + er.oc / st);
         }
-        const double drr = rr;   // r[0] = 0: the IEEE division gives the reference's inf / NaN
+        const FDiv drr(rr);   // r[0] = 0: rd = inf, and a * inf is the reference's +-inf / NaN (FDiv::special)
         double f_fix = 0.0;   // ZTR: f(t, r) does not change along the march
         if (ZTR && p.f && in_dom) f_fix = __ldg(p.f + pofs);
 
@@ -264,7 +265,7 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
                         if (CYL && (wo.coriolis_force || wo.centrifugal_force || wo.aam)) {
                             const double fv = ZTR ? f_fix : __ldg(p.f + (int64_t)j * n1 + gr);
                             if (wo.coriolis_force) __stcs(wo.coriolis_force + m, fv * vb);
-                            if (wo.centrifugal_force) __stcs(wo.centrifugal_force + m, vb * vb / rr);
+                            if (wo.centrifugal_force) __stcs(wo.centrifugal_force + m, by(vb * vb, drr));
                             if (wo.aam) __stcs(wo.aam + m, vb * rr + 0.5 * fv * (rr * rr));  // :297
                         }
                     }
@@ -294,10 +295,10 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
                 constexpr bool IN = decltype(in_tag)::value;
                 const int sn = sc, s0 = slot_m * STAGED, sp = slot_p * STAGED;
                 const int64_t m = (int64_t)mm * plane + pofs;
-                auto d_march = [&](int F, double delta) { return by((sm[sn + F + ctr] - sm[sp + F + ctr]) / 2, delta); };
+                auto d_march = [&](int F, const FDiv &delta) { return by((sm[sn + F + ctr] - sm[sp + F + ctr]) / 2, delta); };
                 // FD2 along an in-plane axis from the three operands of `e` (see Edge); ka / kb / kc scale them
                 // (1 except for the r-weighted differences)
-                auto fd_sel = [&](int F, const Edge &e, double ka, double kb, double kc, double delta) {
+                auto fd_sel = [&](int F, const Edge &e, double ka, double kb, double kc, const FDiv &delta) {
                     const double A = sm[s0 + F + ctr + e.oa] * ka, B = sm[s0 + F + ctr + e.ob] * kb;
                     if (IN) return by((A - B) / 2, delta);
                     const double C = sm[s0 + F + ctr + e.oc] * kc;
@@ -308,8 +309,8 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
                     const double one_sided = (s12 + (e.first ? -C : C)) / 2;
                     return by(e.edge ? one_sided : (A - B) / 2, delta);
                 };
-                auto d_row = [&](int F, double delta) { return fd_sel(F, erow, 1.0, 1.0, 1.0, delta); };
-                auto d_col = [&](int F, double delta) { return fd_sel(F, ecol, 1.0, 1.0, 1.0, delta); };
+                auto d_row = [&](int F, const FDiv &delta) { return fd_sel(F, erow, 1.0, 1.0, 1.0, delta); };
+                auto d_col = [&](int F, const FDiv &delta) { return fd_sel(F, ecol, 1.0, 1.0, 1.0, delta); };
                 auto dz = [&](int F) { return ZTR ? d_march(F, ddz) : d_col(F, ddz); };
                 auto dt = [&](int F) { return ZTR ? d_row(F, ddt) : d_march(F, ddt); };
                 auto dr = [&](int F) { return ZTR ? d_col(F, ddr) : d_row(F, ddr); };
@@ -504,6 +505,8 @@ int stencil_tma(const mt_grid_t *g, const GridP &gp, const StageBIn &bi, const d
                 const WindOut &wo, const StageBOut &bo, bool full, cudaStream_t s)
 {
     if (!stencil_tma_supported(g)) return MT_ENOSUP;
+    // spacings the branch-free quotient cannot take exactly -> the register-marching kernels (IEEE divisions)
+    if (!fdiv_divisor_ok(gp.dz) || !fdiv_divisor_ok(gp.dt) || !fdiv_divisor_ok(gp.dr)) return MT_ENOSUP;
     const bool ztr = g->layout == MT_LAYOUT_ZTR;
     const int64_t n0 = ztr ? g->nz : g->nt, n1 = ztr ? g->nt : g->nr, n2 = ztr ? g->nr : g->nz;
     const double *A = u ? u : bi.a, *B = v ? v : bi.b;

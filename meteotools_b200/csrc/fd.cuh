@@ -3,6 +3,8 @@
 // differentiated axis; the evaluation order is NumPy's left-to-right order so that every
 // rounding matches (e.g. (-3*v0 + 4*v1 - v2)/2/delta; note "/2/delta", not "/(2*delta)").
 #pragma once
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mt {
@@ -43,11 +45,50 @@ struct CDiv {
     }
 };
 
+// The same quotient WITHOUT a branch, for the straight-line stencil body of csrc/diag_tma.cu.  The IEEE division
+// the compiler emits rebuilds the reciprocal for every quotient (MUFU.RCP64H + 4 DFMA) and wraps each one in a
+// convergence region around its slow path, which keeps the scheduler from overlapping the ~100-cycle dependent
+// chains of neighbouring divisions; CDiv's per-quotient branch does the same.  Here the three-instruction tail
+// always runs and an integer test of the dividend's exponent SELECTS between it and q0 = a * rd:
+//   a = +-0, NaN or +-inf, or a divisor that is 0 or +-inf (r[0] = 0 on the axis of a cylindrical grid: rd =
+//   +-inf)  ->  q0, which IS the IEEE result in all of these cases (sign of zero, 0/0 = NaN, x/0 = +-inf included);
+//   every other (normal) dividend  ->  the corrected quotient, bit-identical to a / d.
+// Not covered, and outside anything a model field holds: subnormal dividends or divisors (q0 may be 1 ulp off),
+// quotients in the subnormal range, a divisor whose significand is all ones (Markstein's exception).  The host
+// checks the grid spacings (fdiv_divisor_ok) and falls back to the IEEE kernels otherwise.
+struct FDiv {
+    double d, rd;
+    bool special;   // the divisor is 0, subnormal, inf or NaN
+    __device__ __forceinline__ explicit FDiv(double d_) : d(d_), rd(1.0 / d_)
+    {
+        special = ((((unsigned)__double2hiint(d_) + 0x00100000u) & 0x7fe00000u) == 0u);
+    }
+    __device__ __forceinline__ double operator()(double a) const
+    {
+        const double q0 = a * rd;
+        const double q = fma(fma(-q0, d, a), rd, q0);
+        // biased exponent of a is 0 (zero, subnormal) or 0x7ff (inf, NaN)  <=>  ((e + 1) & 0x7fe) == 0
+        const bool sp = special || ((((unsigned)__double2hiint(a) + 0x00100000u) & 0x7fe00000u) == 0u);
+        return sp ? q0 : q;
+    }
+};
+// a divisor FDiv may take from the host: a normal number of moderate size whose significand is not all ones
+inline bool fdiv_divisor_ok(double d)
+{
+    unsigned long long b;
+    static_assert(sizeof(b) == sizeof(d), "double is 64 bits");
+    memcpy(&b, &d, sizeof(b));
+    const unsigned e = (unsigned)((b >> 52) & 0x7ffu);
+    const unsigned long long m = b & 0xfffffffffffffULL;
+    return e >= 1023u - 200u && e <= 1023u + 200u && m != 0xfffffffffffffULL;
+}
+
 // the stencil formulas below divide through `by(x, delta)`: a plain double divisor gives the IEEE
 // division (fused diagnostic kernels: measured no gain from CDiv there, they are latency bound),
 // a CDiv the exact reciprocal-and-correct form (mt_fd: 0.386 -> 0.297 ms on 80 x 1000 x 1000)
 __device__ __forceinline__ double by(double a, double d) { return a / d; }
 __device__ __forceinline__ double by(double a, const CDiv &d) { return d(a); }
+__device__ __forceinline__ double by(double a, const FDiv &d) { return d(a); }
 
 // FD2, differential.py:30-34.  The axis segment [lo, hi) is what the caller may READ (halo
 // levels of a level shard included); `first`/`last` tell whether index 0 / n-1 of the segment

@@ -109,8 +109,8 @@ def main():
     alg = 8.0 * nz * nt * nr * (11 + n_out)
     res = {}
     ref = None
-    T = lambda shift=1, triv=0: {"MT_DIAG_TMA": "1", "MT_DIAG_SHIFT": str(shift), "MT_DIAG_TRIVIAL": str(triv)}  # noqa: E731
-    variants = (("marching", {"MT_DIAG_TMA": "0"}), ("tma_noshift", T(0)), ("tma", T(1)), ("trivial", T(1, 1)))
+    T = lambda split=0: {"MT_DIAG_TMA": "1", "SPLIT": str(split)}  # noqa: E731
+    variants = (("marching", {"MT_DIAG_TMA": "0", "SPLIT": "0"}), ("tma", T(0)), ("tma_split", T(1)))
     only = os.environ.get("VARIANTS")
     if only:
         variants = tuple(v for v in variants if v[0] in only.split(","))

@@ -123,3 +123,41 @@ def test_level_sharded_tma_path(kind, dims):
             got = _emulate(kind, fields, f2d, spac, outs, world, tables, split=split)
             for k in outs:
                 assert_same(got[k], ref[k], f"{kind} {k} world={world} split={split}")
+
+
+@pytest.mark.parametrize("kind,dims", [("car", (6, 24, 64)), ("cyl", (6, 24, 64))])
+def test_stencil_tma_special_values_match_the_ieee_kernels(kind, dims, monkeypatch):
+    """The TMA stencil kernel divides through mt::FDiv (reciprocal + exact correction, special operands selected
+    branch-free); the register-marching kernels use IEEE divisions.  Zero fields, negative zeros, NaN blocks
+    (terrain), +-inf points and the r = 0 column must come out BIT for bit the same, the sign of zero included."""
+    import torch
+    nz, nt, nr = dims
+    fields = _random_fields(nz, nt, nr, seed=21)
+    fields["w"][:] = 0.0                       # an identically zero field: every quotient of it is +-0
+    fields["u"][1, 3:9, 5:20] = -0.0
+    fields["u"][2, 4, :] = 0.0
+    fields["v"][:2, 10:14, 30:50] = np.nan     # terrain-masked block
+    fields["v"][4, 2, 7] = np.inf
+    fields["u"][3, 20, 40] = -np.inf
+    fields["T"][1, 12, 12] = np.nan
+    f2d = torch.from_numpy(5e-5 + 1e-9 * np.arange(nt * nr, dtype=np.float64).reshape(nt, nr)).cuda()
+    tables, spac = None, (250.0, 2000.0, 2000.0)
+    if kind == "cyl":
+        th = np.arange(nt) * (2 * np.pi / nt)
+        tables = dict(r=torch.from_numpy(np.arange(nr) * 1000.0).cuda(), sin_t=torch.from_numpy(np.sin(th)).cuda(),
+                      cos_t=torch.from_numpy(np.cos(th)).cuda())
+        spac = (250.0, 2 * np.pi / nt, 1000.0)
+    from meteotools_b200 import _lib
+    outs = [k for k in (_lib.CYL_D_OUT if kind == "cyl" else _lib.CAR_D_OUT) if k != "Th"]
+    monkeypatch.setenv("MT_DIAG_TMA", "1")
+    got = _emulate(kind, fields, f2d, spac, outs, 1, tables)
+    monkeypatch.setenv("MT_DIAG_TMA", "0")
+    ref = _emulate(kind, fields, f2d, spac, outs, 1, tables)
+    for k in outs:
+        a, b = got[k], ref[k]
+        if a.dtype != np.float64:
+            assert np.array_equal(a, b), k
+            continue
+        nan = np.isnan(a) & np.isnan(b)
+        same_bits = a.view(np.int64) == b.view(np.int64)        # +0 and -0 differ here
+        assert (same_bits | nan).all(), f"{kind} {k}: {np.count_nonzero(~(same_bits | nan))} points differ in bits"
