@@ -285,19 +285,34 @@ def sharded_car_d(rank, world, dist, reps=10, dims=CAR_S5, unsharded_ms=None):
         e1.record()
         e1.synchronize()
         ns.append(e0.elapsed_time(e1))
-    stats = torch.tensor([float(np.median(ts)), float(np.median(hs)), float(np.median(ns)), 0.0 if ok else 1.0],
-                         device="cuda", dtype=torch.float64)
+    # the shard's kernels alone, no exchange: as run() issues them (interior + boundary launches) and as one launch
+    def only(fn, n=5):
+        out = []
+        for _ in range(n):
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return float(np.median(out))
+    c_split = only(lambda: (job.stage_a(), job.stage_b_split()))
+    c_whole = only(lambda: (job.stage_a(), job.stage_b()))
+    stats = torch.tensor([float(np.median(ts)), float(np.median(hs)), float(np.median(ns)), 0.0 if ok else 1.0,
+                          c_split, c_whole], device="cuda", dtype=torch.float64)
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     comm.close()
     del job
     torch.cuda.empty_cache()
     if rank != 0:
         return None
-    ms, halo_ms, serial_ms, bad = (float(x) for x in stats.tolist())
+    ms, halo_ms, serial_ms, bad, c_split, c_whole = (float(x) for x in stats.tolist())
     npts = nz * ny * nx
     alg = 8.0 * npts * (len(names) + len(outs))
     out = dict(row=f"car_d {dims} level-sharded over {world} ranks, NCCL halo (v, w, theta_rho) overlapped", n_gpus=world,
                ms=round(ms, 4), halo_ms=round(halo_ms, 4), ms_without_overlap=round(serial_ms, 4),
+               ms_kernels_only_split_launches=round(c_split, 4), ms_kernels_only_one_launch=round(c_whole, 4),
                alg_bytes=alg, achieved_gbs_aggregate=round(alg / ms / 1e6, 1), points_per_s=npts / ms * 1e3,
                halo_bytes_per_rank=int(3 * ny * nx * 8 * ((1 if hlo else 0) + (1 if hhi else 0)) * 2),
                boundary_levels_match_unsharded=bool(bad == 0.0), scaling="strong",

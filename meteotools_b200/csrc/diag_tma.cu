@@ -65,7 +65,7 @@ struct Geo {
     static constexpr int STAGED = NHALO * BOXD + RHOD;           // doubles per plane stage
     static constexpr int NCONS = 32 * TR, NTHR = NCONS + 32;
     static constexpr int FA = 0, FB = BOXD, FW = 2 * BOXD, FT = 3 * BOXD, FP = 4 * BOXD, FRHO = NHALO * BOXD;
-    static constexpr size_t SMEM = (size_t)NS * STAGED * 8 + 2 * NS * 8 + 128;
+    static constexpr size_t SMEM = (size_t)NS * STAGED * 8 + 2 * NS * 8 + NS * 4 + 128;
 };
 
 // Operands of FD2 along one in-plane axis for one thread, as element offsets from its point (step = 1 along
@@ -95,6 +95,7 @@ struct KP {
     int m_lo, m_hi;        // march range that receives outputs
     int halo_lo, halo_hi;  // ZTR level shards: halo planes at the ends of the march axis
     int seg_len, nseg, tiles_r, tiles_c;
+    int *counter;          // task counter of this launch (zero at launch)
     unsigned flags;
     double dz, dt, dr;
     const double *r, *sin_t, *cos_t, *f;
@@ -122,6 +123,10 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
     unsigned char *smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * STAGED * 8);
     uint64_t *empty = full + NS;
+    // task of the plane in each stage (written by the producer before the stage's barrier is armed): tasks
+    // are drawn from a global counter, so a CTA that starts late -- its SM was busy with the NCCL kernels of
+    // the halo exchange -- simply takes fewer of them (a static round-robin made every other CTA wait for it)
+    volatile int *slot_task = reinterpret_cast<volatile int *>(empty + NS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -148,16 +153,23 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
                                           (has_rho ? G::RW * TR * 8 : 0));
         int slot = 0;
         uint32_t par = 1;   // a fresh mbarrier passes a wait on parity 1: the ring starts empty
-        for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+        while (true) {
+            const int task = atomicAdd(p.counter, 1);
+            if (task >= ntask) {   // end marker: complete the phase of the next stage without data
+                mbar_wait(empty + slot, par);
+                slot_task[slot] = -1;
+                mbar_arrive(full + slot);
+                break;
+            }
             const int seg = task / per_seg, rem = task - seg * per_seg;
             const int tr = rem / p.tiles_c, tc = rem - tr * p.tiles_c;
             const int s_lo = p.m_lo + seg * p.seg_len, s_hi = min(p.m_hi, s_lo + p.seg_len);
-            if (s_lo >= s_hi) continue;
             const int j_lo = max(s_lo - 1, 0), j_hi = min(s_hi, p.n0 - 1);
             const int x = tc * TC - MSH - HX, y = row0(tr) - HY;
             for (int j = j_lo; j <= j_hi; ++j) {
                 mbar_wait(empty + slot, par);
                 unsigned char *st = smem + (size_t)slot * STAGED * 8;
+                slot_task[slot] = task;
                 mbar_expect_tx(full + slot, bytes);
                 load_3d(st + FA * 8, &M.a, full + slot, x, y, j);
                 load_3d(st + FB * 8, &M.b, full + slot, x, y, j);
@@ -198,11 +210,13 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
         --held;
     };
 
-    for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+    while (true) {
+        mbar_wait(full + slot, par);   // the first plane of the next task, or the end marker
+        const int task = slot_task[slot];
+        if (task < 0) break;
         const int seg = task / per_seg, rem = task - seg * per_seg;
         const int tr = rem / p.tiles_c, tc = rem - tr * p.tiles_c;
         const int s_lo = p.m_lo + seg * p.seg_len, s_hi = min(p.m_hi, s_lo + p.seg_len);
-        if (s_lo >= s_hi) continue;
         const int j_lo = max(s_lo - 1, 0), j_hi = min(s_hi, n0 - 1);
         const int r0 = row0(tr), c0 = tc * TC;
         const int gr = r0 + warp;
@@ -234,7 +248,7 @@ k_stencil_tma(const __grid_constant__ Maps M, const KP p)
 
         int slot_m = 0, slot_p = 0;   // stages of planes j - 1 and j - 2
         for (int j = j_lo; j <= j_hi; ++j) {
-            mbar_wait(full + slot, par);
+            if (j > j_lo) mbar_wait(full + slot, par);
             ++held;
             const int sc = slot * STAGED;
             const bool owned = j >= s_lo && j < s_hi;
@@ -466,6 +480,26 @@ int plane_map(const double *ptr, int64_t n0, int64_t n1, int64_t n2, int bx, int
     return MT_OK;
 }
 
+// One zero-initialised task counter per launch: a pool of 1024 per device, used round-robin (launches on
+// different streams may overlap, so they must not share one); the memset travels on the launch's stream.
+int *task_counter(cudaStream_t s)
+{
+    constexpr int POOL = 1024, MAXDEV = 64;
+    static std::mutex mu;
+    static int *pool[MAXDEV] = {};
+    static unsigned next[MAXDEV] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+    int *c = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pool[dev] && cudaMalloc(&pool[dev], POOL * sizeof(int)) != cudaSuccess) return nullptr;
+        c = pool[dev] + (next[dev]++ % POOL);
+    }
+    if (cudaMemsetAsync(c, 0, sizeof(int), s) != cudaSuccess) return nullptr;
+    return c;
+}
+
 int env_int(const char *name, int dflt)
 {
     const char *e = getenv(name);
@@ -589,6 +623,11 @@ int stencil_tma(const mt_grid_t *g, const GridP &gp, const StageBIn &bi, const d
     if (rc == MT_OK && bi.rho) rc = plane_map(bi.rho, n0, n1, n2, TC + msh, TRv, &M.rho);
     if (rc != MT_OK) return rc;
 
+    kp.counter = task_counter(s);
+    if (!kp.counter) {
+        set_error("stencil_tma: cannot allocate the task counter");
+        return MT_ECUDA;
+    }
     ProfScope prof(CYL ? "k_stencil_tma_cyl" : "k_stencil_tma_car", (mt_stream_t)s);
 #define DT_L(LAYOUT_, FULL_, MSH_) launch<LAYOUT_, CYL, FULL_, 8, 4, 2, MSH_>(M, kp, grid, s)
 #define DT_ZTR(FULL_)                                                                           \
