@@ -578,9 +578,12 @@ def main():
                 unsharded = r5["ms"]
                 secondary.append(r5)
             barrier()
-            sh = bench_rows.sharded_car_d(rank, world, dist, reps=10, unsharded_ms=unsharded)
-            if sh is not None:
-                secondary.append(sh)
+            # the level-sharded S5 with both transports of the halo planes: NVLink peer memory (copy engines +
+            # stream memory operations, the default of pipeline.LevelShardDyn users on one node) and NCCL
+            for transport in ("peer", "nccl"):
+                sh = bench_rows.sharded_car_d(rank, world, dist, reps=10, unsharded_ms=unsharded, transport=transport)
+                if sh is not None:
+                    secondary.append(sh)
 
     if rank == 0:
         out = {

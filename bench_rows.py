@@ -208,12 +208,12 @@ def _level(k, ny, nx, names):
     return one
 
 
-def sharded_car_d(rank, world, dist, reps=10, dims=CAR_S5, unsharded_ms=None):
+def sharded_car_d(rank, world, dist, reps=10, dims=CAR_S5, unsharded_ms=None, transport="nccl"):
     """S5 car_d split into `world` level shards: the real NCCL halo (mt_halo_exchange on a side stream),
     overlapped with the interior levels.  Returns the row on rank 0 (None elsewhere)."""
     import torch
     from meteotools_b200 import _lib
-    from meteotools_b200.pipeline import HaloComm, LevelShardDyn, level_shard
+    from meteotools_b200.pipeline import HaloComm, LevelShardDyn, PeerHalo, level_shard
     nz, ny, nx = dims
     lo, hi, hlo, hhi = level_shard(nz, rank, world)
     names = list(DYN_IN)
@@ -223,7 +223,7 @@ def sharded_car_d(rank, world, dist, reps=10, dims=CAR_S5, unsharded_ms=None):
     f2d = torch.full((ny, nx), 5e-5, device="cuda", dtype=torch.float64)
     outs = list(_lib.CAR_D_OUT)
     spac = (250.0, 2000.0, 2000.0)
-    comm = HaloComm(rank, world, dist)
+    comm = PeerHalo(rank, world, ny * nx, 3, dist) if transport == "peer" else HaloComm(rank, world, dist)
     job = LevelShardDyn("car", local, f2d, spac, (lo, hi, hlo, hhi), nz, outs)
     del local
     job.run(comm)
@@ -278,9 +278,13 @@ def sharded_car_d(rank, world, dist, reps=10, dims=CAR_S5, unsharded_ms=None):
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        comm.exchange(job.halo_inputs, hlo, hhi)
-        job.stage_a()
-        comm.exchange(job.halo_derived, hlo, hhi)
+        if transport == "peer":      # (one exchange per step: the sequence numbers of the ranks must agree)
+            job.stage_a()
+            comm.exchange(job.halo_fields, hlo, hhi)
+        else:
+            comm.exchange(job.halo_inputs, hlo, hhi)
+            job.stage_a()
+            comm.exchange(job.halo_derived, hlo, hhi)
         job.stage_b()
         e1.record()
         e1.synchronize()
@@ -297,6 +301,19 @@ def sharded_car_d(rank, world, dist, reps=10, dims=CAR_S5, unsharded_ms=None):
             e1.synchronize()
             out.append(e0.elapsed_time(e1))
         return float(np.median(out))
+    # timeline of the overlapped run: when each phase ends, ms after the start (median of 5, max over ranks)
+    tl = {}
+    for _ in range(5):
+        dist.barrier()
+        marks = {}
+        job.run(comm, marks=marks)
+        torch.cuda.synchronize()
+        for k, ev in marks.items():
+            if k != "start":
+                tl.setdefault(k, []).append(marks["start"].elapsed_time(ev))
+    tl_keys = ["inputs_exchanged", "stage_a", "theta_rho_exchanged", "interior", "end"]
+    tl_t = torch.tensor([float(np.median(tl[k])) if k in tl else 0.0 for k in tl_keys], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tl_t, op=dist.ReduceOp.MAX)
     c_split = only(lambda: (job.stage_a(), job.stage_b_split()))
     c_whole = only(lambda: (job.stage_a(), job.stage_b()))
     stats = torch.tensor([float(np.median(ts)), float(np.median(hs)), float(np.median(ns)), 0.0 if ok else 1.0,
@@ -310,9 +327,12 @@ def sharded_car_d(rank, world, dist, reps=10, dims=CAR_S5, unsharded_ms=None):
     ms, halo_ms, serial_ms, bad, c_split, c_whole = (float(x) for x in stats.tolist())
     npts = nz * ny * nx
     alg = 8.0 * npts * (len(names) + len(outs))
-    out = dict(row=f"car_d {dims} level-sharded over {world} ranks, NCCL halo (v, w, theta_rho) overlapped", n_gpus=world,
+    how = ("halo planes (v, w, theta_rho) by the copy engines into the neighbour's memory (NVLink peer memory, "
+           "stream memory operations)" if transport == "peer" else "NCCL halo (v, w, theta_rho) overlapped")
+    out = dict(row=f"car_d {dims} level-sharded over {world} ranks, {how}", n_gpus=world, transport=transport,
                ms=round(ms, 4), halo_ms=round(halo_ms, 4), ms_without_overlap=round(serial_ms, 4),
                ms_kernels_only_split_launches=round(c_split, 4), ms_kernels_only_one_launch=round(c_whole, 4),
+               timeline_ms_after_start={k: round(float(v), 4) for k, v in zip(tl_keys, tl_t.tolist())},
                alg_bytes=alg, achieved_gbs_aggregate=round(alg / ms / 1e6, 1), points_per_s=npts / ms * 1e3,
                halo_bytes_per_rank=int(3 * ny * nx * 8 * ((1 if hlo else 0) + (1 if hhi else 0)) * 2),
                boundary_levels_match_unsharded=bool(bad == 0.0), scaling="strong",

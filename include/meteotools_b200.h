@@ -406,6 +406,23 @@ int mt_nccl_comm_destroy(void *comm);
 int mt_halo_exchange(void *comm, double *const *fields, int nfields, int64_t plane_elems, int64_t nz_local,
                      int halo_lo, int halo_hi, int rank_lo, int rank_hi, mt_stream_t stream);
 
+/* ---- the same halo planes over NVLink / NVSwitch PEER MEMORY (csrc/peer.cu): no kernel, no SM -----------------
+ * A "box" is device memory its owner allocates (mt_peer_box_create, which also returns the 64-byte CUDA IPC
+ * handle) and the neighbouring process maps (mt_peer_box_open).  Planes travel with mt_peer_copy
+ * (cudaMemcpyAsync: the copy engines, straight into the neighbour's box) and the two processes order themselves
+ * with stream memory operations: mt_stream_write32(addr, v) stores v when the stream reaches it,
+ * mt_stream_wait_geq32(addr, v) holds the stream until (int32)(*addr - v) >= 0 (cuStreamWriteValue32 /
+ * cuStreamWaitValue32).  pipeline.PeerHalo builds the one-level halo exchange of a level shard from these
+ * (layout and protocol in csrc/peer.cu); the processes must share one node with peer access between the GPUs. */
+int mt_peer_supported(void);
+int mt_peer_box_create(int64_t bytes, void **box, void *ipc_handle64);
+int mt_peer_box_open(const void *ipc_handle64, void **peer_ptr);
+int mt_peer_box_close(void *peer_ptr);
+int mt_peer_box_destroy(void *box);
+int mt_peer_copy(void *dst, const void *src, int64_t bytes, mt_stream_t stream);
+int mt_stream_write32(void *addr, uint32_t value, mt_stream_t stream);
+int mt_stream_wait_geq32(void *addr, uint32_t value, mt_stream_t stream);
+
 /* ---- azimuthal statistics (a13; cylindrical_grid.py:214-235) -------------------------------
  * sym[z,r] = nanmean over theta, asy = var - sym (asy may be NULL). */
 int mt_azimuthal_mean(const double *var, const mt_grid_t *g, double *sym, double *asy,

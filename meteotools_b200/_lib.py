@@ -153,6 +153,14 @@ _SIGS = {
     "mt_nccl_comm_init": (c_int, [ct.POINTER(c_vp), c_int, c_int, c_vp]),
     "mt_nccl_comm_destroy": (c_int, [c_vp]),
     "mt_halo_exchange": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_vp]),
+    "mt_peer_supported": (c_int, []),
+    "mt_peer_box_create": (c_int, [c_i64, ct.POINTER(c_vp), c_vp]),
+    "mt_peer_box_open": (c_int, [c_vp, ct.POINTER(c_vp)]),
+    "mt_peer_box_close": (c_int, [c_vp]),
+    "mt_peer_box_destroy": (c_int, [c_vp]),
+    "mt_peer_copy": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "mt_stream_write32": (c_int, [c_vp, ct.c_uint32, c_vp]),
+    "mt_stream_wait_geq32": (c_int, [c_vp, ct.c_uint32, c_vp]),
     "mt_azimuthal_mean": (c_int, [c_vp, ct.POINTER(mt_grid_t), c_vp, c_vp, c_vp]),
     "mt_scale_box_2d": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_i64, c_i64, c_vp]),
     "mt_cast_f32_f64": (c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -27,7 +27,7 @@ path_of_meteotools = os.path.dirname(os.path.abspath(__file__))
 platform_name = platform.system()
 
 SOURCES = ["api.cu", "interp.cu", "legacy.cu", "interplevel.cu", "fd.cu", "thermo.cu", "diag.cu",
-           "util.cu", "setdata_tma.cu", "reduce.cu", "spline.cu", "diag_tma.cu", "halo.cu"]
+           "util.cu", "setdata_tma.cu", "reduce.cu", "spline.cu", "diag_tma.cu", "halo.cu", "peer.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

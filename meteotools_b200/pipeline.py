@@ -304,6 +304,74 @@ class HaloComm:
             self.comm = None
 
 
+class PeerHalo:
+    """The level-shard halo exchange over NVLink / NVSwitch PEER MEMORY (csrc/peer.cu): the planes travel by
+    the copy engines straight into a mailbox in the neighbour's memory, the processes order themselves with
+    stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32) -- no kernel, no SM, no host
+    synchronisation.  Same call as ``HaloComm.exchange``; all ranks must sit on one node with peer access.
+
+        halo = PeerHalo(rank, world, plane_elems=ny * nx, nfields=3)   # collective: IPC handles are exchanged
+        halo.exchange([w, v, th_rho], hlo, hhi, stream)
+    """
+    HEADER = 256   # bytes: [0] data_seq, [64] ack_seq
+
+    def __init__(self, rank, world, plane_elems, nfields, dist=None):
+        import ctypes as ct
+        import torch.distributed as dist_mod
+        D.require_cuda()
+        dist = dist or dist_mod
+        self.lib, self.rank, self.world = _lib.load(), rank, world
+        if not self.lib.mt_peer_supported():
+            raise RuntimeError("cuStreamWaitValue32 / cuStreamWriteValue32 are not available in this driver")
+        self.plane_bytes, self.nfields, self.seq = int(plane_elems) * 8, int(nfields), 0
+        nbytes = self.HEADER + self.nfields * self.plane_bytes
+        self.box, handles = {}, {}
+        for d, nb in (("lo", rank - 1), ("hi", rank + 1)):
+            if 0 <= nb < world:
+                ptr, h = ct.c_void_p(), ct.create_string_buffer(64)
+                _lib.check(self.lib.mt_peer_box_create(nbytes, ct.byref(ptr), h), "mt_peer_box_create")
+                self.box[d], handles[d] = ptr.value, h.raw
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles)
+        self.peer = {}
+        for d, nb, facing in (("lo", rank - 1, "hi"), ("hi", rank + 1, "lo")):
+            if 0 <= nb < world:     # the neighbour's box that faces me
+                ptr = ct.c_void_p()
+                _lib.check(self.lib.mt_peer_box_open(everyone[nb][facing], ct.byref(ptr)), "mt_peer_box_open")
+                self.peer[d] = ptr.value
+        dist.barrier()
+
+    def exchange(self, tensors, halo_lo, halo_hi, stream=None):
+        """One halo level of every (nz_local, ny, nx) C-order tensor, asynchronous on `stream`."""
+        if not (halo_lo or halo_hi) or not tensors:
+            return
+        lib, pb = self.lib, self.plane_bytes
+        assert len(tensors) <= self.nfields and all(x.is_contiguous() and x[0].numel() * 8 == pb for x in tensors)
+        s = stream.cuda_stream if stream is not None else D.stream()
+        self.seq += 1
+        seq, nzl = self.seq, int(tensors[0].shape[0])
+        sides = ([("lo", halo_lo, 0)] if halo_lo else []) + ([("hi", nzl - 1 - halo_hi, nzl - 1)] if halo_hi else [])
+        for d, own_level, _ in sides:      # my boundary planes -> the neighbour's box
+            _lib.check(lib.mt_stream_wait_geq32(self.box[d] + 64, seq - 1, s), "wait ack")
+            for k, x in enumerate(tensors):
+                _lib.check(lib.mt_peer_copy(self.peer[d] + self.HEADER + k * pb, x.data_ptr() + own_level * pb, pb, s),
+                           "mt_peer_copy")
+            _lib.check(lib.mt_stream_write32(self.peer[d], seq, s), "write data_seq")
+        for d, _, halo_level in sides:     # the neighbour's planes -> my halo levels
+            _lib.check(lib.mt_stream_wait_geq32(self.box[d], seq, s), "wait data")
+            for k, x in enumerate(tensors):
+                _lib.check(lib.mt_peer_copy(x.data_ptr() + halo_level * pb, self.box[d] + self.HEADER + k * pb, pb, s),
+                           "mt_peer_copy")
+            _lib.check(lib.mt_stream_write32(self.peer[d] + 64, seq, s), "write ack_seq")
+
+    def close(self):
+        for ptr in self.peer.values():
+            self.lib.mt_peer_box_close(ptr)
+        for ptr in self.box.values():
+            self.lib.mt_peer_box_destroy(ptr)
+        self.peer, self.box = {}, {}
+
+
 class LevelShardDyn:
     """cyl_d / car_d of ONE time step on ONE level shard.
 
@@ -369,6 +437,8 @@ class LevelShardDyn:
             setattr(dout, k, self.outs[k].data_ptr())
         self._g, self._din, self._dout = g, din, dout
         self._call = self.lib.mt_cyl_d if kind == "cyl" else self.lib.mt_car_d
+        self._plane, self._hyd, self._f2d = nt * nr, hyd, f2d
+        self._views = {}
         # the z-differentiated fields: inputs first (they can travel at once), theta_rho after stage A
         self.halo_inputs = [self.fields["w"], self.fields["v"]] + ([self.fields["u"]] if kind == "cyl" else [])
         self.halo_derived = [self.outs["Th_rho"]]
@@ -383,6 +453,32 @@ class LevelShardDyn:
     def stage_a(self):
         """Thermodynamic point-wise fields of all local levels (Tv, rho, density factor, theta, theta_rho)."""
         self._stage(_lib.MT_STAGE_A | _lib.MT_STAGE_WIND_IN_B)
+
+    def stage_a_levels(self, level0, nlev):
+        """The same for the local levels [level0, level0 + nlev) only: the point-wise stage has no neighbours, so
+        a level range is the same call on pointers moved to its first level."""
+        if nlev <= 0:
+            return
+        key = (level0, nlev)
+        if key not in self._views:
+            off = level0 * self._plane * 8
+            g = _lib.mt_grid_t()
+            for name, _ in _lib.mt_grid_t._fields_:
+                setattr(g, name, getattr(self._g, name))
+            g.nz, g.halo_lo, g.halo_hi, g.is_bottom, g.is_top, g.sub_lo, g.sub_hi = nlev, 0, 0, 1, 1, 0, 0
+            din = _lib.mt_dyn_in_t()
+            for k in ("u", "v", "w", "p", "T", "Th", "qv"):
+                setattr(din, k, self.fields[k].data_ptr() + off if k in self.fields else None)
+            din.f = self._f2d.data_ptr() if self._f2d is not None else None
+            for i in range(6):
+                din.q[i] = self.fields[self._hyd[i]].data_ptr() + off if i < len(self._hyd) else None
+            dout = (_lib.mt_cyl_d_out_t if self.kind == "cyl" else _lib.mt_car_d_out_t)()
+            for k in ("Tv", "rho", "density_factor", "Th", "Th_rho"):
+                if k in self.outs:
+                    setattr(dout, k, self.outs[k].data_ptr() + off)
+            self._views[key] = (g, din, dout)
+        g, din, dout = self._views[key]
+        _lib.check(self._call(g, din, dout, _lib.MT_STAGE_A | _lib.MT_STAGE_WIND_IN_B, D.stream()), "stage A (levels)")
 
     def stage_b(self, sub=(0, 0)):
         """Stencil outputs + the wind-derived point-wise outputs of the owned levels [sub[0], sub[1])
@@ -403,35 +499,93 @@ class LevelShardDyn:
         if self.hhi and (self.nz_own > 1 or not self.hlo):
             self.stage_b((self.nz_own - 1, self.nz_own))
 
-    def run(self, comm=None):
+    def run(self, comm=None, marks=None):
         """The whole set with the halo exchange overlapped (see the class docstring).  `comm`: a HaloComm,
-        or None for a single shard."""
+        or None for a single shard.  `marks`: a dict that receives CUDA events at the phase boundaries
+        (start, inputs_exchanged, stage_a, theta_rho_exchanged, interior, end) for timeline measurements."""
         t = self.t
+
+        def mark(name, stream):
+            if marks is not None:
+                ev = t.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                marks[name] = ev
         if comm is None or not (self.hlo or self.hhi):
             self.stage_a()
             self.stage_b()
             return
+        if isinstance(comm, PeerHalo):
+            return self._run_peer(comm, mark)
         main = t.cuda.current_stream()
         if self._side is None:
-            self._side = t.cuda.Stream()
+            # HIGH priority: the stencil and point-wise kernels are persistent and fill every SM; when the
+            # exchange and a compute kernel become runnable together, NCCL's few CTAs must be placed first,
+            # or the planes only start to move when the compute kernel has finished (measured: no overlap)
+            self._side = t.cuda.Stream(priority=-1)
         side = self._side
+        mark("start", main)
         side.wait_stream(main)                      # the inputs are ready
         comm.exchange(self.halo_inputs, self.hlo, self.hhi, side)
+        mark("inputs_exchanged", side)
         self.stage_a()
+        mark("stage_a", main)
         ev_a = t.cuda.Event()
         ev_a.record(main)
         side.wait_event(ev_a)                       # theta_rho of the boundary levels exists
         comm.exchange(self.halo_derived, self.hlo, self.hhi, side)
         ev_h = t.cuda.Event()
         ev_h.record(side)
+        mark("theta_rho_exchanged", side)
         a, b = self.interior()
         if b > a:
             self.stage_b((a, b))                    # overlaps the planes in flight
+        mark("interior", main)
         main.wait_event(ev_h)
         if self.hlo:
             self.stage_b((0, 1))
         if self.hhi and (self.nz_own > 1 or not self.hlo):
             self.stage_b((self.nz_own - 1, self.nz_own))
+        mark("end", main)
+
+    def _run_peer(self, halo, mark):
+        """run() over peer memory: ONE exchange of all three planes per side, started as soon as theta_rho of
+        the boundary levels exists; it needs no SM, so the point-wise stage of the other levels and the
+        interior stencil levels run beside it undisturbed.
+
+            side:  [theta_rho of the boundary levels] -> put planes -> wait neighbours' planes -> halo levels
+            main:  point-wise stage of the other levels -> stencil interior -> [wait side] -> boundary levels
+        """
+        t = self.t
+        main = t.cuda.current_stream()
+        if self._side is None:
+            self._side = t.cuda.Stream(priority=-1)
+        side = self._side
+        first, last = self.hlo, self.hlo + self.nz_own - 1          # local indices of the owned end levels
+        send = sorted({first} if self.hlo else set()) + sorted(({last} if self.hhi else set()) - ({first} if self.hlo else set()))
+        mark("start", main)
+        for lvl in send:                                            # tiny launches: one level each
+            self.stage_a_levels(lvl, 1)
+        ev0 = t.cuda.Event()
+        ev0.record(main)
+        side.wait_event(ev0)
+        halo.exchange(self.halo_fields, self.hlo, self.hhi, side)
+        ev_h = t.cuda.Event()
+        ev_h.record(side)
+        mark("theta_rho_exchanged", side)
+        lo = first + (1 if first in send else 0)
+        hi = last - (1 if last in send else 0)
+        self.stage_a_levels(lo, hi - lo + 1)                        # never touches the halo levels
+        mark("stage_a", main)
+        a, b = self.interior()
+        if b > a:
+            self.stage_b((a, b))
+        mark("interior", main)
+        main.wait_event(ev_h)
+        if self.hlo:
+            self.stage_b((0, 1))
+        if self.hhi and (self.nz_own > 1 or not self.hlo):
+            self.stage_b((self.nz_own - 1, self.nz_own))
+        mark("end", main)
 
     def result(self):
         return {k: self.outs[k][self.hlo:self.hlo + self.nz_own] for k in self.outputs}

@@ -65,9 +65,10 @@ def sharded(reps):
     if rank == 0 and os.environ.get("MT_SHARD_REF", "1") == "1":
         unsharded = bench_rows.bench_dyn("car", bench_rows.CAR_S5, 5, "S5 car_d, one GPU")["ms"]
     dist.barrier()
-    r = bench_rows.sharded_car_d(rank, world, dist, reps=reps, unsharded_ms=unsharded)
-    if rank == 0:
-        print(json.dumps(r))
+    for transport in os.environ.get("MT_SHARD_TRANSPORT", "nccl,peer").split(","):
+        r = bench_rows.sharded_car_d(rank, world, dist, reps=reps, unsharded_ms=unsharded, transport=transport)
+        if rank == 0:
+            print(json.dumps(r))
     dist.destroy_process_group()
 
 
