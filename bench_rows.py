@@ -128,6 +128,10 @@ class DynCase:
         self._lib.check(self.call(self.g, self.din, self.dout, self._lib.MT_STAGE_ALL, D.stream()), "dyn")
 
     def per_kernel(self, reps=3):
+        import torch
+        for _ in range(2):   # first launches of a process: module load, tensor maps, function attributes
+            self.run()
+        torch.cuda.synchronize()
         self.lib.mt_profile_enable(1)
         for _ in range(reps):
             self.run()

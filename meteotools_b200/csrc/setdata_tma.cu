@@ -59,7 +59,10 @@ struct __align__(16) Meta {   // one staged target (two 16-byte words; a third w
     double fx, fy;
     int tgt;                    // target index (output row = tgt * o_n)
     int terrain;                // terrain level index; bit 30: same four corners as the predecessor
-    uint32_t b01, b23;          // tile-local ids of the four corner columns (rows of `lev`), 16 bits each
+    // the four corner columns as BYTE offsets into `lev` (column id * column pitch, < 65536: 80 columns of
+    // <= 98 doubles): corner (y0, x0) in the low half of `b01`, the step to x1 in its high half, the step to
+    // y1 in `b23` -- the consumer forms the four addresses with five integer instructions
+    uint32_t b01, b23;
 };
 static_assert(sizeof(Meta) == 32, "Meta is read as two 16-byte words");
 
@@ -133,6 +136,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
         int nid = 0;
         int4 nit = make_int4(0, 0, 0, 0);
         constexpr int TS = MAXT / 32;
+        const uint32_t cpitch_p = (uint32_t)LP * 8u;   // bytes per level-interpolated column
         int tgt[TS];
         int4 six[TS];
         double2 sw[TS];
@@ -188,8 +192,9 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                             m.fx = sw[k].x, m.fy = sw[k].y, m.tgt = tgt[k];
                             const uint32_t r0 = (uint32_t)(six[k].z - nit.y) * BX, r1 = (uint32_t)(six[k].w - nit.y) * BX;
                             const uint32_t c0 = (uint32_t)(six[k].x - nit.x), c1 = (uint32_t)(six[k].y - nit.x);
-                            m.b01 = (r0 + c0) | ((r0 + c1) << 16);
-                            m.b23 = (r1 + c0) | ((r1 + c1) << 16);
+                            // x1 >= x0 and y1 >= y0 (equal on the clamped edge of the source grid)
+                            m.b01 = (r0 + c0) * cpitch_p | (((c1 - c0) * cpitch_p) << 16);
+                            m.b23 = (r1 - r0) * cpitch_p;
                             // the predecessor of an odd position is the previous lane's target
                             const uint32_t p01 = __shfl_up_sync(act, m.b01, 1), p23 = __shfl_up_sync(act, m.b23, 1);
                             const bool same = (lane & 1) && p01 == m.b01 && p23 == m.b23;
@@ -250,7 +255,7 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     const bool col_thread = tid < NG * NC;
     const int npair = (nlev + 1) >> 1, ppn = EXACT ? PP : (npair + NG - 1) / NG, lp_own = g_own * ppn;
     const bool wide = ((nlev | (int)o_n) & 1) == 0;   // even rows: 16-byte stores; else two 8-byte stores
-    const int o_pitch = (int)o_n;   // output row pitch in elements (host checks that it fits)
+    const uint32_t o_pitch_b = (uint32_t)o_n * 8u;   // output row pitch in bytes (the host checks that it fits)
     // this thread's brackets (row offsets of the "lo" samples of both levels of a pair, weights)
     int kk[PP];
     double wx[PP], wy[PP];
@@ -343,8 +348,8 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             for (int i = 0; i < PP; ++i) {
                 const int lp = lp_own + i;
                 const bool act = EXACT || (i < ppn && lp < npair);
-                const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;
                 const double want0 = act ? lev_s[2 * lp] : 0.0, want1 = act ? lev_s[2 * lp + 1] : 0.0;
+                const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;
                 const double a0 = (double)vt[ka], a1 = (double)vt[ka + dhi];
                 const double b0 = (double)vt[kb], b1 = (double)vt[kb + dhi];
                 const double q0 = (want0 - a0) / (a1 - a0), q1 = (want1 - b0) / (b1 - b0);
@@ -396,9 +401,9 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             // C: bilinear, one warp per target, two consecutive targets per step; the item's targets
             // are sorted by source cell, so a pair usually shares its four corner columns: one set
             // of shared-memory loads then serves both
-            double *__restrict__ out = P.out[v];
+            // this lane's level pair of output row 0
+            unsigned char *out_b = reinterpret_cast<unsigned char *>(P.out[v]) + lane * 16;
             const uint32_t lane_a = smem_u32(levb_w) + lane * 16;   // this lane's level pair, as a shared address
-            const uint32_t cpitch = (uint32_t)LP * 8u;
             auto lds2 = [](uint32_t addr) {
                 double2 r;
                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
@@ -408,52 +413,61 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
                 const bool two = j + 1 < cnt;
                 const Meta m0 = mt_[j];
                 const Meta m1 = mt_[two ? j + 1 : j];
-                double *o0 = out + (int64_t)m0.tgt * o_pitch, *o1 = out + (int64_t)m1.tgt * o_pitch;   // 32 x 32 -> 64
+                // row address = base + tgt * pitch in bytes: ONE 32 x 32 + 64 multiply-add per target
+                double *o0l = reinterpret_cast<double *>(out_b + (uint64_t)(uint32_t)m0.tgt * o_pitch_b);
+                double *o1l = reinterpret_cast<double *>(out_b + (uint64_t)(uint32_t)m1.tgt * o_pitch_b);
                 const bool same = !two || (m1.terrain >> 30) != 0;
                 const int ter0 = m0.terrain & 0x3fffffff, ter1 = m1.terrain & 0x3fffffff;
                 const bool masked = (ter0 | ter1) > 0;                                   // warp-uniform
-                const uint32_t pa0 = lane_a + (m0.b01 & 0xffffu) * cpitch, pb0 = lane_a + (m0.b01 >> 16) * cpitch;
-                const uint32_t pc0 = lane_a + (m0.b23 & 0xffffu) * cpitch, pd0 = lane_a + (m0.b23 >> 16) * cpitch;
-                const uint32_t pa1 = lane_a + (m1.b01 & 0xffffu) * cpitch, pb1 = lane_a + (m1.b01 >> 16) * cpitch;
-                const uint32_t pc1 = lane_a + (m1.b23 & 0xffffu) * cpitch, pd1 = lane_a + (m1.b23 >> 16) * cpitch;
+                const uint32_t pa0 = lane_a + (m0.b01 & 0xffffu), pb0 = pa0 + (m0.b01 >> 16);
+                const uint32_t pc0 = pa0 + m0.b23, pd0 = pc0 + (m0.b01 >> 16);
+                const uint32_t pa1 = lane_a + (m1.b01 & 0xffffu), pb1 = pa1 + (m1.b01 >> 16);
+                const uint32_t pc1 = pa1 + m1.b23, pd1 = pc1 + (m1.b01 >> 16);
                 constexpr bool ONE_STEP = EXACT && 2 * NG * PP <= 64;
                 for (int l = lane * 2, lo8 = 0; l < nlev; l += 64, lo8 += 512) {
                     const double2 a0 = lds2(pa0 + lo8), b0 = lds2(pb0 + lo8);
                     const double2 c0 = lds2(pc0 + lo8), d0 = lds2(pd0 + lo8);
-                    double2 a1 = a0, b1 = b0, c1 = c0, d1 = d0;
-                    if (!same) {
-                        a1 = lds2(pa1 + lo8), b1 = lds2(pb1 + lo8);
-                        c1 = lds2(pc1 + lo8), d1 = lds2(pd1 + lo8);
-                    }
-                    double2 r0, r1;
-                    {   // fastcompute.f90:100-102
-                        const double t0x = (b0.x - a0.x) * m0.fx + a0.x, t1x = (d0.x - c0.x) * m0.fx + c0.x;
-                        const double t0y = (b0.y - a0.y) * m0.fx + a0.y, t1y = (d0.y - c0.y) * m0.fx + c0.y;
-                        r0.x = (t1x - t0x) * m0.fy + t0x;
-                        r0.y = (t1y - t0y) * m0.fy + t0y;
-                    }
-                    {
-                        const double t0x = (b1.x - a1.x) * m1.fx + a1.x, t1x = (d1.x - c1.x) * m1.fx + c1.x;
-                        const double t0y = (b1.y - a1.y) * m1.fx + a1.y, t1y = (d1.y - c1.y) * m1.fx + c1.y;
-                        r1.x = (t1x - t0x) * m1.fy + t0x;
-                        r1.y = (t1y - t0y) * m1.fy + t0y;
-                    }
-                    if (masked) {   // terrain: level index below hgt_idx -> NaN (cylindrical_grid.py:171-181)
-                        if (ter0 > l) r0.x = nan_f64();
-                        if (ter0 > l + 1) r0.y = nan_f64();
-                        if (ter1 > l) r1.x = nan_f64();
-                        if (ter1 > l + 1) r1.y = nan_f64();
-                    }
-                    if (EXACT || wide) {
-                        MT_TMA_ST(reinterpret_cast<double2 *>(o0 + l), r0);
-                        if (two) MT_TMA_ST(reinterpret_cast<double2 *>(o1 + l), r1);
-                    } else {   // odd level count / odd row pitch: rows are only 8-byte aligned
-                        __stcs(o0 + l, r0.x);
-                        if (l + 1 < nlev) __stcs(o0 + l + 1, r0.y);
-                        if (two) {
-                            __stcs(o1 + l, r1.x);
-                            if (l + 1 < nlev) __stcs(o1 + l + 1, r1.y);
+                    // both targets of the step from their corner values (the SAME registers when the pair
+                    // shares its source cell: two instantiations of the body instead of eight register copies)
+                    auto finish = [&](const double2 &a1, const double2 &b1, const double2 &c1, const double2 &d1) {
+                        double2 r0, r1;
+                        {   // fastcompute.f90:100-102
+                            const double t0x = (b0.x - a0.x) * m0.fx + a0.x, t1x = (d0.x - c0.x) * m0.fx + c0.x;
+                            const double t0y = (b0.y - a0.y) * m0.fx + a0.y, t1y = (d0.y - c0.y) * m0.fx + c0.y;
+                            r0.x = (t1x - t0x) * m0.fy + t0x;
+                            r0.y = (t1y - t0y) * m0.fy + t0y;
                         }
+                        {
+                            const double t0x = (b1.x - a1.x) * m1.fx + a1.x, t1x = (d1.x - c1.x) * m1.fx + c1.x;
+                            const double t0y = (b1.y - a1.y) * m1.fx + a1.y, t1y = (d1.y - c1.y) * m1.fx + c1.y;
+                            r1.x = (t1x - t0x) * m1.fy + t0x;
+                            r1.y = (t1y - t0y) * m1.fy + t0y;
+                        }
+                        if (masked) {   // terrain: level index below hgt_idx -> NaN (cylindrical_grid.py:171-181)
+                            if (ter0 > l) r0.x = nan_f64();
+                            if (ter0 > l + 1) r0.y = nan_f64();
+                            if (ter1 > l) r1.x = nan_f64();
+                            if (ter1 > l + 1) r1.y = nan_f64();
+                        }
+                        double *o0 = o0l + (lo8 >> 3), *o1 = o1l + (lo8 >> 3);   // = row + l
+                        if (EXACT || wide) {
+                            MT_TMA_ST(reinterpret_cast<double2 *>(o0), r0);
+                            if (two) MT_TMA_ST(reinterpret_cast<double2 *>(o1), r1);
+                        } else {   // odd level count / odd row pitch: rows are only 8-byte aligned
+                            __stcs(o0, r0.x);
+                            if (l + 1 < nlev) __stcs(o0 + 1, r0.y);
+                            if (two) {
+                                __stcs(o1, r1.x);
+                                if (l + 1 < nlev) __stcs(o1 + 1, r1.y);
+                            }
+                        }
+                    };
+                    if (same) {
+                        finish(a0, b0, c0, d0);
+                    } else {
+                        const double2 a1 = lds2(pa1 + lo8), b1 = lds2(pb1 + lo8);
+                        const double2 c1 = lds2(pc1 + lo8), d1 = lds2(pd1 + lo8);
+                        finish(a1, b1, c1, d1);
                     }
                     if (ONE_STEP) break;
                 }
@@ -609,7 +623,7 @@ int setdata_tma_impl(const void *const *fields, int nvar, const void *vert, int 
                                                  "from column (0,0) of the full coordinate array)");
     const int64_t eb = dtype == MT_F64 ? 8 : 4;
     MT_REQUIRE(nz >= 2 && nz <= 254 && nlev >= 1 && nlev <= 2 * NG * PP_LARGE && o_n >= nlev &&
-                   o_n < 2147483647LL && n < 2147483647LL,
+                   o_n < (1LL << 28) && n < 2147483647LL,
                "mt_setdata_tma: need 2 <= nz <= 254 and 1..%d target levels", 2 * NG * PP_LARGE);
     const bool wide_rows = nlev % 2 == 0 && o_n % 2 == 0;   // 16-byte stores need 16-byte aligned rows
     MT_REQUIRE(row_pitch >= nx && (row_pitch * eb) % 16 == 0 && ((uintptr_t)vert % 16) == 0,
