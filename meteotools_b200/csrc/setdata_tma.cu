@@ -88,6 +88,131 @@ __device__ unsigned long long g_tma_timing[8];
 #endif
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
+// The producer warp (shared by both kernels): takes items from the atomic counter, stages the item's targets
+// into the ring of shared-memory tables ONE ITEM AHEAD, and streams the tiles coordinate, var 0, var 1, ... of
+// consecutive items through the ring of TMA stages (full / empty mbarriers).
+template <typename T>
+__device__ __forceinline__ void producer_warp(const TmaParams &P, int NT, int nz, int LP, int stages, int stage_bytes,
+                                              int org_x, int org_y, const int4 *__restrict__ pix,
+                                              const double2 *__restrict__ pw, const int32_t *__restrict__ order,
+                                              const int4 *__restrict__ items, int nitems, int n_order,
+                                              int *__restrict__ counter, const int32_t *__restrict__ hgt_idx,
+                                              unsigned char *smem, Meta *meta, uint64_t *full, uint64_t *empty,
+                                              int4 *s_item4, int *s_itemid, int lane)
+{
+    // =============================== producer warp ===============================
+    int q_slot = 0;
+    uint32_t q_par = 1;  // a fresh mbarrier passes a wait on parity 1: the ring starts empty
+    int n = 0;
+    // staging pipeline of the NEXT item (registers)
+    int nid = 0;
+    int4 nit = make_int4(0, 0, 0, 0);
+    constexpr int TS = MAXT / 32;
+    const uint32_t cpitch_p = (uint32_t)LP * 8u;   // bytes per level-interpolated column
+    int tgt[TS];
+    int4 six[TS];
+    double2 sw[TS];
+    int ster[TS];
+    auto stage_phase = [&](int ph, int slot_meta) {
+        switch (ph) {
+            case 0:
+                if (lane == 0) nid = atomicAdd(counter, 1);
+                break;
+            case 1:
+                nid = __shfl_sync(0xffffffffu, nid, 0);
+                if (nid < nitems) nit = items[nid];
+                else nit = make_int4(0, 0, 0, 0);
+                if (nid < nitems) {
+                    // `items` comes from the caller.  A tile origin that is not 16-byte aligned makes the
+                    // TMA unit raise cudaErrorIllegalInstruction (sticky: the context is lost), a bad
+                    // start / count reads beyond `order`: such an item is made harmless here -- origin
+                    // rounded down, no targets -- and reported through the status word counter[1]
+                    // (mt_setdata_tma_status -> MT_EINVAL).
+                    constexpr int ALIGN = 16 / (int)sizeof(T);
+                    const int rel = nit.x - org_x;
+                    const int mis = ((rel % ALIGN) + ALIGN) % ALIGN;
+                    const bool bad = mis != 0 || nit.w < 0 || nit.w > MAXT || nit.z < 0 || nit.z > n_order - nit.w;
+                    if (bad) {
+                        if (lane == 0) atomicOr(counter + 1, 1);
+                        nit.x -= mis, nit.w = 0, nit.z = 0;
+                    }
+                }
+                break;
+            case 2:
+#pragma unroll
+                for (int k = 0; k < TS; ++k) {
+                    const int j = lane + 32 * k;
+                    tgt[k] = j < nit.w ? order[nit.z + j] : -1;
+                }
+                break;
+            case 3:
+#pragma unroll
+                for (int k = 0; k < TS; ++k)
+                    if (tgt[k] >= 0) {
+                        six[k] = pix[tgt[k]];
+                        sw[k] = pw[tgt[k]];
+                        ster[k] = hgt_idx ? hgt_idx[tgt[k]] : 0;
+                    }
+                break;
+            case 4: {
+                Meta *mt_ = meta + slot_meta * MAXT;
+#pragma unroll
+                for (int k = 0; k < TS; ++k) {
+                    const unsigned act = __ballot_sync(0xffffffffu, tgt[k] >= 0);
+                    if (tgt[k] >= 0) {
+                        Meta m;
+                        m.fx = sw[k].x, m.fy = sw[k].y, m.tgt = tgt[k];
+                        const uint32_t r0 = (uint32_t)(six[k].z - nit.y) * BX, r1 = (uint32_t)(six[k].w - nit.y) * BX;
+                        const uint32_t c0 = (uint32_t)(six[k].x - nit.x), c1 = (uint32_t)(six[k].y - nit.x);
+                        // x1 >= x0 and y1 >= y0 (equal on the clamped edge of the source grid)
+                        m.b01 = (r0 + c0) * cpitch_p | (((c1 - c0) * cpitch_p) << 16);
+                        m.b23 = (r1 - r0) * cpitch_p;
+                        // the predecessor of an odd position is the previous lane's target
+                        const uint32_t p01 = __shfl_up_sync(act, m.b01, 1), p23 = __shfl_up_sync(act, m.b23, 1);
+                        const bool same = (lane & 1) && p01 == m.b01 && p23 == m.b23;
+                        m.terrain = ster[k] | (same ? (1 << 30) : 0);
+                        mt_[lane + 32 * k] = m;
+                    }
+                }
+                __syncwarp();
+                break;
+            }
+            default: break;
+        }
+    };
+    for (int ph = 0; ph < 5; ++ph) stage_phase(ph, 0);  // first item: synchronously
+    while (true) {
+        const int id = nid;
+        const int4 it = nit;
+        if (id >= nitems) {  // end marker: complete the phase of the next stage without data
+            if (lane == 0) {
+                mbar_wait(empty + q_slot, q_par);
+                s_itemid[n & 3] = -1;
+                mbar_arrive(full + q_slot);
+            }
+            break;
+        }
+        int ph = 0;
+        for (int t = 0; t < NT; ++t) {
+            if (lane == 0) {
+                mbar_wait(empty + q_slot, q_par);
+                if (t == 0) {
+                    s_itemid[n & 3] = id;
+                    s_item4[n & 3] = it;
+                }
+                mbar_expect_tx(full + q_slot, (uint32_t)(NC * nz * (int)sizeof(T)));
+                load_3d(smem + (size_t)q_slot * stage_bytes, &P.maps[t], full + q_slot, it.x - org_x,
+                            it.y - org_y, 0);
+            }
+            if (++q_slot == stages) q_slot = 0, q_par ^= 1u;
+            __syncwarp();
+            if (ph < 5) stage_phase(ph++, (n + 1) % NMETA);
+        }
+        while (ph < 5) stage_phase(ph++, (n + 1) % NMETA);
+        ++n;
+    }
+}
+
 // PP = level pairs per column thread (>= ceil(nlev / 2 / NG)): the brackets of a thread's own
 // (column, level pair) set live in registers for all variables of the item.
 // EXACT: nlev == 2 * NG * PP, every thread owns exactly PP level pairs (no guards in the column
@@ -128,117 +253,8 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
     __syncthreads();
 
     if (warp == NCONS / 32) {
-        // =============================== producer warp ===============================
-        int q_slot = 0;
-        uint32_t q_par = 1;  // a fresh mbarrier passes a wait on parity 1: the ring starts empty
-        int n = 0;
-        // staging pipeline of the NEXT item (registers)
-        int nid = 0;
-        int4 nit = make_int4(0, 0, 0, 0);
-        constexpr int TS = MAXT / 32;
-        const uint32_t cpitch_p = (uint32_t)LP * 8u;   // bytes per level-interpolated column
-        int tgt[TS];
-        int4 six[TS];
-        double2 sw[TS];
-        int ster[TS];
-        auto stage_phase = [&](int ph, int slot_meta) {
-            switch (ph) {
-                case 0:
-                    if (lane == 0) nid = atomicAdd(counter, 1);
-                    break;
-                case 1:
-                    nid = __shfl_sync(0xffffffffu, nid, 0);
-                    if (nid < nitems) nit = items[nid];
-                    else nit = make_int4(0, 0, 0, 0);
-                    if (nid < nitems) {
-                        // `items` comes from the caller.  A tile origin that is not 16-byte aligned makes the
-                        // TMA unit raise cudaErrorIllegalInstruction (sticky: the context is lost), a bad
-                        // start / count reads beyond `order`: such an item is made harmless here -- origin
-                        // rounded down, no targets -- and reported through the status word counter[1]
-                        // (mt_setdata_tma_status -> MT_EINVAL).
-                        constexpr int ALIGN = 16 / (int)sizeof(T);
-                        const int rel = nit.x - org_x;
-                        const int mis = ((rel % ALIGN) + ALIGN) % ALIGN;
-                        const bool bad = mis != 0 || nit.w < 0 || nit.w > MAXT || nit.z < 0 || nit.z > n_order - nit.w;
-                        if (bad) {
-                            if (lane == 0) atomicOr(counter + 1, 1);
-                            nit.x -= mis, nit.w = 0, nit.z = 0;
-                        }
-                    }
-                    break;
-                case 2:
-#pragma unroll
-                    for (int k = 0; k < TS; ++k) {
-                        const int j = lane + 32 * k;
-                        tgt[k] = j < nit.w ? order[nit.z + j] : -1;
-                    }
-                    break;
-                case 3:
-#pragma unroll
-                    for (int k = 0; k < TS; ++k)
-                        if (tgt[k] >= 0) {
-                            six[k] = pix[tgt[k]];
-                            sw[k] = pw[tgt[k]];
-                            ster[k] = hgt_idx ? hgt_idx[tgt[k]] : 0;
-                        }
-                    break;
-                case 4: {
-                    Meta *mt_ = meta + slot_meta * MAXT;
-#pragma unroll
-                    for (int k = 0; k < TS; ++k) {
-                        const unsigned act = __ballot_sync(0xffffffffu, tgt[k] >= 0);
-                        if (tgt[k] >= 0) {
-                            Meta m;
-                            m.fx = sw[k].x, m.fy = sw[k].y, m.tgt = tgt[k];
-                            const uint32_t r0 = (uint32_t)(six[k].z - nit.y) * BX, r1 = (uint32_t)(six[k].w - nit.y) * BX;
-                            const uint32_t c0 = (uint32_t)(six[k].x - nit.x), c1 = (uint32_t)(six[k].y - nit.x);
-                            // x1 >= x0 and y1 >= y0 (equal on the clamped edge of the source grid)
-                            m.b01 = (r0 + c0) * cpitch_p | (((c1 - c0) * cpitch_p) << 16);
-                            m.b23 = (r1 - r0) * cpitch_p;
-                            // the predecessor of an odd position is the previous lane's target
-                            const uint32_t p01 = __shfl_up_sync(act, m.b01, 1), p23 = __shfl_up_sync(act, m.b23, 1);
-                            const bool same = (lane & 1) && p01 == m.b01 && p23 == m.b23;
-                            m.terrain = ster[k] | (same ? (1 << 30) : 0);
-                            mt_[lane + 32 * k] = m;
-                        }
-                    }
-                    __syncwarp();
-                    break;
-                }
-                default: break;
-            }
-        };
-        for (int ph = 0; ph < 5; ++ph) stage_phase(ph, 0);  // first item: synchronously
-        while (true) {
-            const int id = nid;
-            const int4 it = nit;
-            if (id >= nitems) {  // end marker: complete the phase of the next stage without data
-                if (lane == 0) {
-                    mbar_wait(empty + q_slot, q_par);
-                    s_itemid[n & 3] = -1;
-                    mbar_arrive(full + q_slot);
-                }
-                break;
-            }
-            int ph = 0;
-            for (int t = 0; t < NT; ++t) {
-                if (lane == 0) {
-                    mbar_wait(empty + q_slot, q_par);
-                    if (t == 0) {
-                        s_itemid[n & 3] = id;
-                        s_item4[n & 3] = it;
-                    }
-                    mbar_expect_tx(full + q_slot, (uint32_t)(NC * nz * (int)sizeof(T)));
-                    load_3d(smem + (size_t)q_slot * stage_bytes, &P.maps[t], full + q_slot, it.x - org_x,
-                                it.y - org_y, 0);
-                }
-                if (++q_slot == stages) q_slot = 0, q_par ^= 1u;
-                __syncwarp();
-                if (ph < 5) stage_phase(ph++, (n + 1) % NMETA);
-            }
-            while (ph < 5) stage_phase(ph++, (n + 1) % NMETA);
-            ++n;
-        }
+        producer_warp<T>(P, NT, nz, LP, stages, stage_bytes, org_x, org_y, pix, pw, order, items, nitems, n_order,
+                         counter, hgt_idx, smem, meta, full, empty, s_item4, s_itemid, lane);
         return;
     }
 
@@ -376,18 +392,28 @@ k_setdata_tma(const __grid_constant__ TmaParams P, int nvar, int nz, int nlev, i
             if (col_thread) {
                 const T *fc = raw + (size_t)c_slot * stage_elems + c_own;
                 double *lv = reinterpret_cast<double *>(levb_w) + c_own * LP;
+                // all the samples first, then the lerps and stores: a store to `lev` may alias the tile as far as
+                // the compiler knows, so per-pair code is a chain load -> lerp -> store -> next load (5 round trips)
+                constexpr int BB = PP <= 5 ? PP : 1;   // pairs per batch (4 doubles each in registers; PP = 8 has none to spare)
 #pragma unroll
-                for (int i = 0; i < PP; ++i) {
-                    const int lp = lp_own + i;
-                    if (EXACT || (i < ppn && lp < npair)) {
-                        const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;
-                        const double f00 = (double)fc[ka], f01 = (double)fc[ka + dhi];
-                        const double f10 = (double)fc[kb], f11 = (double)fc[kb + dhi];
-                        double2 r;
-                        r.x = (1.0 - wx[i]) * f00 + wx[i] * f01;
-                        r.y = (1.0 - wy[i]) * f10 + wy[i] * f11;
-                        if (ROUND) r.x = (double)(float)r.x, r.y = (double)(float)r.y;
-                        *reinterpret_cast<double2 *>(lv + 2 * lp) = r;
+                for (int i0 = 0; i0 < PP; i0 += BB) {
+                    double f[BB][4];
+#pragma unroll
+                    for (int i = i0; i < i0 + BB && i < PP; ++i) {
+                        const int ka = kk[i] & 0xffff, kb = kk[i] >> 16;   // valid rows also for unused pairs
+                        f[i - i0][0] = (double)fc[ka], f[i - i0][1] = (double)fc[ka + dhi];
+                        f[i - i0][2] = (double)fc[kb], f[i - i0][3] = (double)fc[kb + dhi];
+                    }
+#pragma unroll
+                    for (int i = i0; i < i0 + BB && i < PP; ++i) {
+                        const int lp = lp_own + i;
+                        if (EXACT || (i < ppn && lp < npair)) {
+                            double2 r;
+                            r.x = (1.0 - wx[i]) * f[i - i0][0] + wx[i] * f[i - i0][1];
+                            r.y = (1.0 - wy[i]) * f[i - i0][2] + wy[i] * f[i - i0][3];
+                            if (ROUND) r.x = (double)(float)r.x, r.y = (double)(float)r.y;
+                            *reinterpret_cast<double2 *>(lv + 2 * lp) = r;
+                        }
                     }
                 }
             }
