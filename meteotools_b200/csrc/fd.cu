@@ -6,6 +6,8 @@
 //               differentiated axis, blockIdx.z (+ a stride loop) the outer index; neighbours are
 //               re-read through L1/L2 (same rows, just loaded by this block);
 //   inner == 1: the differentiated axis itself is contiguous: threads walk it, blockIdx.y the rows.
+#include <cstdlib>
+
 #include "fd.cuh"
 
 namespace {
@@ -77,6 +79,27 @@ k_fd_row(const double *__restrict__ in, double *__restrict__ out, int64_t rows, 
     }
 }
 
+// The contiguous axis in FLAT order: thread <-> element of the whole array, so that every warp stores 32
+// consecutive doubles starting on a 256-byte boundary whatever the row length (rows of 1000 doubles start at
+// multiples of 64 bytes; a warp store that straddles a 256-byte block costs ~20 % of the write bandwidth on
+// B200: profiles/experiments_r02.md section 2).  The row of an element comes from one exact double-precision
+// quotient: floor((idx + 0.5) / n) has no rounding hazard for idx < 2^32.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_fd_row_flat(const double *__restrict__ in, double *__restrict__ out, uint32_t total, int n, double rn, double delta,
+              double rdelta)
+{
+    const mt::CDiv dd(delta, rdelta);
+    for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+        const uint32_t row = (uint32_t)__double2uint_rz(((double)idx + 0.5) * rn);
+        const int i = (int)(idx - row * (uint32_t)n);
+        const double *base = in + (size_t)row * n;
+        auto v = [&](int k) { return __ldg(base + k); };
+        mt::st_stream(out + idx, fd_apply<KIND>(v, i, n, dd));
+        if (idx + gridDim.x * 256u < idx) break;   // wrap of the 32-bit index
+    }
+}
+
 }  // namespace
 
 extern "C" int mt_fd(const double *in, double *out, int64_t outer, int64_t n, int64_t inner,
@@ -88,7 +111,28 @@ extern "C" int mt_fd(const double *in, double *out, int64_t outer, int64_t n, in
     MT_REQUIRE(n >= need, "mt_fd: axis length %lld < %d", (long long)n, need);
     cudaStream_t s = (cudaStream_t)stream;
     mt::ProfScope prof("k_fd", stream);
-    if (inner == 1) {
+    static const bool flat_rows = [] {   // MT_FD_FLAT=0: the row-tiled kernel (A/B runs)
+        const char *e = getenv("MT_FD_FLAT");
+        return !(e && e[0] == '0');
+    }();
+    if (inner == 1 && flat_rows && outer * n < (int64_t)0xffffffffLL && n % 32 != 0) {
+        // rows that do not start on 256-byte boundaries: flat order (rows that do are aligned either way)
+        const uint32_t total = (uint32_t)(outer * n);
+        const unsigned grid = (unsigned)mt::grid_for((int64_t)total, 256, 8);
+        switch (kind) {
+#define FD_CASE(K) \
+    case K: k_fd_row_flat<K><<<grid, 256, 0, s>>>(in, out, total, (int)n, 1.0 / (double)n, delta, 1.0 / delta); break;
+            FD_CASE(MT_FD2)
+            FD_CASE(MT_FD4)
+            FD_CASE(MT_FD2_FRONT)
+            FD_CASE(MT_FD2_BACK)
+            FD_CASE(MT_FD2_2)
+            FD_CASE(MT_FD2_2_FRONT)
+            FD_CASE(MT_FD2_2_BACK)
+#undef FD_CASE
+            default: mt::set_error("mt_fd: unknown kind %d", kind); return MT_EINVAL;
+        }
+    } else if (inner == 1) {
         const dim3 grid((unsigned)((n + 255) / 256), (unsigned)(outer < 32768 ? outer : 32768));
         switch (kind) {
 #define FD_CASE(K) \
