@@ -40,6 +40,18 @@ def test_fd_kat_and_shapes(C):  # test_calc.py:81-91
         C.FD2(np.zeros((5, 5)), 1.0, 0, cyclic=True)   # unreachable in the reference too
 
 
+def test_fd_contiguous_axis_flat_and_tiled_orders(C):
+    """The contiguous axis runs in flat order (thread <-> element of the whole array, csrc/fd.cu k_fd_row_flat)
+    when its rows are not multiples of 32 doubles and in row tiles otherwise: every kind, row lengths on both
+    sides of the switch, row counts that leave ragged last blocks."""
+    rng = np.random.default_rng(11)
+    for rows, n in ((1, 5), (7, 31), (3, 33), (129, 100), (5, 1000), (4, 64), (9, 1024)):
+        v = rng.standard_normal((rows, n))
+        v[rows // 2, n // 2] = np.nan
+        for name in ("FD2", "FD4", "FD2_front", "FD2_back", "FD2_2", "FD2_2_front", "FD2_2_back"):
+            assert_same(getattr(C, name)(v, 0.37, 1), getattr(co, name)(v, 0.37, 1), f"{name} ({rows}, {n})")
+
+
 def test_thermo_golden(C, golden_calc):
     g = golden_calc
     T, P, qv, ql, RH = g["t_T"], g["t_P"], g["t_qv"], g["t_ql"], g["t_RH"]
