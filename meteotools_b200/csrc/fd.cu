@@ -24,10 +24,20 @@ __device__ __forceinline__ double fd_apply(V v, int i, int n, const mt::CDiv &de
     return mt::fd2_2_back(v, i, n, delta);
 }
 
-constexpr int FD_CHUNK = 16;   // points of the differentiated axis per thread (inner > 1)
+// Points of the differentiated axis per thread (inner > 1) and resident CTAs per SM.  Eight points at 40
+// registers: with sixteen (round 1) the eighteen operands did not fit the 80 registers of three resident CTAs and
+// ptxas kept them in LOCAL memory (168 bytes of stack): 0.33 ms; 8 / 6 CTAs: 0.22 / 0.21 ms along axes 0 / 1 of
+// (80, 1000, 1000) (profiles/experiments_r02.md section 3).  -DMT_FD_CHUNK / -DMT_FD_MINB for A/B builds.
+#ifndef MT_FD_CHUNK
+#define MT_FD_CHUNK 8
+#endif
+#ifndef MT_FD_MINB
+#define MT_FD_MINB 6
+#endif
+constexpr int FD_CHUNK = MT_FD_CHUNK;
 
 template <int KIND>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, MT_FD_MINB)
 k_fd(const double *__restrict__ in, double *__restrict__ out, int64_t outer, int n, int64_t inner,
      double delta)
 {
@@ -40,10 +50,9 @@ k_fd(const double *__restrict__ in, double *__restrict__ out, int64_t outer, int
         double *ob = out + o * n * inner + j;
         auto v = [&](int k) { return __ldg(base + (int64_t)k * inner); };
         if (KIND == MT_FD2) {
-            // the hot kind: the chunk's FD_CHUNK + 2 operands are loaded FIRST -- eighteen independent loads in
-            // flight per thread (a rolling prev / cur / next loop keeps one: the stream probe of
-            // profiles/experiments_r02.md runs such "march" reads at 60 % of the linear rate) -- then
-            // differenced from registers; one load per point either way
+            // the hot kind: the chunk's FD_CHUNK + 2 operands are loaded FIRST -- ten independent loads in flight
+            // per thread (a rolling prev / cur / next loop keeps one) -- then differenced from registers; the two
+            // halo operands of a chunk are the neighbouring chunks' own, i.e. L2 hits
             double val[FD_CHUNK + 2];
 #pragma unroll
             for (int k = 0; k < FD_CHUNK + 2; ++k) {
@@ -65,6 +74,12 @@ k_fd(const double *__restrict__ in, double *__restrict__ out, int64_t outer, int
     }
 }
 
+#ifndef MT_FD_FLAT_U
+#define MT_FD_FLAT_U 6
+#endif
+#ifndef MT_FD_FLAT_MINB
+#define MT_FD_FLAT_MINB 4
+#endif
 template <int KIND>
 __global__ void __launch_bounds__(256)
 k_fd_row(const double *__restrict__ in, double *__restrict__ out, int64_t rows, int n, double delta, double rdelta)
@@ -72,7 +87,7 @@ k_fd_row(const double *__restrict__ in, double *__restrict__ out, int64_t rows, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const mt::CDiv dd(delta, rdelta);   // 1 / delta comes from the host: one point per thread, no division per thread
-    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {   // (several rows per trip measured slower: 0.41 vs 0.29 ms)
         const double *base = in + r * n;
         auto v = [&](int k) { return __ldg(base + k); };
         mt::st_stream(out + r * n + i, fd_apply<KIND>(v, i, n, dd));
@@ -85,18 +100,45 @@ k_fd_row(const double *__restrict__ in, double *__restrict__ out, int64_t rows, 
 // B200: profiles/experiments_r02.md section 2).  The row of an element comes from one exact double-precision
 // quotient: floor((idx + 0.5) / n) has no rounding hazard for idx < 2^32.
 template <int KIND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MT_FD_FLAT_MINB)
 k_fd_row_flat(const double *__restrict__ in, double *__restrict__ out, uint32_t total, int n, double rn, double delta,
               double rdelta)
 {
+    // U elements per thread and trip, a grid stride apart: their neighbour loads are issued together (one element
+    // per trip keeps 16 bytes per thread in flight: latency bound at full occupancy, ncu long_scoreboard 32 per issue)
+    constexpr int U = MT_FD_FLAT_U;
     const mt::CDiv dd(delta, rdelta);
-    for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
-        const uint32_t row = (uint32_t)__double2uint_rz(((double)idx + 0.5) * rn);
-        const int i = (int)(idx - row * (uint32_t)n);
-        const double *base = in + (size_t)row * n;
-        auto v = [&](int k) { return __ldg(base + k); };
-        mt::st_stream(out + idx, fd_apply<KIND>(v, i, n, dd));
-        if (idx + gridDim.x * 256u < idx) break;   // wrap of the 32-bit index
+    const uint64_t stride = (uint64_t)gridDim.x * 256u;
+    for (uint64_t base = blockIdx.x * 256u + threadIdx.x; base < total; base += U * stride) {
+        uint32_t row[U];
+        int i[U];
+        double hi[U], lo[U];
+        bool act[U], inner[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const uint64_t idx = base + k * stride;
+            act[k] = idx < total;
+            const uint32_t ix = act[k] ? (uint32_t)idx : 0u;
+            row[k] = (uint32_t)__double2uint_rz(((double)ix + 0.5) * rn);
+            i[k] = (int)(ix - row[k] * (uint32_t)n);
+            inner[k] = KIND == MT_FD2 && act[k] && i[k] > 0 && i[k] < n - 1;
+            hi[k] = inner[k] ? __ldg(in + ix + 1) : 0.0;
+            lo[k] = inner[k] ? __ldg(in + ix - 1) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (!act[k]) continue;
+            const uint32_t ix = (uint32_t)(base + k * stride);
+            double r;
+            if (inner[k]) {
+                r = dd((hi[k] - lo[k]) / 2);   // the interior expression of mt::fd2
+            } else {
+                const double *b = in + (size_t)row[k] * n;
+                auto v = [&](int j) { return __ldg(b + j); };
+                r = fd_apply<KIND>(v, i[k], n, dd);
+            }
+            mt::st_stream(out + ix, r);
+        }
     }
 }
 
