@@ -10,7 +10,10 @@
 // the contiguous one -- so they are bit-identical to the reference's.  The full-grid sums (IKE,
 // the last step of calc_RZaverage) use a block tree and stay tolerance-class (1e-10 relative,
 // north star); the smoothers are pure +,*,/ in the reference's order: bit-exact.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "fd.cuh"
 
 namespace {
 
@@ -35,7 +38,27 @@ k_axis_wsum(const double *__restrict__ var, int64_t n_f, int64_t n_s, int64_t n_
         const int64_t s = q / n_f, f = q - s * n_f;
         const double *p = var + f * s_f + s * s_s;
         double acc = 0.0, wsum = 0.0;
-        for (int64_t k = 0; k < n_k; ++k) {
+        // eight terms are loaded before they are added IN ORDER: the sum is sequential by contract (NumPy's order
+        // along a strided axis), but its loads need not wait for each other
+        constexpr int U = 8;
+        int64_t k = 0;
+        for (; k + U <= n_k; k += U) {
+            double wk[U], t[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                wk[j] = __ldg(w + k + j);
+                t[j] = __ldg(p + (k + j) * s_k);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const double x = t[j] * wk[j];
+                if (!isnan(x)) {
+                    acc += x;
+                    wsum += wk[j];
+                }
+            }
+        }
+        for (; k < n_k; ++k) {
             const double wk = __ldg(w + k);
             const double t = __ldg(p + k * s_k) * wk;
             if (!isnan(t)) {
@@ -165,7 +188,20 @@ k_azimuthal_stats(const double *__restrict__ var, int nz, int nt, int nr, int64_
         const int64_t base = iz * sz + ir * sr;
         double s = 0.0;
         int cnt = 0;
-        for (int t = 0; t < nt; ++t) {
+        constexpr int U = 8;   // loads in flight; the additions stay in order
+        int t0 = 0;
+        for (; t0 + U <= nt; t0 += U) {
+            double v[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) v[j] = __ldg(var + base + (int64_t)(t0 + j) * st);
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (!isnan(v[j])) {
+                    s += v[j];
+                    ++cnt;
+                }
+        }
+        for (int t = t0; t < nt; ++t) {
             const double v = __ldg(var + base + t * st);
             if (!isnan(v)) {
                 s += v;
@@ -175,13 +211,27 @@ k_azimuthal_stats(const double *__restrict__ var, int nz, int nt, int nr, int64_
         const double mean = cnt ? s / (double)cnt : nan_f64();
         if (sym) sym[(int64_t)iz * nr + ir] = mean;  // (nz, nr) C-order
         double ssq = 0.0;
-        if (asy || axisym)
-            for (int t = 0; t < nt; ++t) {
+        if (asy || axisym) {
+            int t1 = 0;
+            for (; t1 + U <= nt; t1 += U) {
+                double v[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j) v[j] = __ldg(var + base + (int64_t)(t1 + j) * st);
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const double a = v[j] - mean;
+                    if (asy) asy[base + (int64_t)(t1 + j) * st] = a;
+                    const double a2 = a * a;
+                    if (!isnan(a2)) ssq += a2;
+                }
+            }
+            for (int t = t1; t < nt; ++t) {
                 const double a = __ldg(var + base + t * st) - mean;
                 if (asy) asy[base + t * st] = a;
                 const double a2 = a * a;
                 if (!isnan(a2)) ssq += a2;
             }
+        }
         if (axisym) {
             const double m2 = mean * mean;
             axisym[(int64_t)iz * nr + ir] = m2 / (m2 + ssq * dtheta / 2 / 3.141592653589793);
@@ -255,42 +305,70 @@ k_sum_partials(const double *__restrict__ partial, int n, double *__restrict__ o
 //   NS=1 (axis A):      (prev + next) + cur*cw                                   / (2 + cw)   :165-166
 //   NS=2 (axes A, B):   (((A- + A+) + B-) + B+) + cur*cw                         / (4 + cw)   :195-197
 //   NS=3:               (((((0- + 0+) + 1-) + 1+) + 2+) + 2-) + cur*cw           / (6 + cw)   :224-228
+// Thread <-> i2 (contiguous), blockIdx.y <-> i1, blockIdx.z (+ a stride loop, four planes per trip with their loads
+// issued together) <-> i0: no integer division, no indexed local arrays (the first version decoded a flat index with
+// three 64-bit divisions and kept idx[] / n[] / str[] in local memory: 0.41-0.68 ms per pass on 80 x 1000 x 1000).
 template <int NS>
 __global__ void __launch_bounds__(256)
 k_smooth_pass(const double *__restrict__ v0, const double *__restrict__ cur, double *__restrict__ out, int n0,
-              int n1, int n2, int axA, int axB, double cw, double denom)
+              int n1, int n2, int axA, int axB, double cw, double denom, double rdenom)
 {
-    const int64_t total = (int64_t)n0 * n1 * n2;
-    const int n[3] = {n0, n1, n2};
-    const int64_t str[3] = {(int64_t)n1 * n2, (int64_t)n2, 1};
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total;
-         q += (int64_t)gridDim.x * blockDim.x) {
-        int idx[3];
-        idx[2] = (int)(q % n2);
-        const int64_t q2 = q / n2;
-        idx[1] = (int)(q2 % n1);
-        idx[0] = (int)(q2 / n1);
-        auto nb = [&](int ax, int d) {  // neighbour along `ax`, d = -1 / +1, frozen ghost outside
-            const int j = idx[ax] + d;
-            return (j < 0 || j >= n[ax]) ? __ldg(v0 + q) : __ldg(cur + q + d * str[ax]);
-        };
-        double s;
-        if (NS == 1) {
-            s = nb(axA, -1) + nb(axA, +1);
-        } else if (NS == 2) {
-            s = nb(axA, -1) + nb(axA, +1);
-            s = s + nb(axB, -1);
-            s = s + nb(axB, +1);
-        } else {
-            s = nb(0, -1) + nb(0, +1);
-            s = s + nb(1, -1);
-            s = s + nb(1, +1);
-            s = s + nb(2, +1);
-            s = s + nb(2, -1);
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i2 >= n2) return;
+    const int64_t s0 = (int64_t)n1 * n2, s1 = n2;
+    const mt::CDiv dd(denom, rdenom);
+    constexpr int U = 4;
+    for (int i1 = blockIdx.y; i1 < n1; i1 += gridDim.y)
+    for (int ib = blockIdx.z; ib < n0; ib += U * gridDim.z) {
+        double res[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i0 = ib + u * gridDim.z;
+            res[u] = 0.0;
+            if (i0 >= n0) continue;
+            const int64_t q = i0 * s0 + i1 * s1 + i2;
+            // neighbour along `ax`, d = -1 / +1; outside the array: the frozen ghost cell = v0 at the edge point
+            auto nb = [&](int ax, int d) {
+                const int pos = ax == 0 ? i0 : (ax == 1 ? i1 : i2), lim = ax == 0 ? n0 : (ax == 1 ? n1 : n2);
+                const int64_t str = ax == 0 ? s0 : (ax == 1 ? s1 : 1);
+                const int j = pos + d;
+                return (j < 0 || j >= lim) ? __ldg(v0 + q) : __ldg(cur + q + d * str);
+            };
+            double s;
+            if (NS == 1) {
+                s = nb(axA, -1) + nb(axA, +1);
+            } else if (NS == 2) {
+                s = nb(axA, -1) + nb(axA, +1);
+                s = s + nb(axB, -1);
+                s = s + nb(axB, +1);
+            } else {
+                s = nb(0, -1) + nb(0, +1);
+                s = s + nb(1, -1);
+                s = s + nb(1, +1);
+                s = s + nb(2, +1);
+                s = s + nb(2, -1);
+            }
+            res[u] = s + __ldg(cur + q) * cw;
         }
-        s = s + __ldg(cur + q) * cw;
-        out[q] = s / denom;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i0 = ib + u * gridDim.z;
+            if (i0 < n0) mt::st_stream(out + i0 * s0 + i1 * s1 + i2, dd(res[u]));
+        }
     }
+}
+
+// planes per thread = n0 / gridDim.z: MT_SMOOTH_PPT (default 80: a thread walks up to 80 planes, four per trip, so the
+// axis-0 neighbours of a trip are the planes the previous trip just touched; 4 / 8 / 16 / 40 measured no better)
+unsigned smooth_gz(int64_t n0)
+{
+    static const int ppt = [] {
+        const char *e = getenv("MT_SMOOTH_PPT");
+        const int v = e ? atoi(e) : 80;
+        return v < 1 ? 1 : v;
+    }();
+    const int64_t gz = (n0 + ppt - 1) / ppt;
+    return (unsigned)(gz < 1 ? 1 : (gz > 64 ? 64 : gz));
 }
 
 }  // namespace
@@ -375,15 +453,24 @@ int mt_smooth_pass(const double *v0, const double *cur, double *out, int64_t n0,
     MT_REQUIRE(naxes >= 1 && naxes <= 3, "mt_smooth_pass: naxes must be 1, 2 or 3");
     MT_REQUIRE(naxes == 3 || (ax_a >= 0 && ax_a <= 2), "mt_smooth_pass: bad axis");
     MT_REQUIRE(naxes != 2 || (ax_b >= 0 && ax_b <= 2 && ax_b != ax_a), "mt_smooth_pass: bad second axis");
-    const unsigned grid = mt::grid_for(n0 * n1 * n2, 256, 8);
+    // threads walk the last axis: an array whose last axis has one element and is not smoothed (smooth1d along the
+    // last axis of the caller's array arrives as (outer, n, 1)) is the same array with its axes shifted by one
+    if (n2 == 1 && naxes < 3 && ax_a != 2 && (naxes == 1 || ax_b != 2)) {
+        n2 = n1, n1 = n0, n0 = 1;
+        ax_a += 1, ax_b += 1;
+    }
+    const int threads = n2 >= 256 ? 256 : (n2 >= 128 ? 128 : (n2 >= 64 ? 64 : 32));
+    const dim3 grid((unsigned)((n2 + threads - 1) / threads), (unsigned)(n1 < 65535 ? n1 : 65535),
+                    (unsigned)smooth_gz(n0));
     cudaStream_t s = (cudaStream_t)stream;
     mt::ProfScope prof("k_smooth_pass", stream);
+    const double rd = 1.0 / denom;
     if (naxes == 1)
-        k_smooth_pass<1><<<grid, 256, 0, s>>>(v0, cur, out, (int)n0, (int)n1, (int)n2, ax_a, 0, center_weight, denom);
+        k_smooth_pass<1><<<grid, threads, 0, s>>>(v0, cur, out, (int)n0, (int)n1, (int)n2, ax_a, 0, center_weight, denom, rd);
     else if (naxes == 2)
-        k_smooth_pass<2><<<grid, 256, 0, s>>>(v0, cur, out, (int)n0, (int)n1, (int)n2, ax_a, ax_b, center_weight, denom);
+        k_smooth_pass<2><<<grid, threads, 0, s>>>(v0, cur, out, (int)n0, (int)n1, (int)n2, ax_a, ax_b, center_weight, denom, rd);
     else
-        k_smooth_pass<3><<<grid, 256, 0, s>>>(v0, cur, out, (int)n0, (int)n1, (int)n2, 0, 1, center_weight, denom);
+        k_smooth_pass<3><<<grid, threads, 0, s>>>(v0, cur, out, (int)n0, (int)n1, (int)n2, 0, 1, center_weight, denom, rd);
     MT_LAUNCH_CHECK();
     return MT_OK;
 }
