@@ -9,8 +9,8 @@
 //   * one producer thread streams the planes of the tile -- one 3-D TMA box {36, TR + 2, 1} per
 //     differentiated field (u|vr, v|vt, w, theta_rho, p), i.e. the tile with its one-point halo (two
 //     columns on the contiguous axis: a TMA box must start 16-byte aligned), and the {32, TR, 1} tile of
-//     rho -- through a ring of NS = 4 plane stages guarded by full / empty mbarriers.  While plane k is
-//     worked on, plane k + 1 has landed and plane k + 2 is in flight; parts of a box outside the array
+//     rho -- through a ring of NS = 5 plane stages guarded by full / empty mbarriers.  While plane k is
+//     worked on, plane k + 1 has landed and planes k + 2, k + 3 are in flight; parts of a box outside the array
 //     are zero-filled by the TMA unit and never used;
 //   * TR consumer warps (one point per thread and plane) take all 3 x 3 x 3 stencil operands from shared
 //     memory: the march-axis difference from the stages of planes k - 1 / k + 1, the two in-plane
@@ -42,9 +42,14 @@ constexpr int TC = 32;             // tile points along the contiguous axis = la
 constexpr int HX = 2, HY = 1;      // halo: 2 columns (16-byte aligned box start), 1 row
 
 // NS: plane stages of the ring.  Three are in use by the stencil (k - 1, k, k + 1); the others are the
-// prefetch distance: with NS = 4 a plane is requested ONE step before it is needed and consumer warps
-// spent 28 % of their time waiting for it (ncu, profiles/experiments_r02.md); NS = 6 requests it three
-// steps ahead.
+// prefetch distance.  Tile height, ring depth and resident CTAs were swept together at the end of round 2
+// (profiles/experiments_r02.md section 10; Cartesian stencil on 80 x 1000 x 1000 / S5, ms):
+//   8 rows, 2 CTAs / SM, NS = 4 (until then) 2.13 / 8.73     8 rows, 2 CTAs, NS = 5  1.93 / 8.00     NS = 6  2.29 / 9.31
+//   4 rows, 4 CTAs / SM, NS = 4              1.94 / 7.98     4 rows, 4 CTAs, NS = 5  1.86 / 7.5-7.6  NS = 6  2.15 / 8.11
+//   4 rows, 5 CTAs (72 registers) 2.02 / 7.90   2 rows, 8 CTAs 2.28 / 8.27   6 rows, 3 CTAs 1.91 / 7.72   NS = 3  2.92 / 11.3
+// Four small CTAs per SM are four independent pipelines (their waits for a landing plane fall at different
+// times) and a fifth stage requests a plane two steps ahead; deeper rings cost a resident CTA.  The cylindrical
+// kernel (FP64 / issue bound) does not care: 0.375-0.380 ms in every shape.
 // MSH (0, 16 or 24): the tile's columns are SHIFTED per row so that every warp's 32 doubles start on a
 // 256-BYTE boundary of the output arrays -- on B200 a warp-wide store that straddles a 256-byte block costs
 // ~20 % of the write bandwidth (scratch/stream_probe.cu: 12 write streams run at 6.0 TB/s aligned, 4.7 TB/s
@@ -513,7 +518,7 @@ int launch(const Maps &M, const KP &kp, unsigned grid, cudaStream_t s)
     auto kern = k_stencil_tma<LAYOUT, CYL, FULL, TR, NS, MB, MSH>;
     constexpr size_t smem = G::SMEM;
     MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two CTAs of the 8-row shape share an SM: ask for the full shared-memory carve-out
+    // several CTAs share an SM: ask for the full shared-memory carve-out
     MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<grid, G::NTHR, smem, s>>>(M, kp);
     MT_LAUNCH_CHECK();
@@ -549,7 +554,13 @@ int stencil_tma(const mt_grid_t *g, const GridP &gp, const StageBIn &bi, const d
         if ((uintptr_t)ptr % 16 != 0) return MT_ENOSUP;
     if (!A || !B) return MT_ENOSUP;
 
-    constexpr int TRv = 8;   // 16-row tiles (one 544-thread CTA per SM) measured 5-8 % slower
+#ifndef MT_DIAG_TR
+#define MT_DIAG_TR 4
+#endif
+#ifndef MT_DIAG_MB
+#define MT_DIAG_MB 4
+#endif
+    constexpr int TRv = MT_DIAG_TR;   // rows per tile = consumer warps per CTA (see the sweep at the top of the file)
     KP kp;
     kp.n0 = (int)n0, kp.n1 = (int)n1, kp.n2 = (int)n2;
     // march range: the owned levels of a ZTR level shard; every theta plane of a TRZ array
@@ -591,8 +602,9 @@ int stencil_tma(const mt_grid_t *g, const GridP &gp, const StageBIn &bi, const d
 
     // persistent CTAs; the march axis is cut into segments only as far as that balances the SMs: pick the
     // segment count that minimises  rounds x (planes per segment + 2 ramp planes)
-    // two CTAs (2 x 8 consumer warps, 96 registers) per SM: three or four at 72 / 56 registers measured slower
-    const int ctas_per_sm = 2;
+    // MT_DIAG_MB CTAs of MT_DIAG_TR consumer warps (96 registers) per SM; where the shifted boxes are wide,
+    // shared memory admits one fewer
+    const int ctas_per_sm = MT_DIAG_MB;
     const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
     const int64_t ntiles = (int64_t)kp.tiles_r * kp.tiles_c;
     int best_nseg = 1;
@@ -629,7 +641,10 @@ int stencil_tma(const mt_grid_t *g, const GridP &gp, const StageBIn &bi, const d
         return MT_ECUDA;
     }
     ProfScope prof(CYL ? "k_stencil_tma_cyl" : "k_stencil_tma_car", (mt_stream_t)s);
-#define DT_L(LAYOUT_, FULL_, MSH_) launch<LAYOUT_, CYL, FULL_, 8, 4, 2, MSH_>(M, kp, grid, s)
+#ifndef MT_DIAG_NS
+#define MT_DIAG_NS 5
+#endif
+#define DT_L(LAYOUT_, FULL_, MSH_) launch<LAYOUT_, CYL, FULL_, MT_DIAG_TR, MT_DIAG_NS, MT_DIAG_MB, MSH_>(M, kp, grid, s)
 #define DT_ZTR(FULL_)                                                                           \
     (msh == 0 ? DT_L(MT_LAYOUT_ZTR, FULL_, 0) : msh == 16 ? DT_L(MT_LAYOUT_ZTR, FULL_, 16) : DT_L(MT_LAYOUT_ZTR, FULL_, 24))
     if (ztr) return full ? DT_ZTR(true) : DT_ZTR(false);
