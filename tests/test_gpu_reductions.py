@@ -148,3 +148,32 @@ def test_smooth3d_larger_against_oracle():
     assert_same(car.smooth3d_q, co.smooth3d(np.asarray(car.q), 3, 5), "smooth3d 20x70x130")
     car.smooth2d("q", passes=7)
     assert_same(car.smooth2d_q, co.smooth2d(np.asarray(car.q), (1, 2), 2, 7), "smooth2d 20x70x130")
+
+
+def test_smoothers_degenerate_and_long_axes_against_oracle():
+    """Shapes that exercise the launch geometry of mt_smooth_pass (csrc/reduce.cu): a 1-D array and the last axis of
+    a 2-D one arrive as (outer, n, 1) and are re-read with their axes shifted by one; a middle axis longer than
+    the 65535 blocks of grid.y is walked by a stride loop; fewer planes than one trip of four; 81 planes (a
+    second, partial trip of the plane loop)."""
+    from meteotools_b200.grids import cartesian_grid
+    rng = np.random.default_rng(21)
+    car = cartesian_grid(dict(RED_CAR, Nx=40, Ny=30, Nz=10))
+    car.a1 = rng.standard_normal(70001)                       # 1-D, longer than 65535
+    car.smooth1d("a1", axis=0, center_weight=2, passes=3)
+    assert_same(car.smooth1d_a1, co.smooth1d(np.asarray(car.a1), 0, 2, 3), "smooth1d of a long 1-D array")
+    car.a2 = rng.standard_normal((70001, 3))                   # smoothed along a first axis longer than 65535
+    car.a2[5, 1] = np.nan
+    for ax in (0, 1):
+        car.smooth1d("a2", axis=ax, center_weight=1.5, passes=2)
+        assert_same(car.smooth1d_a2, co.smooth1d(np.asarray(car.a2), ax, 1.5, 2), f"smooth1d (70001, 3) axis {ax}")
+    car.a3 = rng.standard_normal((81, 7, 37))                  # 81 planes, ragged rows
+    for ax in (0, 1, 2):
+        car.smooth1d("a3", axis=ax, passes=2)
+        assert_same(car.smooth1d_a3, co.smooth1d(np.asarray(car.a3), ax, 2, 2), f"smooth1d (81, 7, 37) axis {ax}")
+    car.smooth2d("a3", axis=(0, 2), center_weight=2, passes=3)
+    assert_same(car.smooth2d_a3, co.smooth2d(np.asarray(car.a3), (0, 2), 2, 3), "smooth2d (81, 7, 37) axes (0, 2)")
+    car.smooth3d("a3", center_weight=1, passes=2)
+    assert_same(car.smooth3d_a3, co.smooth3d(np.asarray(car.a3), 1, 2), "smooth3d (81, 7, 37)")
+    car.a4 = rng.standard_normal((2, 5, 9))                    # fewer planes than one trip
+    car.smooth3d("a4", passes=4)
+    assert_same(car.smooth3d_a4, co.smooth3d(np.asarray(car.a4), 2, 4), "smooth3d (2, 5, 9)")
