@@ -139,7 +139,13 @@ __device__ __forceinline__ double dmarch(const Roll &r, int i, int n, bool first
 //                neighbour loads of a point together (the generic body issues them in small groups
 //                between run-time branches and pays the L2 latency once per group).
 template <int LAYOUT, bool CYL, bool SHELL, bool FULL>
-__global__ void __launch_bounds__(128, SHELL ? 6 : MT_STAGEB_MINB)
+// the shell launch (two end planes: one thread per point, ~35 dependent-free loads) is latency bound: twelve CTAs of
+// 40 registers per SM beat six of 80 although a few values spill (S5: 0.56 -> 0.38 ms; 4 / 6 / 8 / 10 / 12 / 16 CTAs on
+// 80 x 1000 x 1000: 0.158 / 0.140 / 0.129 / 0.111 / 0.101 / 0.107 ms)
+#ifndef MT_SHELL_MINB
+#define MT_SHELL_MINB 12
+#endif
+__global__ void __launch_bounds__(128, SHELL ? MT_SHELL_MINB : MT_STAGEB_MINB)
 k_stage_b(Lay<LAYOUT> L, GridP g, StageBIn in, StageBOut o, int seg_len)
 {
     constexpr bool ZTR = LAYOUT == MT_LAYOUT_ZTR;
