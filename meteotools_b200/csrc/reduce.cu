@@ -305,11 +305,18 @@ k_sum_partials(const double *__restrict__ partial, int n, double *__restrict__ o
 //   NS=1 (axis A):      (prev + next) + cur*cw                                   / (2 + cw)   :165-166
 //   NS=2 (axes A, B):   (((A- + A+) + B-) + B+) + cur*cw                         / (4 + cw)   :195-197
 //   NS=3:               (((((0- + 0+) + 1-) + 1+) + 2+) + 2-) + cur*cw           / (6 + cw)   :224-228
-// Thread <-> i2 (contiguous), blockIdx.y <-> i1, blockIdx.z (+ a stride loop, four planes per trip with their loads
-// issued together) <-> i0: no integer division, no indexed local arrays (the first version decoded a flat index with
+// Thread <-> i2 (contiguous), blockIdx.y <-> i1, blockIdx.z (+ a stride loop of MT_SMOOTH_U planes per trip) <-> i0.
+// One plane per trip at eight resident CTAs of 32 registers measured best (U = 1 / 2 / 4 / 8: 0.61 / 0.52 / 0.52 / 0.41 of
+// the measured peak on the contiguous axis of 80 x 1000 x 1000: occupancy beats loads in flight here): no integer division, no indexed local arrays (the first version decoded a flat index with
 // three 64-bit divisions and kept idx[] / n[] / str[] in local memory: 0.41-0.68 ms per pass on 80 x 1000 x 1000).
+#ifndef MT_SMOOTH_U
+#define MT_SMOOTH_U 1
+#endif
+#ifndef MT_SMOOTH_MINB
+#define MT_SMOOTH_MINB 8
+#endif
 template <int NS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MT_SMOOTH_MINB)
 k_smooth_pass(const double *__restrict__ v0, const double *__restrict__ cur, double *__restrict__ out, int n0,
               int n1, int n2, int axA, int axB, double cw, double denom, double rdenom)
 {
@@ -317,7 +324,7 @@ k_smooth_pass(const double *__restrict__ v0, const double *__restrict__ cur, dou
     if (i2 >= n2) return;
     const int64_t s0 = (int64_t)n1 * n2, s1 = n2;
     const mt::CDiv dd(denom, rdenom);
-    constexpr int U = 4;
+    constexpr int U = MT_SMOOTH_U;
     for (int i1 = blockIdx.y; i1 < n1; i1 += gridDim.y)
     for (int ib = blockIdx.z; ib < n0; ib += U * gridDim.z) {
         double res[U];
