@@ -38,9 +38,9 @@ k_axis_wsum(const double *__restrict__ var, int64_t n_f, int64_t n_s, int64_t n_
         const int64_t s = q / n_f, f = q - s * n_f;
         const double *p = var + f * s_f + s * s_s;
         double acc = 0.0, wsum = 0.0;
-        // eight terms are loaded before they are added IN ORDER: the sum is sequential by contract (NumPy's order
+        // 32 terms are loaded before they are added IN ORDER (8 / 16 / 32: 0.039 / 0.039 / 0.034 ms on the S3 grid): the sum is sequential by contract (NumPy's order
         // along a strided axis), but its loads need not wait for each other
-        constexpr int U = 8;
+        constexpr int U = 32;
         int64_t k = 0;
         for (; k + U <= n_k; k += U) {
             double wk[U], t[U];
@@ -188,7 +188,7 @@ k_azimuthal_stats(const double *__restrict__ var, int nz, int nt, int nr, int64_
         const int64_t base = iz * sz + ir * sr;
         double s = 0.0;
         int cnt = 0;
-        constexpr int U = 8;   // loads in flight; the additions stay in order
+        constexpr int U = 16;   // loads in flight; the additions stay in order (8 / 16 / 32: 0.064 / 0.049 / 0.050 ms, S3 grid)
         int t0 = 0;
         for (; t0 + U <= nt; t0 += U) {
             double v[U];
